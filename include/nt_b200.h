@@ -1,0 +1,94 @@
+/*
+ * nt_b200.h — C-ABI of the B200-native resident-decode kernels (libnt_b200.so).
+ *
+ * Drop-in boundary: every entry point below replaces one launcher of the reference's
+ * kernel interface  /root/reference/src/cuda/kernels.h:10-74  (C++ free functions in
+ * namespace nt::cuda) or one of its extern "C" memory helpers
+ * /root/reference/src/core/device.h:79-88.  Same argument order, meaning, units and
+ * (absence of) error reporting as the reference; `dtype` carries the numeric value of
+ * nt::DType (reference src/core/types.h:24-35: F32 0, F16 1, Q8_0 2, Q4_0 3, Q4_K_M 4,
+ * Q6_K 5, Q5_K 6); `stream` is a cudaStream_t passed as void*.  All pointers are DEVICE
+ * pointers owned by the caller; launches are asynchronous on `stream`.  The library also
+ * exports the original mangled names (nt::cuda::launch_*) so the unmodified reference host
+ * code links against it — see INTEGRATION.md.
+ *
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef NT_B200_H
+#define NT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- kernels.h:14-19  launch_rmsnorm / launch_rmsnorm_f16 ---- */
+void nt_b200_rmsnorm(float* output, const float* input, const float* weight,
+                     int batch_size, int hidden_size, float eps, void* stream);
+void nt_b200_rmsnorm_f16(void* output, const float* input, const float* weight,
+                         int batch_size, int hidden_size, float eps, void* stream);
+/* ---- kernels.h:22-25  launch_rope ---- */
+void nt_b200_rope(float* q, float* k, const int* positions, int batch_size, int seq_len,
+                  int n_heads, int n_kv_heads, int head_dim, float theta_base,
+                  float freq_scale, int interleaved, void* stream);
+/* ---- kernels.h:28-31  launch_softmax / launch_masked_softmax ---- */
+void nt_b200_softmax(float* output, const float* input, int rows, int cols, void* stream);
+void nt_b200_masked_softmax(float* output, const float* input, const unsigned char* mask,
+                            int rows, int cols, void* stream);
+/* ---- kernels.h:34-36  launch_gemv : y[out] = W[out,in] . x, W in GGUF block layout ---- */
+void nt_b200_gemv(float* y, const void* W, const float* x, int out_features,
+                  int in_features, int weight_dtype, void* stream);
+/* ---- kernels.h:39-41  launch_gemv_add : y += W . x (F16 only, like the reference) ---- */
+void nt_b200_gemv_add(float* y, const void* W, const float* x, int out_features,
+                      int in_features, int weight_dtype, void* stream);
+/* ---- kernels.h:42-44  launch_gemm_f32 : C[M,N] = A[M,K] . B[N,K]^T ---- */
+void nt_b200_gemm_f32(float* C, const float* A, const float* B, int M, int N, int K, void* stream);
+/* ---- kernels.h:45-48  launch_silu_mul / launch_add_bias ---- */
+void nt_b200_silu_mul(float* output, const float* gate, const float* up, int size, void* stream);
+void nt_b200_add_bias(float* y, const float* bias, int size, void* stream);
+/* ---- kernels.h:51-63  attention over the F16 KV cache [max_seq, n_kv_heads, head_dim] ---- */
+void nt_b200_attention_decode(float* output, const float* q, const void* k_cache,
+                              const void* v_cache, int seq_len, int n_heads, int n_kv_heads,
+                              int head_dim, int max_seq, float scale, void* stream);
+void nt_b200_attention_prefill(float* output, const float* Q, const void* k_cache,
+                               const void* v_cache, int seq_len, int start_pos, int n_heads,
+                               int n_kv_heads, int head_dim, int max_seq, float scale, void* stream);
+void nt_b200_copy_to_kv_cache(void* k_cache, void* v_cache, const float* k, const float* v,
+                              int seq_len, int n_kv_heads, int head_dim, int start_pos,
+                              int max_seq, void* stream);
+/* ---- kernels.h:66-71  element-wise ops and cosine similarity ---- */
+void nt_b200_add(float* out, const float* a, const float* b, int size, void* stream);
+void nt_b200_add_inplace(float* a, const float* b, int size, void* stream);
+void nt_b200_copy(float* dst, const float* src, int size, void* stream);
+void nt_b200_cosine_similarity(float* result, const float* a, const float* b, int size, void* stream);
+
+/* ---- core/device.h:79-88  memory helpers (same names as the reference exports) ---- */
+void* nt_cuda_malloc(size_t size);
+void  nt_cuda_free(void* ptr);
+void  nt_cuda_memcpy_h2d(void* dst, const void* src, size_t size);
+void  nt_cuda_memcpy_d2h(void* dst, const void* src, size_t size);
+void  nt_cuda_memcpy_d2d(void* dst, const void* src, size_t size);
+void  nt_cuda_memset(void* ptr, int value, size_t size);
+void* nt_cuda_malloc_host(size_t size);
+void  nt_cuda_free_host(void* ptr);
+
+/* ---- additions (no reference counterpart): fused-path building blocks and introspection ---- */
+/* bytes of the block-scaled int8x3 activation buffer for K elements */
+size_t nt_b200_xq_bytes(int K);
+void   nt_b200_quantize_x(const float* x, void* xq, int K, void* stream);
+/* fused K-quant GEMV over n_mat (<=3) matrices sharing one quantised activation vector.
+ * epilogue: 0 store, 1 y += W.x, 2 y0 = silu(W0.x) * (W1.x) */
+int    nt_b200_gemv_fused(int n_mat, float* const* y, const void* const* W, const int* out_features,
+                          const int* dtypes, int in_features, const void* xq, int epilogue, void* stream);
+void   nt_b200_embed_rows(float* out, const void* table, int dtype, const int* tokens_dev,
+                          int n_tokens, int hidden, void* stream);
+unsigned long long nt_b200_launch_count(void);   /* kernels launched by this library so far */
+int    nt_b200_stream_sync(void* stream);        /* cudaStreamSynchronize; returns cudaError_t */
+const char* nt_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NT_B200_H */

@@ -1,0 +1,321 @@
+// attention.cu — GQA KV-cache attention for decode and prefill on sm_100a.
+//
+// Replaces reference kernels K16 (attention_decode_generic_kernel, src/cuda/attention.cu:108-202) and
+// K18 (attention_prefill_kernel, :216-311).  Same math (F32 q, F16 K/V, scores * scale, softmax with the
+// fast-math exp, P.V in F32) with a different work split:
+//   * one CTA serves GC query heads that share a KV head, so K/V rows are fetched once per GQA group
+//     instead of once per head (the reference re-reads them n_heads/n_kv_heads times);
+//   * decode is split along the context (flash-decoding): grid = head-groups x splits so 148 SMs are
+//     busy at ctx 2048 where the reference launches only n_heads CTAs; partial (max, sum, P.V) are merged
+//     by a small combine kernel;
+//   * K rows are read coalesced (one row per warp step, DPL dims per lane) and the GC partial dot
+//     products are reduced with a transpose-reduce (GC-1 + log2(32/GC) shuffles instead of 5*GC).
+// Compiled with --use_fast_math (expf -> ex2.approx path, as the reference build).
+#include "kernels_internal.h"
+#include <cuda_fp16.h>
+#include <cfloat>
+#include <mutex>
+
+namespace nt { namespace b200 {
+
+namespace {
+
+constexpr int AW = 8;                    // warps per CTA
+constexpr int MAX_SPLITS = 64;
+
+template <int N> struct HalfVec;         // N halfs loaded as one vector
+template <> struct HalfVec<2> { using T = uint32_t; };
+template <> struct HalfVec<4> { using T = uint2; };
+template <> struct HalfVec<8> { using T = uint4; };
+
+template <int DPL>
+__device__ __forceinline__ void load_row(const __half* p, float (&f)[DPL]) {
+    typename HalfVec<DPL>::T raw = __ldg(reinterpret_cast<const typename HalfVec<DPL>::T*>(p));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < DPL / 2; i++) { float2 t = __half22float2(h2[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+// Reduce GC per-lane partial sums across the warp. On return lane L holds (in v[0]) the full sum of
+// value index (L / (32 / GC)) ... valid in every lane of that group.
+template <int GC>
+__device__ __forceinline__ float transpose_reduce(float (&v)[GC], int lane) {
+    // exchange phase: halve the number of live values per step
+#pragma unroll
+    for (int n = GC, off = 16; n > 1; n >>= 1, off >>= 1) {
+        const bool upper = lane & off;
+#pragma unroll
+        for (int i = 0; i < n / 2; i++) {
+            float send = upper ? v[i] : v[i + n / 2];
+            float keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, off);
+        }
+    }
+    // plain butterfly over the remaining lanes of the group
+    float r = v[0];
+#pragma unroll
+    for (int off = 16 / GC; off > 0; off >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, off);
+    return r;
+}
+
+// One CTA: GC query heads of one KV head, keys [k_begin, k_end).
+// q_base: first of the GC heads' query vectors (contiguous [GC][hd]); out likewise.
+// If part_* != nullptr writes unnormalised partials, else the normalised output.
+template <int DPL, int GC>
+__device__ void attend_group(float* __restrict__ out, const float* __restrict__ q_base, const __half* __restrict__ kc,
+                             const __half* __restrict__ vc, int kv_head, int n_kv, int k_begin, int k_end, float scale,
+                             float* __restrict__ part_o, float* __restrict__ part_ml, float* smem) {
+    constexpr int HD = DPL * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_keys = k_end - k_begin;
+    float* sc = smem;                                   // [GC][n_keys]
+    float* red = smem + (size_t)GC * n_keys;            // [AW][GC][HD]
+    __shared__ float s_max[GC], s_sum[GC];
+    const size_t row_stride = (size_t)n_kv * HD;
+    const __half* kbase = kc + (size_t)kv_head * HD + (size_t)lane * DPL;
+    const __half* vbase = vc + (size_t)kv_head * HD + (size_t)lane * DPL;
+
+    float qr[GC][DPL];
+#pragma unroll
+    for (int g = 0; g < GC; g++)
+#pragma unroll
+        for (int i = 0; i < DPL; i++) qr[g][i] = q_base[(size_t)g * HD + lane * DPL + i];
+
+    // ---- phase 1: scores ----
+    for (int p = warp; p < n_keys; p += AW) {
+        float kf[DPL];
+        load_row<DPL>(kbase + (size_t)(k_begin + p) * row_stride, kf);
+        float part[GC];
+#pragma unroll
+        for (int g = 0; g < GC; g++) {
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < DPL; i++) a = fmaf(qr[g][i], kf[i], a);
+            part[g] = a;
+        }
+        float tot = transpose_reduce<GC>(part, lane);
+        if ((lane & (32 / GC - 1)) == 0) sc[(size_t)(lane / (32 / GC)) * n_keys + p] = tot * scale;
+    }
+    __syncthreads();
+    // ---- phase 2: per-head max / exp / sum (warp g <-> head g) ----
+    for (int g = warp; g < GC; g += AW) {
+        float* s = sc + (size_t)g * n_keys;
+        float mx = -FLT_MAX;
+        for (int p = lane; p < n_keys; p += 32) mx = fmaxf(mx, s[p]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        float sum = 0.f;
+        for (int p = lane; p < n_keys; p += 32) { float e = expf(s[p] - mx); s[p] = e; sum += e; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        if (lane == 0) { s_max[g] = mx; s_sum[g] = sum; }
+    }
+    __syncthreads();
+    // ---- phase 3: P.V (warp <-> keys, lane <-> DPL dims) ----
+    float acc[GC][DPL];
+#pragma unroll
+    for (int g = 0; g < GC; g++)
+#pragma unroll
+        for (int i = 0; i < DPL; i++) acc[g][i] = 0.f;
+    for (int p = warp; p < n_keys; p += AW) {
+        float vf[DPL];
+        load_row<DPL>(vbase + (size_t)(k_begin + p) * row_stride, vf);
+#pragma unroll
+        for (int g = 0; g < GC; g++) {
+            float w = sc[(size_t)g * n_keys + p];
+#pragma unroll
+            for (int i = 0; i < DPL; i++) acc[g][i] = fmaf(w, vf[i], acc[g][i]);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < GC; g++)
+#pragma unroll
+        for (int i = 0; i < DPL; i++) red[((size_t)warp * GC + g) * HD + lane * DPL + i] = acc[g][i];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < GC * HD; idx += AW * 32) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < AW; w++) t += red[(size_t)w * GC * HD + idx];
+        const int g = idx / HD, d = idx - g * HD;
+        if (part_o) {
+            part_o[(size_t)g * HD + d] = t;             // caller strides heads by HD inside its split slot
+        } else {
+            float l = s_sum[g];
+            out[(size_t)g * HD + d] = t * ((l > 0.f) ? 1.0f / l : 0.f);
+        }
+    }
+    if (part_ml && threadIdx.x < GC) {
+        part_ml[2 * threadIdx.x] = s_max[threadIdx.x];
+        part_ml[2 * threadIdx.x + 1] = s_sum[threadIdx.x];
+    }
+}
+
+// Scratch layout for split decode: [head][split][HD] floats then [head][split][2] (max, sum).
+template <int DPL, int GC>
+__global__ void __launch_bounds__(AW * 32) decode_kernel(float* __restrict__ out, const float* __restrict__ q,
+                                                         const __half* __restrict__ kc, const __half* __restrict__ vc,
+                                                         int seq_len, int n_heads, int n_kv, float scale, int n_splits,
+                                                         int split_len, float* __restrict__ scratch) {
+    constexpr int HD = DPL * 32;
+    extern __shared__ float smem_dyn[];
+    const int head0 = blockIdx.x * GC, split = blockIdx.y;
+    const int kv_head = head0 / (n_heads / n_kv);
+    const int k_begin = split * split_len, k_end = min(seq_len, k_begin + split_len);
+    if (k_begin >= k_end) return;
+    if (n_splits == 1) {
+        attend_group<DPL, GC>(out + (size_t)head0 * HD, q + (size_t)head0 * HD, kc, vc, kv_head, n_kv, k_begin, k_end, scale,
+                              nullptr, nullptr, smem_dyn);
+    } else {
+        // partials for head (head0+g) live at scratch[((head0+g) * n_splits + split) * HD]; attend_group strides
+        // heads by HD, so hand it a staging area in shared memory and scatter afterwards.
+        float* stage = smem_dyn + (size_t)GC * (k_end - k_begin) + (size_t)AW * GC * HD;   // [GC][HD] + [GC][2]
+        attend_group<DPL, GC>(nullptr, q + (size_t)head0 * HD, kc, vc, kv_head, n_kv, k_begin, k_end, scale, stage,
+                              stage + GC * HD, smem_dyn);
+        __syncthreads();
+        float* ml = scratch + (size_t)n_heads * n_splits * HD;
+        for (int idx = threadIdx.x; idx < GC * HD; idx += AW * 32) {
+            const int g = idx / HD, d = idx - g * HD;
+            scratch[((size_t)(head0 + g) * n_splits + split) * HD + d] = stage[idx];
+        }
+        if (threadIdx.x < 2 * GC) {
+            const int g = threadIdx.x >> 1;
+            ml[((size_t)(head0 + g) * n_splits + split) * 2 + (threadIdx.x & 1)] = stage[GC * HD + threadIdx.x];
+        }
+    }
+}
+
+// Merge split partials: out[h] = sum_i e^{m_i - m} o_i / sum_i e^{m_i - m} l_i
+__global__ void decode_combine_kernel(float* __restrict__ out, const float* __restrict__ scratch, int n_heads, int hd,
+                                      int n_splits, int seq_len, int split_len) {
+    const int h = blockIdx.x;
+    const float* ml = scratch + (size_t)n_heads * n_splits * hd + (size_t)h * n_splits * 2;
+    const int used = (seq_len + split_len - 1) / split_len;
+    float m = -FLT_MAX;
+    for (int i = 0; i < used; i++) m = fmaxf(m, ml[2 * i]);
+    float l = 0.f;
+    for (int i = 0; i < used; i++) l += ml[2 * i + 1] * expf(ml[2 * i] - m);
+    const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+    for (int d = threadIdx.x; d < hd; d += blockDim.x) {
+        float o = 0.f;
+        for (int i = 0; i < used; i++) o += scratch[((size_t)h * n_splits + i) * hd + d] * expf(ml[2 * i] - m);
+        out[(size_t)h * hd + d] = o * inv;
+    }
+}
+
+template <int DPL, int GC>
+__global__ void __launch_bounds__(AW * 32) prefill_kernel(float* __restrict__ out, const float* __restrict__ Q,
+                                                          const __half* __restrict__ kc, const __half* __restrict__ vc,
+                                                          int start_pos, int n_heads, int n_kv, float scale) {
+    constexpr int HD = DPL * 32;
+    extern __shared__ float smem_dyn[];
+    const int head0 = blockIdx.x * GC, qi = blockIdx.y;
+    const int kv_head = head0 / (n_heads / n_kv);
+    const size_t qoff = ((size_t)qi * n_heads + head0) * HD;
+    attend_group<DPL, GC>(out + qoff, Q + qoff, kc, vc, kv_head, n_kv, 0, start_pos + qi + 1, scale, nullptr, nullptr, smem_dyn);
+}
+
+float* g_scratch = nullptr;
+size_t g_scratch_floats = 0;
+std::mutex g_scratch_mu;
+float* attn_scratch(size_t floats) {
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    if (floats > g_scratch_floats) {
+        if (g_scratch) { cudaDeviceSynchronize(); cudaFree(g_scratch); }
+        size_t want = floats < (1u << 20) ? (1u << 20) : floats;
+        NT_CUDA_CHECK(cudaMalloc(&g_scratch, want * sizeof(float)));
+        g_scratch_floats = want;
+    }
+    return g_scratch;
+}
+
+int pick_gc(int group) { return group % 8 == 0 ? 8 : group % 4 == 0 ? 4 : group % 2 == 0 ? 2 : 1; }
+
+template <int DPL, int GC>
+void launch_decode(float* out, const float* q, const __half* kc, const __half* vc, int seq_len, int n_heads, int n_kv,
+                   float scale, cudaStream_t s) {
+    constexpr int HD = DPL * 32;
+    // split so that head-groups x splits covers the chip, with at least 32 keys per split
+    int groups = n_heads / GC;
+    int n_splits = 1;
+    if (seq_len > 64) {
+        n_splits = (2 * 148 + groups - 1) / groups;
+        int max_by_len = (seq_len + 31) / 32;
+        if (n_splits > max_by_len) n_splits = max_by_len;
+        if (n_splits > MAX_SPLITS) n_splits = MAX_SPLITS;
+        if (n_splits < 1) n_splits = 1;
+    }
+    int split_len = (seq_len + n_splits - 1) / n_splits;
+    n_splits = (seq_len + split_len - 1) / split_len;
+    size_t smem = ((size_t)GC * split_len + (size_t)AW * GC * HD + (size_t)GC * HD + 2 * GC) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+        NT_CUDA_CHECK(cudaFuncSetAttribute(decode_kernel<DPL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = 227 * 1024;
+    }
+    NT_CHECK(smem <= 227 * 1024, "attention_decode: context slice does not fit shared memory");
+    float* scratch = nullptr;
+    if (n_splits > 1) scratch = attn_scratch((size_t)n_heads * n_splits * (HD + 2));
+    decode_kernel<DPL, GC><<<dim3(groups, n_splits), AW * 32, smem, s>>>(out, q, kc, vc, seq_len, n_heads, n_kv, scale,
+                                                                        n_splits, split_len, scratch);
+    count_launch();
+    if (n_splits > 1) {
+        decode_combine_kernel<<<n_heads, 128, 0, s>>>(out, scratch, n_heads, HD, n_splits, seq_len, split_len);
+        count_launch();
+    }
+}
+
+template <int DPL, int GC>
+void launch_prefill(float* out, const float* Q, const __half* kc, const __half* vc, int seq_len, int start_pos, int n_heads,
+                    int n_kv, float scale, cudaStream_t s) {
+    constexpr int HD = DPL * 32;
+    size_t smem = ((size_t)GC * (start_pos + seq_len) + (size_t)AW * GC * HD) * sizeof(float);
+    NT_CHECK(smem <= 227 * 1024, "attention_prefill: context does not fit shared memory");
+    static bool configured = false;
+    if (!configured) {
+        NT_CUDA_CHECK(cudaFuncSetAttribute(prefill_kernel<DPL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    prefill_kernel<DPL, GC><<<dim3(n_heads / GC, seq_len), AW * 32, smem, s>>>(out, Q, kc, vc, start_pos, n_heads, n_kv, scale);
+    count_launch();
+}
+
+#define NT_DISPATCH_ATTN(FN, ...)                                                         \
+    do {                                                                                  \
+        const int gc_ = pick_gc(n_heads / n_kv);                                          \
+        const int dpl_ = hd / 32;                                                         \
+        NT_CHECK(hd % 32 == 0 && (dpl_ == 2 || dpl_ == 4 || dpl_ == 8),                  \
+                 "attention: head_dim must be 64, 128 or 256");                           \
+        NT_CHECK(n_kv > 0 && n_heads % n_kv == 0, "attention: n_heads % n_kv_heads != 0"); \
+        if (dpl_ == 4) {                                                                  \
+            if (gc_ == 8) FN<4, 8>(__VA_ARGS__); else if (gc_ == 4) FN<4, 4>(__VA_ARGS__); \
+            else if (gc_ == 2) FN<4, 2>(__VA_ARGS__); else FN<4, 1>(__VA_ARGS__);         \
+        } else if (dpl_ == 2) {                                                           \
+            if (gc_ == 8) FN<2, 8>(__VA_ARGS__); else if (gc_ == 4) FN<2, 4>(__VA_ARGS__); \
+            else if (gc_ == 2) FN<2, 2>(__VA_ARGS__); else FN<2, 1>(__VA_ARGS__);         \
+        } else {                                                                          \
+            if (gc_ == 8) FN<8, 8>(__VA_ARGS__); else if (gc_ == 4) FN<8, 4>(__VA_ARGS__); \
+            else if (gc_ == 2) FN<8, 2>(__VA_ARGS__); else FN<8, 1>(__VA_ARGS__);         \
+        }                                                                                 \
+    } while (0)
+
+}  // namespace
+
+void attention_decode(float* out, const float* q, const void* kc, const void* vc, int seq_len, int n_heads, int n_kv,
+                      int hd, int max_seq, float scale, cudaStream_t s) {
+    (void)max_seq;
+    if (seq_len <= 0 || n_heads <= 0) return;
+    const __half* k = static_cast<const __half*>(kc);
+    const __half* v = static_cast<const __half*>(vc);
+    NT_DISPATCH_ATTN(launch_decode, out, q, k, v, seq_len, n_heads, n_kv, scale, s);
+}
+
+void attention_prefill(float* out, const float* Q, const void* kc, const void* vc, int seq_len, int start_pos, int n_heads,
+                       int n_kv, int hd, int max_seq, float scale, cudaStream_t s) {
+    (void)max_seq;
+    if (seq_len <= 0 || n_heads <= 0) return;
+    const __half* k = static_cast<const __half*>(kc);
+    const __half* v = static_cast<const __half*>(vc);
+    NT_DISPATCH_ATTN(launch_prefill, out, Q, k, v, seq_len, start_pos, n_heads, n_kv, scale, s);
+}
+
+}}  // namespace nt::b200

@@ -1,0 +1,75 @@
+// kernels_internal.h — host-callable launch functions behind the C-ABI (include/nt_b200.h)
+// and behind the nt::cuda::launch_* drop-in symbols. Everything here is sm_100a CUDA; there is
+// deliberately no CPU path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include "nt_types.h"
+
+namespace nt { namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// Block-scaled 3-term int8 activations ("xq").  x[e] ~= scale[e/32] * (q1*16384 + q2*128 + q3)
+// with q1 in [-127,127], q2,q3 in [-64,64]: |error| <= 2^-22 of the 32-block absmax, i.e. F32-class.
+// Integer dot products against the 4/5/6/8-bit weight codes are exact (IDP.4A), the float work is
+// one scale per 16/32 weights instead of one convert + FMA per weight.
+//   layout for K elements (K % 32 == 0):  [q1: K][q2: K][q3: K][scale: K/32 f32][sum16: K/16 f32]
+// sum16 holds exact F32 sums of x over 16-element groups (for the dmin / -32 offset terms).
+// ---------------------------------------------------------------------------------------------
+inline size_t xq_bytes(int K) { return (size_t)3 * K + (size_t)(K / 32) * 4 + (size_t)(K / 16) * 4; }
+void quantize_x(const float* x, void* xq, int K, cudaStream_t s);
+
+// One weight matrix inside a (possibly fused) GEMV launch.
+struct GemvMat {
+    const void* W = nullptr;   // row-major GGUF blocks
+    float* y = nullptr;        // output rows
+    int out = 0;               // rows
+    DType dtype = DType::F32;
+    size_t row_pitch = 0;      // bytes between rows (0 = dense GGUF rows)
+};
+enum GemvEpilogue { GEMV_STORE = 0, GEMV_ADD = 1 /* y += W.x (residual) */, GEMV_SWIGLU = 2 /* y0 = silu(W0.x) * (W1.x) */ };
+
+// Fused K-quant GEMV over up to 3 matrices sharing one activation vector (already in xq form).
+// All matrices must be Q4_K / Q5_K / Q6_K with 16-byte aligned W and row pitch.
+bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K);
+void gemv_kq(const GemvMat* mats, int n_mat, int K, const void* xq, GemvEpilogue ep, cudaStream_t s);
+
+// Generic GEMV for every dtype / any alignment, F32 activations (Q8_0, Q4_0, F16, F32 and
+// unaligned K-quant shards).
+void gemv_generic(float* y, const void* W, const float* x, int out, int in, DType dt, size_t row_pitch,
+                  GemvEpilogue ep, cudaStream_t s);
+
+// Scratch activations for the stateless launch_gemv entry point (one per device+stream).
+void* gemv_scratch_xq(int K, cudaStream_t s);
+
+// ---- elementwise / norm / rope / kv / attention (reference kernels K10-K21) ----
+void rmsnorm(float* y, const float* x, const float* w, int rows, int hidden, float eps, cudaStream_t s);
+void rmsnorm_f16(void* y, const float* x, const float* w, int rows, int hidden, float eps, cudaStream_t s);
+// fused: y = rmsnorm(x) (optional, may be null) and xq = quantise(rmsnorm(x)); rows == 1
+void rmsnorm_xq(float* y, void* xq, const float* x, const float* w, int hidden, float eps, cudaStream_t s);
+void rope(float* q, float* k, const int* positions, int seq_len, int n_heads, int n_kv_heads, int head_dim,
+          float theta, float freq_scale, bool interleaved, cudaStream_t s);
+void copy_to_kv_cache(void* kc, void* vc, const float* k, const float* v, int seq_len, int n_kv, int hd,
+                      int start_pos, int max_seq, cudaStream_t s);
+void silu_mul(float* out, const float* gate, const float* up, int n, cudaStream_t s);
+void add_bias(float* y, const float* b, int n, cudaStream_t s);
+void add(float* out, const float* a, const float* b, int n, cudaStream_t s);
+void add_inplace(float* a, const float* b, int n, cudaStream_t s);
+void copy(float* dst, const float* src, int n, cudaStream_t s);
+void cosine_similarity(float* result, const float* a, const float* b, int n, cudaStream_t s);
+void softmax(float* out, const float* in, int rows, int cols, cudaStream_t s);
+void masked_softmax(float* out, const float* in, const bool* mask, int rows, int cols, cudaStream_t s);
+void gemm_f32(float* C, const float* A, const float* B, int M, int N, int K, cudaStream_t s);
+void attention_decode(float* out, const float* q, const void* kc, const void* vc, int seq_len, int n_heads,
+                      int n_kv, int hd, int max_seq, float scale, cudaStream_t s);
+void attention_prefill(float* out, const float* Q, const void* kc, const void* vc, int seq_len, int start_pos,
+                       int n_heads, int n_kv, int hd, int max_seq, float scale, cudaStream_t s);
+// Embedding-row gather + dequant on the GPU (reference does this on the CPU, transformer.cpp:419-599).
+void embed_rows(float* out, const void* table, DType dt, const int* tokens_dev, int n_tokens, int hidden, cudaStream_t s);
+
+// Number of kernels launched by this library since load (bench.py's gpu_launches claim).
+unsigned long long launch_count();
+void count_launch(int n = 1);
+
+}}  // namespace nt::b200

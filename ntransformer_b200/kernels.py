@@ -1,0 +1,134 @@
+"""Host-side mirror of the reference's kernel-launcher interface (src/cuda/kernels.h:10-74).
+
+Same names, argument order and meaning as nt::cuda::launch_*; arguments are torch CUDA tensors (used
+only as owners of device memory) or raw device pointers (ints).  Everything calls the C-ABI of
+libnt_b200.so; like the reference the launches are asynchronous and return nothing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import lib
+from .dtypes import DType
+
+
+def _p(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return t.data_ptr()
+
+
+def _s(stream):
+    if stream is None:
+        return torch.cuda.current_stream().cuda_stream
+    return stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+
+
+def launch_rmsnorm(output, input, weight, batch_size, hidden_size, eps, stream=None):
+    lib().nt_b200_rmsnorm(_p(output), _p(input), _p(weight), batch_size, hidden_size, eps, _s(stream))
+
+
+def launch_rmsnorm_f16(output, input, weight, batch_size, hidden_size, eps, stream=None):
+    lib().nt_b200_rmsnorm_f16(_p(output), _p(input), _p(weight), batch_size, hidden_size, eps, _s(stream))
+
+
+def launch_rope(q, k, positions, batch_size, seq_len, n_heads, n_kv_heads, head_dim, theta_base, freq_scale,
+                interleaved, stream=None):
+    lib().nt_b200_rope(_p(q), _p(k), _p(positions), batch_size, seq_len, n_heads, n_kv_heads, head_dim, theta_base,
+                       freq_scale, int(bool(interleaved)), _s(stream))
+
+
+def launch_softmax(output, input, rows, cols, stream=None):
+    lib().nt_b200_softmax(_p(output), _p(input), rows, cols, _s(stream))
+
+
+def launch_masked_softmax(output, input, mask, rows, cols, stream=None):
+    lib().nt_b200_masked_softmax(_p(output), _p(input), _p(mask), rows, cols, _s(stream))
+
+
+def launch_gemv(y, W, x, out_features, in_features, weight_dtype, stream=None):
+    lib().nt_b200_gemv(_p(y), _p(W), _p(x), out_features, in_features, int(weight_dtype), _s(stream))
+
+
+def launch_gemv_add(y, W, x, out_features, in_features, weight_dtype, stream=None):
+    lib().nt_b200_gemv_add(_p(y), _p(W), _p(x), out_features, in_features, int(weight_dtype), _s(stream))
+
+
+def launch_gemm_f32(Cm, A, B, M, N, K, stream=None):
+    lib().nt_b200_gemm_f32(_p(Cm), _p(A), _p(B), M, N, K, _s(stream))
+
+
+def launch_silu_mul(output, gate, up, size, stream=None):
+    lib().nt_b200_silu_mul(_p(output), _p(gate), _p(up), size, _s(stream))
+
+
+def launch_add_bias(y, bias, size, stream=None):
+    lib().nt_b200_add_bias(_p(y), _p(bias), size, _s(stream))
+
+
+def launch_attention_decode(output, q, k_cache, v_cache, seq_len, n_heads, n_kv_heads, head_dim, max_seq, scale,
+                            stream=None):
+    lib().nt_b200_attention_decode(_p(output), _p(q), _p(k_cache), _p(v_cache), seq_len, n_heads, n_kv_heads,
+                                   head_dim, max_seq, scale, _s(stream))
+
+
+def launch_attention_prefill(output, Q, k_cache, v_cache, seq_len, start_pos, n_heads, n_kv_heads, head_dim,
+                             max_seq, scale, stream=None):
+    lib().nt_b200_attention_prefill(_p(output), _p(Q), _p(k_cache), _p(v_cache), seq_len, start_pos, n_heads,
+                                    n_kv_heads, head_dim, max_seq, scale, _s(stream))
+
+
+def launch_copy_to_kv_cache(k_cache, v_cache, k, v, seq_len, n_kv_heads, head_dim, start_pos, max_seq, stream=None):
+    lib().nt_b200_copy_to_kv_cache(_p(k_cache), _p(v_cache), _p(k), _p(v), seq_len, n_kv_heads, head_dim, start_pos,
+                                   max_seq, _s(stream))
+
+
+def launch_add(out, a, b, size, stream=None):
+    lib().nt_b200_add(_p(out), _p(a), _p(b), size, _s(stream))
+
+
+def launch_add_inplace(a, b, size, stream=None):
+    lib().nt_b200_add_inplace(_p(a), _p(b), size, _s(stream))
+
+
+def launch_copy(dst, src, size, stream=None):
+    lib().nt_b200_copy(_p(dst), _p(src), size, _s(stream))
+
+
+def launch_cosine_similarity(result, a, b, size, stream=None):
+    lib().nt_b200_cosine_similarity(_p(result), _p(a), _p(b), size, _s(stream))
+
+
+# ---- additions without a reference counterpart ----
+def xq_bytes(K: int) -> int:
+    return lib().nt_b200_xq_bytes(K)
+
+
+def quantize_x(x, xq, K, stream=None):
+    lib().nt_b200_quantize_x(_p(x), _p(xq), K, _s(stream))
+
+
+def gemv_fused(ys, Ws, outs, dtypes, in_features, xq, epilogue=0, stream=None):
+    """Fused K-quant GEMV over up to 3 matrices sharing the quantised activations `xq`.
+    epilogue: 0 store, 1 y += W.x, 2 ys[0] = silu(W0.x) * (W1.x)."""
+    n = len(Ws)
+    yp = (C.c_void_p * n)(*[_p(y) for y in ys])
+    wp = (C.c_void_p * n)(*[_p(w) for w in Ws])
+    op = (C.c_int * n)(*outs)
+    dp = (C.c_int * n)(*[int(d) for d in dtypes])
+    rc = lib().nt_b200_gemv_fused(n, yp, wp, op, dp, in_features, _p(xq), epilogue, _s(stream))
+    if rc != 0:
+        raise ValueError(f"nt_b200_gemv_fused rejected the launch (code {rc})")
+
+
+def embed_rows(out, table, dtype, tokens_dev, n_tokens, hidden, stream=None):
+    lib().nt_b200_embed_rows(_p(out), _p(table), int(dtype), _p(tokens_dev), n_tokens, hidden, _s(stream))
+
+
+def launch_count() -> int:
+    return int(lib().nt_b200_launch_count())

@@ -1,0 +1,42 @@
+"""CPU tests of the drop-in boundary: the shared library loads without a GPU and exports every symbol that
+include/nt_b200.h declares, plus the reference's mangled C++ launcher names (src/cuda/kernels.h:10-74)."""
+import re
+import subprocess
+from pathlib import Path
+
+from ntransformer_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "nt_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(nt_b200_\w+|nt_cuda_\w+)\s*\(", text))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.lib()
+    decl = declared_symbols()
+    assert len(decl) >= 30
+    for name in sorted(decl):
+        assert hasattr(lib, name), f"{name} declared in include/nt_b200.h but not exported"
+    assert decl == set(_lib.SIGNATURES), "python binding table and header disagree"
+    assert lib.nt_b200_version().startswith(b"ntransformer_b200")
+    assert lib.nt_b200_xq_bytes(8192) == 3 * 8192 + 8192 // 32 * 4 + 8192 // 16 * 4
+
+
+def test_reference_cxx_launcher_names_are_exported():
+    out = subprocess.run(["nm", "-D", "--defined-only", "-C", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    for fn in _lib.CXX_LAUNCHERS:
+        assert re.search(rf"\bnt::cuda::{fn}\(", out), f"nt::cuda::{fn} missing"
+    # the exact signature the reference host code calls (kernels.h:34-36)
+    assert "nt::cuda::launch_gemv(float*, void const*, float const*, int, int, nt::DType, void*)" in out
+
+
+def test_sass_is_sm100a_with_tma_and_dp4a():
+    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    assert "UBLKCP" in sass, "TMA bulk copies missing from the GEMV"
+    assert "IDP.4A" in sass
+    assert "SYNCS.ARRIVE.TRANS64" in sass
