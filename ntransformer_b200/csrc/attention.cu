@@ -22,6 +22,7 @@ namespace {
 
 constexpr int AW = 8;                    // warps per CTA
 constexpr int MAX_SPLITS = 64;
+constexpr int ATTN_MAX_DYN_SMEM = 227 * 1024 - 1024;   // static __shared__ (s_max/s_sum) counts against the 227 KB cap
 
 template <int N> struct HalfVec;         // N halfs loaded as one vector
 template <> struct HalfVec<2> { using T = uint32_t; };
@@ -247,12 +248,12 @@ void launch_decode(float* out, const float* q, const __half* kc, const __half* v
     int split_len = (seq_len + n_splits - 1) / n_splits;
     n_splits = (seq_len + split_len - 1) / split_len;
     size_t smem = ((size_t)GC * split_len + (size_t)AW * GC * HD + (size_t)GC * HD + 2 * GC) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        NT_CUDA_CHECK(cudaFuncSetAttribute(decode_kernel<DPL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = 227 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        NT_CUDA_CHECK(cudaFuncSetAttribute(decode_kernel<DPL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_MAX_DYN_SMEM));
+        configured = true;
     }
-    NT_CHECK(smem <= 227 * 1024, "attention_decode: context slice does not fit shared memory");
+    NT_CHECK(smem <= (size_t)ATTN_MAX_DYN_SMEM, "attention_decode: context slice does not fit shared memory");
     float* scratch = nullptr;
     if (n_splits > 1) scratch = attn_scratch((size_t)n_heads * n_splits * (HD + 2));
     decode_kernel<DPL, GC><<<dim3(groups, n_splits), AW * 32, smem, s>>>(out, q, kc, vc, seq_len, n_heads, n_kv, scale,
@@ -269,10 +270,10 @@ void launch_prefill(float* out, const float* Q, const __half* kc, const __half* 
                     int n_kv, float scale, cudaStream_t s) {
     constexpr int HD = DPL * 32;
     size_t smem = ((size_t)GC * (start_pos + seq_len) + (size_t)AW * GC * HD) * sizeof(float);
-    NT_CHECK(smem <= 227 * 1024, "attention_prefill: context does not fit shared memory");
+    NT_CHECK(smem <= (size_t)ATTN_MAX_DYN_SMEM, "attention_prefill: context does not fit shared memory");
     static bool configured = false;
     if (!configured) {
-        NT_CUDA_CHECK(cudaFuncSetAttribute(prefill_kernel<DPL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NT_CUDA_CHECK(cudaFuncSetAttribute(prefill_kernel<DPL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_MAX_DYN_SMEM));
         configured = true;
     }
     prefill_kernel<DPL, GC><<<dim3(n_heads / GC, seq_len), AW * 32, smem, s>>>(out, Q, kc, vc, start_pos, n_heads, n_kv, scale);
