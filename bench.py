@@ -1,0 +1,425 @@
+#!/usr/bin/env python3
+"""bench.py — resident decode throughput of the B200-native engine on BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one decoded token (batch 1) of the named Llama-3 shape with synthetic, seeded random GGUF blocks
+generated on the GPU.  N > 1 runs the same model tensor-parallel over N ranks (strong scaling).
+Prints ONE JSON line on rank 0 (see the task contract): value = tok/s with the token already handed to the
+device-side step state; e2e = tok/s through the C-ABI with HOST token ids in and HOST logits out every step.
+
+--impl reference times the UNMODIFIED reference (its own CUDA kernels and Transformer::forward, compiled for
+sm_100 into oracle/_ref by oracle/Makefile) on the same synthetic model on one GPU of this box.  The reference
+has no CPU path, so its own implementation of this path IS a CUDA implementation; the CPU figure
+reported next to it (cpu_baseline, kind "port") is the oracle's C restatement on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (shape, mix, prompt_len, max_seq)          BASELINE.json configs[2] is the metric's own config
+    "llama3-70b-q4_k_m-decode": ("70b", "Q4_K_M", 16, 4096),
+    "llama3-8b-q4_k_m-decode-ctx2048": ("8b", "Q4_K_M", 2047, 4096),
+    "llama3-8b-q8_0-decode": ("8b", "Q8_0", 16, 4096),
+    "llama3-70b-q6_k-decode": ("70b", "Q6_K", 16, 4096),
+    "llama3-8b-q4_k_m-decode": ("8b", "Q4_K_M", 16, 4096),
+    "tiny-q4_k_m-decode": ("tiny", "Q4_K_M", 8, 128),
+}
+DTYPE_NOTE = "k-quant codes x block-scaled int8x3 activations via dp4a (s32 exact) + f32 scales/accumulate; KV f16"
+
+
+def shape_cfg(shape: str, max_seq: int):
+    from dataclasses import replace
+    from ntransformer_b200.model_spec import LLAMA3_8B, LLAMA3_70B, TINY
+    return replace({"8b": LLAMA3_8B, "70b": LLAMA3_70B, "tiny": TINY}[shape], max_seq_len=max_seq)
+
+
+def token_at(i: int, vocab: int) -> int:
+    return (i * 7919 + 11) % min(vocab, 128000)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            self.path = tempfile.NamedTemporaryFile(prefix="clk", suffix=".csv", delete=False).name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from ntransformer_b200 import kernels as K
+    from ntransformer_b200._lib import lib
+    from ntransformer_b200.dtypes import DType
+    from ntransformer_b200.engine import Model
+    from ntransformer_b200.model_spec import bytes_per_token, tensor_table
+
+    shape, mix, prompt_len, max_seq = WORKLOADS[args.workload]
+    cfg = shape_cfg(shape, max_seq)
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    model = Model.synthetic(cfg, mix, seed=1234, tp_rank=rank, tp_size=world)
+    if world > 1:
+        model.init_tp()
+    stream = torch.cuda.ExternalStream(model.stream)
+    vocab = cfg.vocab_size
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- prefill (untimed) then warm-up ----
+    prompt = [token_at(i, vocab) for i in range(prompt_len)]
+    model.forward(prompt, 0, want_logits=False)
+    pos = prompt_len
+    for i in range(args.warmup):
+        model.forward_async([token_at(pos, vocab)], pos)
+        pos += 1
+    model.sync()
+
+    # ---- timed: device-resident decode (value) ----
+    sampler = ClockSampler(local)
+    launches0 = K.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ctx_first = pos
+    ev0.record(stream)
+    for i in range(args.steps):
+        model.forward_async([token_at(pos, vocab)], pos)
+        pos += 1
+    ev1.record(stream)
+    model.sync()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = K.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    tok_s = args.steps / (ms / 1e3)
+
+    # ---- timed: end to end through the C-ABI, host token in / host logits out each step ----
+    for i in range(min(3, args.warmup)):
+        model.forward([token_at(pos, vocab)], pos)
+        pos += 1
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        logits = model.forward([token_at(pos, vocab)], pos)     # sync + 513 KB D2H inside
+        pos += 1
+    e1.record(stream)
+    model.sync()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, wall_ms)                                # host-visible time is what a caller sees
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_tok_s = args.steps / (e2e_ms / 1e3)
+    assert np.isfinite(logits).all(), "non-finite logits"
+
+    # ---- roofline of the dominant kernel (fused gate+up K-quant GEMV), measured live ----
+    peak, peak_src = measured_peak_hbm()
+    ctx_mid = ctx_first + args.steps // 2
+    b_tok = model.bytes_per_token(ctx_mid)                       # this rank's algorithmic bytes per token
+    roof = None
+    if rank == 0:
+        names = [(f"blk.{i}.ffn_gate.weight", f"blk.{i}.ffn_up.weight") for i in range(cfg.n_layers)]
+        g0, dt0 = model._keep[names[0][0]]
+        if dt0 in (DType.Q4_K_M, DType.Q5_K, DType.Q6_K):
+            inter_l = cfg.intermediate_size // world
+            x = torch.randn(cfg.hidden_size, device="cuda")
+            xq = torch.zeros(K.xq_bytes(cfg.hidden_size), device="cuda", dtype=torch.uint8)
+            act, up = torch.zeros(inter_l, device="cuda"), torch.zeros(inter_l, device="cuda")
+            K.quantize_x(x, xq, cfg.hidden_size)
+            reps = 3 if cfg.n_layers >= 16 else 50
+            evs = []
+            for r in range(reps + 1):
+                for gn, un in names:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    K.gemv_fused([act, up], [model._keep[gn][0], model._keep[un][0]], [inter_l, inter_l], [dt0, dt0],
+                                 cfg.hidden_size, xq, epilogue=2)
+                    b.record()
+                    if r > 0:
+                        evs.append((a, b))
+            torch.cuda.synchronize()
+            dur_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+            kbytes = 2 * model._keep[names[0][0]][0].numel()
+            ach = kbytes / (dur_ms / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": "gemv_kq_kernel (ffn gate+up fused, SwiGLU epilogue)", "achieved": round(ach, 1),
+                    "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                    "bytes_per_launch": kbytes, "avg_launch_us": round(dur_ms * 1e3, 2), "launches_timed": len(evs),
+                    "peak_source": peak_src}
+        step_ach = b_tok * tok_s / 1e9
+        if roof is None:
+            roof = {"bound": "hbm", "kernel": "whole decode step", "achieved": round(step_ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(step_ach / peak, 4), "traffic": None, "peak_source": peak_src}
+        roof["step_achieved"] = round(step_ach, 1)
+        roof["step_frac"] = round(step_ach / peak, 4)
+        roof["step_bytes_per_gpu"] = b_tok
+
+    cpu = cpu_baseline(model, cfg, mix, world) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+
+    if rank == 0:
+        line = {
+            "metric": "decode_tok_s", "value": round(tok_s, 2), "unit": "tok/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": DTYPE_NOTE, "data": "synthetic (seeded random valid GGUF blocks generated on the GPU)",
+            "config": {"workload": args.workload, "quant_mix": mix, "batch": 1, "prompt_tokens": prompt_len,
+                       "ctx_during_timing": [ctx_first, ctx_first + args.steps], "max_seq": max_seq,
+                       "parallelism": f"tp{world}" if world > 1 else "single",
+                       "l2_policy": "weights per step (%.1f GB/GPU) exceed the 126 MB L2; no flush needed" % (b_tok / 1e9),
+                       "cuda_graph": True},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_tok_s, 2), "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": vocab * 4,
+                    "ms_per_step": round(e2e_ms / args.steps, 4)},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(model, cfg, mix, world):
+    """Times the oracle's C restatement of one decoded token on a bounded sample (2 layers + LM head), host cores."""
+    from oracle import oracle as O
+    from ntransformer_b200.model_spec import use_more_bits
+
+    n = cfg.n_layers
+    hi = 0
+    lo = next((i for i in range(n) if not use_more_bits(i, n)), 0)
+    picks = [hi, lo] if n > 1 else [0]
+    host = {}
+    for name in ("token_embd.weight", "output.weight", "output_norm.weight"):
+        t, dt = model._keep[name]
+        host[name] = (t.cpu().numpy(), int(dt))
+    for j, li in enumerate(picks):
+        for suffix in ("attn_norm", "attn_q", "attn_k", "attn_v", "attn_output", "ffn_norm", "ffn_gate", "ffn_up", "ffn_down"):
+            t, dt = model._keep[f"blk.{li}.{suffix}.weight"]
+            host[f"blk.{j}.{suffix}.weight"] = (t.cpu().numpy(), int(dt))
+    for j in range(len(picks), n):          # unused layer slots alias the first sample (never run)
+        for suffix in ("attn_norm", "attn_q", "attn_k", "attn_v", "attn_output", "ffn_norm", "ffn_gate", "ffn_up", "ffn_down"):
+            host[f"blk.{j}.{suffix}.weight"] = host[f"blk.0.{suffix}.weight"]
+    c = cfg.dict()
+    c["max_seq_len"] = 64
+    om = O.Model(c, host)
+
+    def timed(k, min_s):
+        om.forward([5], 0, n_layers_run=k)                       # warm page cache / thread pool
+        t0, reps = time.perf_counter(), 0
+        while reps < 2 or time.perf_counter() - t0 < min_s:
+            om.forward([6 + reps], 1 + reps, n_layers_run=k)
+            reps += 1
+            if reps >= 30:
+                break
+        return (time.perf_counter() - t0) / reps, reps
+
+    t_head, r0 = timed(0, 2.0)                                  # final norm + LM head only
+    t_1, r1 = timed(1, 3.0)                                     # + layer picks[0]
+    t_2, r2 = timed(len(picks), 4.0) if len(picks) == 2 else (t_1, r1)
+    n_hi = sum(1 for i in range(n) if use_more_bits(i, n)) if len(picks) == 2 else n
+    l_hi, l_lo = max(t_1 - t_head, 1e-9), max(t_2 - t_1, 1e-9)
+    token_s = n_hi * l_hi + (n - n_hi) * l_lo + t_head
+    om.close()
+    return {"value": round(1.0 / token_s, 4), "unit": "tok/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"oracle/nt_oracle.c (C + OpenMP) forward of 1 token: LM head {t_head * 1e3:.0f} ms, layer {picks[0]} "
+                      f"{l_hi * 1e3:.0f} ms, layer {picks[-1]} {l_lo * 1e3:.0f} ms ({r0 + r1 + r2} timed calls), extrapolated to "
+                      f"{n} layers ({n_hi} of the first kind)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own CUDA path (oracle/_ref, built from /root/reference for sm_100) on the same synthetic model."""
+    if rank != 0:
+        return
+    so = ROOT / "oracle" / "_ref" / "libnt_ref.so"
+    shape, mix, prompt_len, max_seq = WORKLOADS[args.workload]
+    if not so.exists():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnt_ref.so was not built (no /root/reference at build time)"}))
+        return
+    import torch
+    from ntransformer_b200.gguf_write import write_gguf_streaming
+    from ntransformer_b200.synth import random_blocks_cuda
+    from ntransformer_b200.model_spec import tensor_table
+
+    cfg = shape_cfg(shape, max_seq)
+    torch.cuda.set_device(0)
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(tmpdir, f"nt_ref_{args.workload}_{os.getpid()}.gguf")
+    t_gen = time.perf_counter()
+
+    def gen():
+        for idx, (name, dt, rows, cols) in enumerate(tensor_table(cfg, mix)):
+            s = 1234 + idx * 16
+            if name.endswith("norm.weight"):
+                g = torch.Generator(device="cuda")
+                g.manual_seed(s)
+                t = 1.0 + 0.1 * torch.randn(cols, generator=g, device="cuda", dtype=torch.float32)
+            else:
+                t = random_blocks_cuda(dt, rows, cols, s)
+            yield name, t.cpu().numpy(), dt, rows, cols
+    write_gguf_streaming(path, cfg, gen(), tensor_table(cfg, mix))
+    t_gen = time.perf_counter() - t_gen
+    try:
+        ref = C.CDLL(str(so))
+        ref.ref_model_load.restype = C.c_void_p
+        ref.ref_model_load.argtypes = [C.c_char_p, C.c_int]
+        ref.ref_model_forward.restype = C.c_float
+        ref.ref_model_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        ref.ref_model_free.argtypes = [C.c_void_p]
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(2)
+        os.dup2(devnull, 2)                                       # the reference logs every layer to stderr
+        try:
+            h = ref.ref_model_load(path.encode(), max_seq)
+        finally:
+            os.dup2(saved, 2)
+            os.close(devnull)
+        if not h:
+            print(json.dumps({"impl": "reference", "unavailable": "reference failed to load the synthetic GGUF"}))
+            return
+        vocab = cfg.vocab_size
+        # bounded prefill: the reference prefills with per-token GEMVs, so keep the prompt short
+        p_len = min(prompt_len, 16)
+        toks = np.array([token_at(i, vocab) for i in range(p_len)], np.int32)
+        logits = np.empty(vocab, np.float32)
+        ref.ref_model_forward(h, toks.ctypes.data_as(C.c_void_p), p_len, 0, None)
+        pos = p_len
+        for i in range(args.warmup):
+            t = np.array([token_at(pos, vocab)], np.int32)
+            ref.ref_model_forward(h, t.ctypes.data_as(C.c_void_p), 1, pos, None)
+            pos += 1
+        sampler = ClockSampler(0)
+        sampler.start()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            t = np.array([token_at(pos, vocab)], np.int32)
+            ref.ref_model_forward(h, t.ctypes.data_as(C.c_void_p), 1, pos, logits.ctypes.data_as(C.c_void_p))
+            pos += 1
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        clocks = sampler.stop()
+        ref.ref_model_free(h)
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
+    tok_s = args.steps / (ms / 1e3)
+    print(json.dumps({
+        "impl": "reference", "metric": "decode_tok_s", "value": round(tok_s, 2), "unit": "tok/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 activations x dequantised codes (reference CUDA-core kernels, sm_100 build)",
+        "data": "synthetic (same seeded blocks as the B200 arm, written to a GGUF in /dev/shm)",
+        "config": {"workload": args.workload, "quant_mix": mix, "batch": 1, "prompt_tokens": p_len, "max_seq": max_seq,
+                   "parallelism": "single (the reference is single-GPU)", "device": "cuda:0",
+                   "note": "reference has no CPU path; this is its own CUDA path rebuilt for sm_100 (oracle/Makefile ref)"},
+        "clocks": clocks,
+        "cpu_baseline": {"value": round(tok_s, 2), "unit": "tok/s", "cores": 1, "kind": "reference",
+                         "sample": f"{args.steps} decode steps through nt::Transformer::forward (1 host thread drives the GPU)"},
+        "e2e": {"value": round(tok_s, 2), "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "setup_s": round(t_gen, 1),
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--workload", default="llama3-70b-q4_k_m-decode", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        sys.exit("bench.py --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,66 @@
+/*
+ * nt_b200_engine.h — token-level C-ABI of the resident model (additions to include/ntransformer.h).
+ *
+ * Mirrors the reference's C++ surface nt::Transformer::{load,forward,config} (src/model/transformer.h:31-61,
+ * forward = src/model/transformer.cpp:604-669): tokens in (HOST int32), logits out (HOST or DEVICE float32
+ * [vocab]).  Weights come either from a GGUF file or from caller-owned device tensors in GGUF block layout
+ * (synthetic benchmarks); tensor names are the reference's GGUF names (transformer.cpp:89-104, 286-322).
+ * Tensor parallelism (new; the reference is single GPU): one process per GPU, ranks exchange a 128-byte
+ * NCCL id through their own plumbing and call nt_tp_init before the first forward.
+ */
+#ifndef NT_B200_ENGINE_H
+#define NT_B200_ENGINE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    int vocab_size, hidden_size, intermediate_size, n_layers, n_heads, n_kv_heads, head_dim, max_seq_len;
+    float norm_eps, rope_theta;
+    int bos_token_id, eos_token_id;
+} nt_model_config;
+
+typedef void* nt_model_t;
+
+/* GGUF path: returns NULL on failure.  max_context caps llama.context_length like the CLI's -c. */
+nt_model_t nt_model_load_gguf(const char* path, int max_context, int tp_rank, int tp_size);
+/* Device-pointer path: create -> set_tensor (every tensor, shapes already sharded for the rank) -> finalize */
+nt_model_t nt_model_create(const nt_model_config* cfg, int tp_rank, int tp_size);
+int  nt_model_set_tensor(nt_model_t m, const char* gguf_name, const void* dev_ptr, int dtype, size_t row_pitch);
+int  nt_model_finalize(nt_model_t m);
+void nt_model_free(nt_model_t m);
+int  nt_model_get_config(nt_model_t m, nt_model_config* out);
+
+/* forward(tokens[seq_len], start_pos): logits of the last token. logits_host may be NULL.  Returns 0. */
+int  nt_model_forward(nt_model_t m, const int* tokens_host, int seq_len, int start_pos, float* logits_host);
+/* asynchronous launch only (no sync, no copy); nt_model_sync waits for the model's stream */
+int  nt_model_forward_async(nt_model_t m, const int* tokens_host, int seq_len, int start_pos);
+int  nt_model_sync(nt_model_t m);
+float* nt_model_logits_device(nt_model_t m);
+void*  nt_model_stream(nt_model_t m);
+int  nt_model_argmax(nt_model_t m);                 /* greedy token of the last logits, computed on the GPU */
+void nt_model_clear_kv(nt_model_t m);
+void nt_model_use_graph(nt_model_t m, int on);
+/* algorithmic bytes read per decoded token by this rank at context length ctx */
+unsigned long long nt_model_bytes_per_token(nt_model_t m, int ctx);
+
+/* ---- host-only helpers (no GPU needed): GGUF header, tokenizer and sampler of the CLI path ---- */
+/* JSON description of a GGUF file as the engine parses it (config, vocab size, tensor table). Returns the
+ * number of bytes written (excluding NUL) or -1. */
+int  nt_gguf_describe(const char* path, char* out, size_t cap);
+int  nt_tokenize(const char* gguf_path, const char* text, int add_bos, int* ids, int cap);      /* returns count or -1 */
+int  nt_detokenize(const char* gguf_path, const int* ids, int n, char* out, size_t cap);       /* returns bytes or -1 */
+/* One draw of the reference-compatible sampler (repeat penalty over `recent`, temperature, top-k, top-p, mt19937(seed)). */
+int  nt_sample_token(const float* logits, int n, float temperature, int top_k, float top_p, float repeat_penalty,
+                     int repeat_window, const int* recent, int n_recent, uint64_t seed);
+
+/* tensor-parallel communicator */
+int  nt_tp_unique_id(void* out128);                 /* rank 0; returns 0 on success */
+int  nt_tp_init(nt_model_t m, const void* id128, int rank, int size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

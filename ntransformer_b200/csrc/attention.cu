@@ -156,14 +156,19 @@ template <int DPL, int GC>
 __global__ void __launch_bounds__(AW * 32) decode_kernel(float* __restrict__ out, const float* __restrict__ q,
                                                          const __half* __restrict__ kc, const __half* __restrict__ vc,
                                                          int seq_len, int n_heads, int n_kv, float scale, int n_splits,
-                                                         int split_len, float* __restrict__ scratch) {
+                                                         int split_len, float* __restrict__ scratch,
+                                                         const int* __restrict__ pos_dev) {
     constexpr int HD = DPL * 32;
     extern __shared__ float smem_dyn[];
+    if (pos_dev) {                       // CUDA-graph replay: context length lives in device memory
+        seq_len = *pos_dev + 1;
+        split_len = (seq_len + n_splits - 1) / n_splits;
+    }
     const int head0 = blockIdx.x * GC, split = blockIdx.y;
     const int kv_head = head0 / (n_heads / n_kv);
     const int k_begin = split * split_len, k_end = min(seq_len, k_begin + split_len);
     if (k_begin >= k_end) return;
-    if (n_splits == 1) {
+    if (n_splits == 1 && !pos_dev) {
         attend_group<DPL, GC>(out + (size_t)head0 * HD, q + (size_t)head0 * HD, kc, vc, kv_head, n_kv, k_begin, k_end, scale,
                               nullptr, nullptr, smem_dyn);
     } else {
@@ -187,8 +192,9 @@ __global__ void __launch_bounds__(AW * 32) decode_kernel(float* __restrict__ out
 
 // Merge split partials: out[h] = sum_i e^{m_i - m} o_i / sum_i e^{m_i - m} l_i
 __global__ void decode_combine_kernel(float* __restrict__ out, const float* __restrict__ scratch, int n_heads, int hd,
-                                      int n_splits, int seq_len, int split_len) {
+                                      int n_splits, int seq_len, int split_len, const int* __restrict__ pos_dev) {
     const int h = blockIdx.x;
+    if (pos_dev) { seq_len = *pos_dev + 1; split_len = (seq_len + n_splits - 1) / n_splits; }
     const float* ml = scratch + (size_t)n_heads * n_splits * hd + (size_t)h * n_splits * 2;
     const int used = (seq_len + split_len - 1) / split_len;
     float m = -FLT_MAX;
@@ -257,12 +263,33 @@ void launch_decode(float* out, const float* q, const __half* kc, const __half* v
     float* scratch = nullptr;
     if (n_splits > 1) scratch = attn_scratch((size_t)n_heads * n_splits * (HD + 2));
     decode_kernel<DPL, GC><<<dim3(groups, n_splits), AW * 32, smem, s>>>(out, q, kc, vc, seq_len, n_heads, n_kv, scale,
-                                                                        n_splits, split_len, scratch);
+                                                                        n_splits, split_len, scratch, nullptr);
     count_launch();
     if (n_splits > 1) {
-        decode_combine_kernel<<<n_heads, 128, 0, s>>>(out, scratch, n_heads, HD, n_splits, seq_len, split_len);
+        decode_combine_kernel<<<n_heads, 128, 0, s>>>(out, scratch, n_heads, HD, n_splits, seq_len, split_len, nullptr);
         count_launch();
     }
+}
+
+// Graph-replayable decode: the context length (pos + 1) is read from device memory, the launch shape is fixed
+// by max_seq, partials always go through caller-owned scratch (n_heads * n_splits * (HD + 2) floats).
+template <int DPL, int GC>
+void launch_decode_dyn(float* out, const float* q, const __half* kc, const __half* vc, const int* pos_dev, int max_seq,
+                       int n_heads, int n_kv, float scale, float* scratch, int n_splits, cudaStream_t s) {
+    constexpr int HD = DPL * 32;
+    const int groups = n_heads / GC;
+    const int max_split_len = (max_seq + n_splits - 1) / n_splits;
+    size_t smem = ((size_t)GC * max_split_len + (size_t)AW * GC * HD + (size_t)GC * HD + 2 * GC) * sizeof(float);
+    NT_CHECK(smem <= (size_t)ATTN_MAX_DYN_SMEM, "attention_decode_dyn: context slice does not fit shared memory");
+    static bool configured = false;
+    if (!configured) {
+        NT_CUDA_CHECK(cudaFuncSetAttribute(decode_kernel<DPL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_MAX_DYN_SMEM));
+        configured = true;
+    }
+    decode_kernel<DPL, GC><<<dim3(groups, n_splits), AW * 32, smem, s>>>(out, q, kc, vc, 0, n_heads, n_kv, scale, n_splits, 0,
+                                                                        scratch, pos_dev);
+    decode_combine_kernel<<<n_heads, 128, 0, s>>>(out, scratch, n_heads, HD, n_splits, 0, 0, pos_dev);
+    count_launch(2);
 }
 
 template <int DPL, int GC>
@@ -308,6 +335,25 @@ void attention_decode(float* out, const float* q, const void* kc, const void* vc
     const __half* k = static_cast<const __half*>(kc);
     const __half* v = static_cast<const __half*>(vc);
     NT_DISPATCH_ATTN(launch_decode, out, q, k, v, seq_len, n_heads, n_kv, scale, s);
+}
+
+int attention_decode_dyn_splits(int max_seq, int n_heads, int n_kv) {
+    const int groups = n_heads / pick_gc(n_heads / n_kv);
+    int n = (2 * 148 + groups - 1) / groups;
+    int by_len = (max_seq + 31) / 32;
+    if (n > by_len) n = by_len;
+    if (n > MAX_SPLITS) n = MAX_SPLITS;
+    return n < 1 ? 1 : n;
+}
+size_t attention_decode_dyn_scratch_floats(int max_seq, int n_heads, int n_kv, int hd) {
+    return (size_t)n_heads * attention_decode_dyn_splits(max_seq, n_heads, n_kv) * (hd + 2);
+}
+void attention_decode_dyn(float* out, const float* q, const void* kc, const void* vc, const int* pos_dev, int max_seq,
+                          int n_heads, int n_kv, int hd, float scale, float* scratch, cudaStream_t s) {
+    const __half* k = static_cast<const __half*>(kc);
+    const __half* v = static_cast<const __half*>(vc);
+    const int n_splits = attention_decode_dyn_splits(max_seq, n_heads, n_kv);
+    NT_DISPATCH_ATTN(launch_decode_dyn, out, q, k, v, pos_dev, max_seq, n_heads, n_kv, scale, scratch, n_splits, s);
 }
 
 void attention_prefill(float* out, const float* Q, const void* kc, const void* vc, int seq_len, int start_pos, int n_heads,

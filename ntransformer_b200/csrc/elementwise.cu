@@ -136,6 +136,35 @@ __global__ void kv_write_kernel(__half* __restrict__ kc, __half* __restrict__ vc
     vc[(size_t)cp * row + c] = __float2half(v[idx]);
 }
 
+// Decode-step fusion of K14 + K15: rotate q and k (pairs (i, i + hd/2)), then store F16 k, v at cache row *pos_dev.
+__global__ void rope_kv_decode_kernel(float* __restrict__ q, float* __restrict__ k, const float* __restrict__ v,
+                                      __half* __restrict__ kc, __half* __restrict__ vc, const int* __restrict__ pos_dev,
+                                      int n_heads, int n_kv, int head_dim, float theta_base, float freq_scale, int max_seq) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half_dim = head_dim / 2;
+    const int total_q = n_heads * half_dim, total_k = n_kv * half_dim;
+    if (idx >= total_q + total_k) return;
+    const bool is_key = idx >= total_q;
+    const int li = is_key ? idx - total_q : idx;
+    const int pair = li % half_dim, head = li / half_dim;
+    const int pos = *pos_dev;
+    float freq = 1.0f / powf(theta_base, (2.0f * pair) / head_dim);
+    float angle = pos * freq * freq_scale;
+    float c = cosf(angle), sn = sinf(angle);
+    float* d = (is_key ? k : q) + (size_t)head * head_dim;
+    float x0 = d[pair], x1 = d[pair + half_dim];
+    float r0 = x0 * c - x1 * sn, r1 = x1 * c + x0 * sn;
+    d[pair] = r0;
+    d[pair + half_dim] = r1;
+    if (is_key && pos < max_seq) {
+        const size_t row = (size_t)pos * n_kv * head_dim + (size_t)head * head_dim;
+        kc[row + pair] = __float2half(r0);
+        kc[row + pair + half_dim] = __float2half(r1);
+        vc[row + pair] = __float2half(v[(size_t)head * head_dim + pair]);
+        vc[row + pair + half_dim] = __float2half(v[(size_t)head * head_dim + pair + half_dim]);
+    }
+}
+
 __global__ void silu_mul_kernel(float* __restrict__ out, const float* __restrict__ gate, const float* __restrict__ up, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { float g = gate[i]; float silu = g / (1.0f + expf(-g)); out[i] = silu * up[i]; }
@@ -289,6 +318,13 @@ void copy_to_kv_cache(void* kc, void* vc, const float* k, const float* v, int se
     if (total <= 0) return;
     kv_write_kernel<<<cdiv(total, 256), 256, 0, s>>>(static_cast<__half*>(kc), static_cast<__half*>(vc), k, v, seq_len,
                                                      n_kv * hd, start_pos, max_seq);
+    count_launch();
+}
+void rope_kv_decode(float* q, float* k, const float* v, void* kc, void* vc, const int* pos_dev, int n_heads, int n_kv,
+                    int hd, float theta, float freq_scale, int max_seq, cudaStream_t s) {
+    int total = (n_heads + n_kv) * (hd / 2);
+    rope_kv_decode_kernel<<<cdiv(total, 256), 256, 0, s>>>(q, k, v, static_cast<__half*>(kc), static_cast<__half*>(vc), pos_dev,
+                                                          n_heads, n_kv, hd, theta, freq_scale, max_seq);
     count_launch();
 }
 void silu_mul(float* out, const float* gate, const float* up, int n, cudaStream_t s) {

@@ -1,0 +1,161 @@
+// capi.cpp — extern "C" surface of the engine: include/ntransformer.h and include/nt_b200_engine.h.
+#include "../../../include/ntransformer.h"
+#include "../../../include/nt_b200_engine.h"
+#include "engine.h"
+#include "tp_comm.h"
+#include <cstring>
+#include <memory>
+
+using namespace nt::b200;
+
+namespace {
+struct ModelHandle {
+    Model model;
+    std::unique_ptr<TPComm> comm;
+};
+ModelHandle* H(nt_model_t m) { return static_cast<ModelHandle*>(m); }
+}  // namespace
+
+extern "C" {
+
+// ---- include/ntransformer.h ----
+nt_engine_t nt_engine_create(void) { return new Engine(); }
+void nt_engine_destroy(nt_engine_t e) { delete static_cast<Engine*>(e); }
+int nt_engine_load(nt_engine_t e, const char* path) { return (e && path && static_cast<Engine*>(e)->load(path)) ? 0 : -1; }
+char* nt_engine_generate(nt_engine_t e, const char* prompt, int max_tokens, float temperature, int top_k, float top_p) {
+    if (!e || !prompt) return nullptr;
+    GenerateConfig cfg;
+    cfg.max_tokens = max_tokens; cfg.temperature = temperature; cfg.top_k = top_k; cfg.top_p = top_p; cfg.verbose = false;
+    std::string out = static_cast<Engine*>(e)->generate(prompt, cfg);
+    char* r = static_cast<char*>(malloc(out.size() + 1));
+    if (r) memcpy(r, out.c_str(), out.size() + 1);
+    return r;
+}
+void nt_free(char* p) { free(p); }
+int nt_engine_vocab_size(nt_engine_t e) { return e ? static_cast<Engine*>(e)->config().vocab_size : 0; }
+int nt_engine_n_layers(nt_engine_t e) { return e ? static_cast<Engine*>(e)->config().n_layers : 0; }
+int nt_engine_hidden_size(nt_engine_t e) { return e ? static_cast<Engine*>(e)->config().hidden_size : 0; }
+
+// ---- include/nt_b200_engine.h ----
+nt_model_t nt_model_load_gguf(const char* path, int max_context, int tp_rank, int tp_size) {
+    auto* h = new ModelHandle();
+    if (!path || !h->model.load_gguf(path, max_context, tp_rank, tp_size)) { delete h; return nullptr; }
+    return h;
+}
+nt_model_t nt_model_create(const nt_model_config* c, int tp_rank, int tp_size) {
+    if (!c) return nullptr;
+    ModelConfig cfg;
+    cfg.vocab_size = c->vocab_size; cfg.hidden_size = c->hidden_size; cfg.intermediate_size = c->intermediate_size;
+    cfg.n_layers = c->n_layers; cfg.n_heads = c->n_heads; cfg.n_kv_heads = c->n_kv_heads; cfg.head_dim = c->head_dim;
+    cfg.max_seq_len = c->max_seq_len; cfg.norm_eps = c->norm_eps; cfg.rope_theta = c->rope_theta;
+    cfg.bos_token_id = c->bos_token_id; cfg.eos_token_id = c->eos_token_id;
+    auto* h = new ModelHandle();
+    h->model.init(cfg, tp_rank, tp_size);
+    return h;
+}
+int nt_model_set_tensor(nt_model_t m, const char* name, const void* p, int dtype, size_t pitch) {
+    return (m && name && H(m)->model.set_tensor(name, p, (nt::DType)dtype, pitch)) ? 0 : -1;
+}
+int nt_model_finalize(nt_model_t m) { return (m && H(m)->model.finalize()) ? 0 : -1; }
+void nt_model_free(nt_model_t m) { delete H(m); }
+int nt_model_get_config(nt_model_t m, nt_model_config* o) {
+    if (!m || !o) return -1;
+    const ModelConfig& c = H(m)->model.config();
+    *o = nt_model_config{c.vocab_size, c.hidden_size, c.intermediate_size, c.n_layers, c.n_heads, c.n_kv_heads, c.head_dim,
+                         c.max_seq_len, c.norm_eps, c.rope_theta, c.bos_token_id, c.eos_token_id};
+    return 0;
+}
+int nt_model_forward(nt_model_t m, const int* tokens, int n, int start_pos, float* logits_host) {
+    if (!m || !tokens) return -1;
+    float* dl = H(m)->model.forward(tokens, n, start_pos);
+    if (logits_host)
+        NT_CUDA_CHECK(cudaMemcpy(logits_host, dl, sizeof(float) * (size_t)H(m)->model.config().vocab_size, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int nt_model_forward_async(nt_model_t m, const int* tokens, int n, int start_pos) {
+    if (!m || !tokens) return -1;
+    H(m)->model.forward_async(tokens, n, start_pos);
+    return 0;
+}
+int nt_model_sync(nt_model_t m) { return m ? (int)cudaStreamSynchronize(H(m)->model.stream()) : -1; }
+float* nt_model_logits_device(nt_model_t m) { return m ? H(m)->model.logits_device() : nullptr; }
+void* nt_model_stream(nt_model_t m) { return m ? (void*)H(m)->model.stream() : nullptr; }
+int nt_model_argmax(nt_model_t m) { return m ? H(m)->model.argmax_last() : -1; }
+void nt_model_clear_kv(nt_model_t m) { if (m) H(m)->model.clear_kv(); }
+void nt_model_use_graph(nt_model_t m, int on) { if (m) H(m)->model.set_use_graph(on != 0); }
+unsigned long long nt_model_bytes_per_token(nt_model_t m, int ctx) { return m ? H(m)->model.bytes_per_token(ctx) : 0; }
+
+int nt_gguf_describe(const char* path, char* out, size_t cap) {
+    if (!path || !out || !cap) return -1;
+    GGUFFile f;
+    if (!f.open(path)) return -1;
+    const ModelConfig& c = f.config();
+    std::string j = "{";
+    auto kv = [&](const char* k, long long v) { j += "\"" + std::string(k) + "\": " + std::to_string(v) + ", "; };
+    kv("vocab_size", c.vocab_size); kv("hidden_size", c.hidden_size); kv("intermediate_size", c.intermediate_size);
+    kv("n_layers", c.n_layers); kv("n_heads", c.n_heads); kv("n_kv_heads", c.n_kv_heads); kv("head_dim", c.head_dim);
+    kv("max_seq_len", c.max_seq_len); kv("bos_token_id", c.bos_token_id); kv("eos_token_id", c.eos_token_id);
+    kv("n_vocab_tokens", (long long)f.vocab().tokens.size()); kv("data_offset", (long long)f.data_offset());
+    char fl[96];
+    snprintf(fl, sizeof(fl), "\"norm_eps\": %.9g, \"rope_theta\": %.9g, ", c.norm_eps, c.rope_theta);
+    j += fl;
+    j += "\"architecture\": \"" + c.architecture + "\", \"tensors\": [";
+    bool first = true;
+    for (const auto& t : f.tensors()) {
+        if (!first) j += ", ";
+        first = false;
+        j += "{\"name\": \"" + t.name + "\", \"dtype\": " + std::to_string((int)t.dtype) + ", \"offset\": " + std::to_string(t.offset) +
+             ", \"nbytes\": " + std::to_string(t.nbytes) + ", \"shape\": [";
+        for (size_t d = 0; d < t.shape.size(); d++) j += (d ? ", " : "") + std::to_string(t.shape[d]);
+        j += "]}";
+    }
+    j += "]}";
+    if (j.size() + 1 > cap) return -1;
+    memcpy(out, j.c_str(), j.size() + 1);
+    return (int)j.size();
+}
+int nt_tokenize(const char* gguf_path, const char* text, int add_bos, int* ids, int cap) {
+    if (!gguf_path || !text) return -1;
+    GGUFFile f;
+    if (!f.open(gguf_path)) return -1;
+    Tokenizer t;
+    t.init(f.vocab(), f.config().bos_token_id, f.config().eos_token_id);
+    std::vector<int> v = t.encode(text, add_bos != 0);
+    for (int i = 0; i < (int)v.size() && i < cap; i++) ids[i] = v[(size_t)i];
+    return (int)v.size();
+}
+int nt_detokenize(const char* gguf_path, const int* ids, int n, char* out, size_t cap) {
+    if (!gguf_path || !out || !cap) return -1;
+    GGUFFile f;
+    if (!f.open(gguf_path)) return -1;
+    Tokenizer t;
+    t.init(f.vocab(), f.config().bos_token_id, f.config().eos_token_id);
+    std::string s = t.decode(std::vector<int>(ids, ids + n));
+    if (s.size() + 1 > cap) return -1;
+    memcpy(out, s.data(), s.size());
+    out[s.size()] = 0;
+    return (int)s.size();
+}
+int nt_sample_token(const float* logits, int n, float temperature, int top_k, float top_p, float repeat_penalty,
+                    int repeat_window, const int* recent, int n_recent, uint64_t seed) {
+    if (!logits || n <= 0) return -1;
+    SamplerConfig sc;
+    sc.temperature = temperature; sc.top_k = top_k; sc.top_p = top_p; sc.repeat_penalty = repeat_penalty;
+    sc.repeat_window = repeat_window; sc.seed = seed;
+    Sampler s;
+    s.init(sc);
+    std::vector<float> l(logits, logits + n);
+    s.apply_repeat_penalty(l.data(), n, std::vector<int>(recent, recent + (recent ? n_recent : 0)));
+    return s.sample(l.data(), n);
+}
+
+int nt_tp_unique_id(void* out128) { return TPComm::unique_id(out128) ? 0 : -1; }
+int nt_tp_init(nt_model_t m, const void* id128, int rank, int size) {
+    if (!m) return -1;
+    auto c = std::make_unique<TPComm>();
+    if (!c->init(id128, rank, size)) return -2;
+    H(m)->model.set_comm(c.get());
+    H(m)->comm = std::move(c);
+    return 0;
+}
+}  // extern "C"

@@ -1,0 +1,103 @@
+#include "engine.h"
+#include <chrono>
+#include <iostream>
+
+namespace nt { namespace b200 {
+using Clock = std::chrono::steady_clock;
+static float ms_since(Clock::time_point t0) { return std::chrono::duration<float, std::milli>(Clock::now() - t0).count(); }
+
+bool Engine::load(const std::string& path, int max_context) {
+    if (!model_.load_gguf(path, max_context)) return false;
+    tok_.init(model_.vocab(), model_.config().bos_token_id, model_.config().eos_token_id);
+    return true;
+}
+
+std::string Engine::generate(const std::string& prompt, const GenerateConfig& cfg, TokenCallback cb) {
+    Stats st;
+    Sampler sampler;
+    SamplerConfig sc;
+    sc.temperature = cfg.temperature; sc.top_k = cfg.top_k; sc.top_p = cfg.top_p;
+    sc.repeat_penalty = cfg.repeat_penalty; sc.repeat_window = cfg.repeat_window; sc.seed = cfg.seed;
+    sampler.init(sc);
+
+    std::vector<int> tokens = tok_.encode(prompt, true);
+    st.prompt_tokens = (int)tokens.size();
+    if (cfg.verbose) fprintf(stderr, "Prompt tokens: %d\n", st.prompt_tokens);
+    const int vocab = model_.config().vocab_size;
+    std::vector<float> logits((size_t)vocab);
+    // Greedy without a repeat penalty needs no logits on the host: argmax runs on the GPU (4 B D2H instead of 513 KB).
+    const bool gpu_greedy = cfg.temperature <= 0.0f && cfg.repeat_penalty <= 1.0f;
+    auto next_from = [&](float* dev_logits) {
+        if (gpu_greedy) return model_.argmax_last();
+        NT_CUDA_CHECK(cudaMemcpy(logits.data(), dev_logits, sizeof(float) * (size_t)vocab, cudaMemcpyDeviceToHost));
+        sampler.apply_repeat_penalty(logits.data(), vocab, tokens);
+        return sampler.sample(logits.data(), vocab);
+    };
+
+    model_.clear_kv();
+    auto t0 = Clock::now();
+    float* dl = model_.forward(tokens.data(), (int)tokens.size(), 0);
+    st.prefill_ms = ms_since(t0);
+    int next = next_from(dl);
+    tokens.push_back(next);
+    std::string out, piece = tok_.decode_token(next);
+    out += piece;
+    bool stop = false;
+    if (cb) stop = !cb(piece, next);
+    else if (cfg.verbose) { fputs(piece.c_str(), stdout); fflush(stdout); }
+
+    if (!stop) {
+        auto d0 = Clock::now();
+        int pos = st.prompt_tokens;
+        for (int i = 1; i < cfg.max_tokens; i++) {
+            if (next == tok_.eos_id()) break;
+            if (pos >= model_.config().max_seq_len) break;           // the reference silently overruns its cache here
+            dl = model_.forward(&next, 1, pos++);
+            next = next_from(dl);
+            tokens.push_back(next);
+            piece = tok_.decode_token(next);
+            out += piece;
+            st.gen_tokens++;
+            if (cb) { if (!cb(piece, next)) break; }
+            else if (cfg.verbose) { fputs(piece.c_str(), stdout); fflush(stdout); }
+        }
+        st.decode_ms = ms_since(d0);
+    }
+    stats_ = st;
+    if (cfg.verbose) { fputc('\n', stdout); print_stats(st); }
+    return out;
+}
+
+void Engine::chat(const GenerateConfig& cfg) {
+    fprintf(stderr, "\n=== NTransformer Chat ===\nType your message and press Enter. Type 'quit' to exit.\n\n");
+    std::string line;
+    for (;;) {
+        fputs("> ", stdout); fflush(stdout);
+        if (!std::getline(std::cin, line)) break;
+        if (line == "quit" || line == "exit") break;
+        if (line.empty()) continue;
+        generate(line, cfg);                                         // stateless turns, like the reference
+        fputc('\n', stdout);
+    }
+}
+
+void Engine::benchmark(const std::string& prompt, int n_tokens) {
+    GenerateConfig cfg;
+    cfg.max_tokens = n_tokens; cfg.temperature = 0.0f; cfg.verbose = false;
+    fprintf(stderr, "=== Benchmark ===\nPrompt: \"%s\"\nMax tokens: %d\n", prompt.c_str(), n_tokens);
+    auto t0 = Clock::now();
+    std::string out = generate(prompt, cfg);
+    fprintf(stderr, "Total time: %.1f ms\nOutput length: %zu chars\n", ms_since(t0), out.size());
+    print_stats(stats_);                                             // (the reference prints no tok/s here, quirk Q5)
+}
+
+void Engine::print_stats(const Stats& s) const {
+    fprintf(stderr, "\n--- Stats ---\n");
+    fprintf(stderr, "Prompt: %d tokens, %.1f ms (%.1f tok/s)\n", s.prompt_tokens, s.prefill_ms, s.prompt_tokens / (s.prefill_ms / 1000.0f));
+    fprintf(stderr, "Decode: %d tokens, %.1f ms (%.1f tok/s)\n", s.gen_tokens, s.decode_ms, s.gen_tokens / (s.decode_ms / 1000.0f));
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    fprintf(stderr, "VRAM: %.1f / %.1f GB\n", (tot - fr) / (1024.0 * 1024 * 1024), tot / (1024.0 * 1024 * 1024));
+}
+
+}}  // namespace nt::b200

@@ -1,0 +1,45 @@
+// engine.h — text generation over the resident model: the reference's nt::Engine plain path
+// (src/inference/engine.h:31-65, engine.cpp:16-23 load, :40-145 generate, :557-593 chat/benchmark, :595-607 stats).
+// Speculative / self-speculative variants exist in the reference only to hide PCIe streaming and are out of scope.
+#pragma once
+#include <functional>
+#include <string>
+#include "model.h"
+#include "text.h"
+
+namespace nt { namespace b200 {
+
+struct GenerateConfig {             // defaults of engine.h:17-26
+    int max_tokens = 256;
+    float temperature = 0.7f;
+    int top_k = 40;
+    float top_p = 0.9f;
+    float repeat_penalty = 1.1f;
+    int repeat_window = 64;
+    uint64_t seed = 42;
+    bool verbose = true;
+};
+using TokenCallback = std::function<bool(const std::string& token, int token_id)>;
+
+class Engine {
+public:
+    bool load(const std::string& model_path, int max_context = 4096);
+    std::string generate(const std::string& prompt, const GenerateConfig& cfg, TokenCallback cb = nullptr);
+    void chat(const GenerateConfig& cfg);
+    void benchmark(const std::string& prompt, int n_tokens);
+    const ModelConfig& config() const { return model_.config(); }
+    Model& model() { return model_; }
+    const Tokenizer& tokenizer() const { return tok_; }
+    struct Stats {
+        int prompt_tokens = 0, gen_tokens = 0;
+        float prefill_ms = 0, decode_ms = 0;
+    };
+    const Stats& last_stats() const { return stats_; }
+private:
+    void print_stats(const Stats& s) const;
+    Model model_;
+    Tokenizer tok_;
+    Stats stats_;
+};
+
+}}  // namespace nt::b200

@@ -1,0 +1,378 @@
+// model.cu — see model.h.
+#include "model.h"
+#include "tp_comm.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace nt { namespace b200 {
+
+namespace {
+
+__global__ void set_step_kernel(int* step, int token, int pos) { step[0] = token; step[1] = pos; }
+
+// argmax over n floats, lowest index wins ties (reference Sampler::argmax, sampler.cpp:18-28)
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ x, int n, int* __restrict__ out) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    float best = -FLT_MAX;
+    int bi = 0x7FFFFFFF;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = x[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = sv[threadIdx.x]; bi = si[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) *out = bi;
+    }
+}
+
+template <typename T> T* dmalloc(size_t n) {
+    T* p = nullptr;
+    NT_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+}  // namespace
+
+Model::~Model() {
+    release_graphs();
+    for (void* p : owned_) cudaFree(p);
+    for (void* p : {(void*)hidden_, (void*)xnorm_, (void*)q_, (void*)k_, (void*)v_, (void*)attn_, (void*)act_, (void*)up_, (void*)part_,
+                    (void*)logits_, (void*)logits_l_, (void*)attn_scratch_, xq_h_, xq_a_, xq_i_, kc_, vc_, (void*)step_dev_,
+                    (void*)argmax_dev_})
+        if (p) cudaFree(p);
+    if (argmax_host_) cudaFreeHost(argmax_host_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Model::release_graphs() {
+    if (g_full_) { cudaGraphExecDestroy(g_full_); g_full_ = nullptr; }
+    if (g_body_) { cudaGraphExecDestroy(g_body_); g_body_ = nullptr; }
+}
+
+void Model::init(const ModelConfig& cfg, int tp_rank, int tp_size) {
+    cfg_ = cfg;
+    tp_rank_ = tp_rank;
+    tp_size_ = tp_size;
+    NT_CHECK(tp_size >= 1 && tp_rank >= 0 && tp_rank < tp_size, "bad tensor-parallel rank/size");
+    NT_CHECK(cfg.n_heads % tp_size == 0 && cfg.n_kv_heads % tp_size == 0, "heads must divide by tp_size");
+    NT_CHECK(cfg.intermediate_size % tp_size == 0, "intermediate_size must divide by tp_size");
+    nh_l_ = cfg.n_heads / tp_size;
+    nkv_l_ = cfg.n_kv_heads / tp_size;
+    inter_l_ = cfg.intermediate_size / tp_size;
+    vocab_l_ = (cfg.vocab_size + tp_size - 1) / tp_size;
+    layers_.assign((size_t)cfg.n_layers, LayerWeights{});
+}
+
+bool Model::set_tensor(const std::string& name, const void* ptr, DType dt, size_t pitch) {
+    const int hidden = cfg_.hidden_size, hd = cfg_.head_dim;
+    auto W = [&](Weight& w, int rows, int cols) {
+        w.ptr = ptr; w.dtype = dt; w.rows = rows; w.cols = cols;
+        w.pitch = pitch ? pitch : dtype_row_size(dt, (size_t)cols);
+        w.owned = false;
+        return true;
+    };
+    if (name == "token_embd.weight") return W(embd_, cfg_.vocab_size, hidden);
+    if (name == "output.weight") {
+        int rows = (tp_size_ == 1) ? cfg_.vocab_size : std::max(0, std::min(vocab_l_, cfg_.vocab_size - tp_rank_ * vocab_l_));
+        return W(head_, rows, hidden);
+    }
+    if (name == "output_norm.weight") { out_norm_ = static_cast<const float*>(ptr); return true; }
+    int li = -1;
+    char field[64] = {0};
+    if (sscanf(name.c_str(), "blk.%d.%63s", &li, field) != 2 || li < 0 || li >= cfg_.n_layers) return false;
+    LayerWeights& L = layers_[(size_t)li];
+    const std::string f = field;
+    if (f == "attn_norm.weight") { L.attn_norm = static_cast<const float*>(ptr); return true; }
+    if (f == "ffn_norm.weight") { L.ffn_norm = static_cast<const float*>(ptr); return true; }
+    if (f == "attn_q.weight") return W(L.wq, nh_l_ * hd, hidden);
+    if (f == "attn_k.weight") return W(L.wk, nkv_l_ * hd, hidden);
+    if (f == "attn_v.weight") return W(L.wv, nkv_l_ * hd, hidden);
+    if (f == "attn_output.weight") return W(L.wo, hidden, nh_l_ * hd);
+    if (f == "ffn_gate.weight") return W(L.gate, inter_l_, hidden);
+    if (f == "ffn_up.weight") return W(L.up, inter_l_, hidden);
+    if (f == "ffn_down.weight") return W(L.down, hidden, inter_l_);
+    return false;
+}
+
+// Uploads tensor `name` (sharded) and fills *w. split: 0 replicate, 1 rows, 2 columns (quant-block aligned).
+const void* Model::upload(const GGUFFile& f, const std::string& name, Weight* w, int split) {
+    const GGUFTensorInfo* ti = f.find(name);
+    NT_CHECK(ti != nullptr, ("Tensor not found: " + name).c_str());
+    const uint8_t* src = static_cast<const uint8_t*>(f.data(*ti));
+    const DType dt = ti->dtype;
+    const int cols = (int)ti->shape[0];
+    const int rows = ti->shape.size() > 1 ? (int)ti->shape[1] : 1;
+    const size_t row_bytes = dtype_row_size(dt, (size_t)cols);
+    void* dst = nullptr;
+    if (split == 0 || tp_size_ == 1) {
+        NT_CUDA_CHECK(cudaMalloc(&dst, std::max<size_t>(ti->nbytes, 16)));
+        NT_CUDA_CHECK(cudaMemcpy(dst, src, ti->nbytes, cudaMemcpyHostToDevice));
+        if (w) { w->rows = rows; w->cols = cols; w->pitch = row_bytes; }
+    } else if (split == 1) {
+        int per = (rows + tp_size_ - 1) / tp_size_;
+        int r0 = std::min(rows, tp_rank_ * per), r1 = std::min(rows, r0 + per);
+        size_t bytes = (size_t)(r1 - r0) * row_bytes;
+        NT_CUDA_CHECK(cudaMalloc(&dst, std::max<size_t>(bytes, 16)));
+        if (bytes) NT_CUDA_CHECK(cudaMemcpy(dst, src + (size_t)r0 * row_bytes, bytes, cudaMemcpyHostToDevice));
+        if (w) { w->rows = r1 - r0; w->cols = cols; w->pitch = row_bytes; }
+    } else {
+        const int bs = (int)dtype_block_size(dt);
+        NT_CHECK(cols % tp_size_ == 0 && (cols / tp_size_) % bs == 0, "column shard is not quant-block aligned");
+        const int c_l = cols / tp_size_;
+        const size_t shard_row = dtype_row_size(dt, (size_t)c_l);
+        const size_t pitch = round16(shard_row);                // rows start 16 B aligned for the TMA path
+        NT_CUDA_CHECK(cudaMalloc(&dst, std::max<size_t>(pitch * rows, 16)));
+        NT_CUDA_CHECK(cudaMemset(dst, 0, pitch * rows));
+        NT_CUDA_CHECK(cudaMemcpy2D(dst, pitch, src + (size_t)tp_rank_ * shard_row, row_bytes, shard_row, (size_t)rows,
+                                   cudaMemcpyHostToDevice));
+        if (w) { w->rows = rows; w->cols = c_l; w->pitch = pitch; }
+    }
+    owned_.push_back(dst);
+    if (w) { w->ptr = dst; w->dtype = dt; w->owned = true; }
+    return dst;
+}
+
+bool Model::load_gguf(const std::string& path, int max_context, int tp_rank, int tp_size) {
+    fprintf(stderr, "Loading model: %s\n", path.c_str());
+    GGUFFile f;
+    if (!f.open(path)) return false;
+    ModelConfig cfg = f.config();
+    if (cfg.max_seq_len > max_context) {          // transformer.cpp:70-74
+        fprintf(stderr, "Note: Capping context from %d to %d tokens (use --ctx-size to change)\n", cfg.max_seq_len, max_context);
+        cfg.max_seq_len = max_context;
+    }
+    cfg.print();
+    f.print_info();
+    vocab_ = f.vocab();
+    init(cfg, tp_rank, tp_size);
+
+    upload(f, "token_embd.weight", &embd_, 0);
+    if (embd_.dtype == DType::Q5_K)
+        fprintf(stderr, "Error: Unsupported embedding dtype: Q5_K (rows read as zeros, like the reference)\n");
+    if (f.find("output.weight")) {
+        upload(f, "output.weight", &head_, 1);
+    } else if (tp_size_ == 1) {
+        head_ = embd_;                               // tied embeddings (transformer.cpp:96-99)
+        head_.owned = false;
+    } else {
+        upload(f, "token_embd.weight", &head_, 1);
+    }
+    out_norm_ = static_cast<const float*>(upload(f, "output_norm.weight", nullptr, 0));
+    for (int i = 0; i < cfg_.n_layers; i++) {
+        const std::string p = "blk." + std::to_string(i) + ".";
+        LayerWeights& L = layers_[(size_t)i];
+        L.attn_norm = static_cast<const float*>(upload(f, p + "attn_norm.weight", nullptr, 0));
+        upload(f, p + "attn_q.weight", &L.wq, 1);
+        upload(f, p + "attn_k.weight", &L.wk, 1);
+        upload(f, p + "attn_v.weight", &L.wv, 1);
+        upload(f, p + "attn_output.weight", &L.wo, 2);
+        L.ffn_norm = static_cast<const float*>(upload(f, p + "ffn_norm.weight", nullptr, 0));
+        upload(f, p + "ffn_gate.weight", &L.gate, 1);
+        upload(f, p + "ffn_up.weight", &L.up, 1);
+        upload(f, p + "ffn_down.weight", &L.down, 2);
+        if ((i & 7) == 7 || i + 1 == cfg_.n_layers) fprintf(stderr, "  Loaded layer %d/%d\n", i + 1, cfg_.n_layers);
+    }
+    if (!finalize()) return false;
+    fprintf(stderr, "Model loaded successfully!\n");
+    return true;
+}
+
+bool Model::finalize() {
+    const int hidden = cfg_.hidden_size, hd = cfg_.head_dim;
+    if (!embd_.ptr || !out_norm_) { fprintf(stderr, "model: token_embd / output_norm missing\n"); return false; }
+    if (!head_.ptr) {
+        if (tp_size_ != 1) { fprintf(stderr, "model: output.weight shard missing\n"); return false; }
+        head_ = embd_; head_.owned = false;
+    }
+    for (int i = 0; i < cfg_.n_layers; i++) {
+        const LayerWeights& L = layers_[(size_t)i];
+        if (!L.attn_norm || !L.ffn_norm || !L.wq.ptr || !L.wk.ptr || !L.wv.ptr || !L.wo.ptr || !L.gate.ptr || !L.up.ptr || !L.down.ptr) {
+            fprintf(stderr, "model: layer %d is missing tensors\n", i);
+            return false;
+        }
+    }
+    NT_CHECK(hidden % 32 == 0 && (nh_l_ * hd) % 32 == 0 && inter_l_ % 32 == 0, "dimensions must be multiples of 32");
+    NT_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    const int max_seq = cfg_.max_seq_len;
+    hidden_ = dmalloc<float>(hidden);
+    xnorm_ = dmalloc<float>(hidden);
+    q_ = dmalloc<float>((size_t)nh_l_ * hd);
+    k_ = dmalloc<float>((size_t)nkv_l_ * hd);
+    v_ = dmalloc<float>((size_t)nkv_l_ * hd);
+    attn_ = dmalloc<float>((size_t)nh_l_ * hd);
+    act_ = dmalloc<float>(inter_l_);
+    up_ = dmalloc<float>(inter_l_);
+    part_ = dmalloc<float>(hidden);
+    logits_ = dmalloc<float>((size_t)vocab_l_ * tp_size_);
+    logits_l_ = dmalloc<float>(vocab_l_);
+    attn_scratch_ = dmalloc<float>(attention_decode_dyn_scratch_floats(max_seq, nh_l_, nkv_l_, hd));
+    xq_h_ = dmalloc<uint8_t>(xq_bytes(hidden));
+    xq_a_ = dmalloc<uint8_t>(xq_bytes(nh_l_ * hd));
+    xq_i_ = dmalloc<uint8_t>(xq_bytes(inter_l_));
+    const size_t kv_elems = (size_t)cfg_.n_layers * max_seq * nkv_l_ * hd;     // F16 [L, max_seq, n_kv, hd], transformer.cpp:340-346
+    kc_ = dmalloc<uint16_t>(kv_elems);
+    vc_ = dmalloc<uint16_t>(kv_elems);
+    NT_CUDA_CHECK(cudaMemset(kc_, 0, kv_elems * 2));
+    NT_CUDA_CHECK(cudaMemset(vc_, 0, kv_elems * 2));
+    NT_CUDA_CHECK(cudaMemset(logits_, 0, sizeof(float) * (size_t)vocab_l_ * tp_size_));
+    step_dev_ = dmalloc<int>(2);
+    argmax_dev_ = dmalloc<int>(1);
+    NT_CUDA_CHECK(cudaMallocHost(&argmax_host_, sizeof(int)));
+    finalized_ = true;
+    return true;
+}
+
+void Model::clear_kv() {
+    const size_t kv_elems = (size_t)cfg_.n_layers * cfg_.max_seq_len * nkv_l_ * cfg_.head_dim;
+    NT_CUDA_CHECK(cudaMemsetAsync(kc_, 0, kv_elems * 2, stream_));
+    NT_CUDA_CHECK(cudaMemsetAsync(vc_, 0, kv_elems * 2, stream_));
+}
+
+size_t Model::weight_bytes() const {
+    size_t b = head_.bytes() + (size_t)(2 * cfg_.n_layers + 1) * cfg_.hidden_size * 4;
+    for (const LayerWeights& L : layers_) b += L.wq.bytes() + L.wk.bytes() + L.wv.bytes() + L.wo.bytes() + L.gate.bytes() + L.up.bytes() + L.down.bytes();
+    return b;
+}
+size_t Model::bytes_per_token(int ctx) const {
+    return weight_bytes() + (size_t)2 * cfg_.n_layers * ctx * nkv_l_ * cfg_.head_dim * 2;
+}
+
+// y_i = W_i . x for n matrices sharing x; picks the fused TMA/dp4a kernel when every matrix qualifies.
+void Model::matvec(const Weight* const* ws, float* const* ys, int n, const float* x_f32, const void* xq, GemvEpilogue ep,
+                   cudaStream_t s) {
+    GemvMat mats[3];
+    const int K = ws[0]->cols;
+    for (int i = 0; i < n; i++) { mats[i].W = ws[i]->ptr; mats[i].y = ys[i]; mats[i].out = ws[i]->rows; mats[i].dtype = ws[i]->dtype; mats[i].row_pitch = ws[i]->pitch; }
+    if (gemv_kq_supported(mats, n, K)) { gemv_kq(mats, n, K, xq, ep, s); return; }
+    if (ep == GEMV_SWIGLU) {           // unfused fallback: gate -> ys[0], up -> ys[1], then silu_mul in place
+        const Weight* g = ws[0]; const Weight* u = ws[1];
+        matvec(&g, &ys[0], 1, x_f32, xq, GEMV_STORE, s);
+        matvec(&u, &ys[1], 1, x_f32, xq, GEMV_STORE, s);
+        silu_mul(ys[0], ys[0], ys[1], ws[0]->rows, s);
+        return;
+    }
+    for (int i = 0; i < n; i++) {
+        if (gemv_kq_supported(&mats[i], 1, K)) gemv_kq(&mats[i], 1, K, xq, ep, s);
+        else gemv_generic(ys[i], ws[i]->ptr, x_f32, ws[i]->rows, K, ws[i]->dtype, ws[i]->pitch, ep, s);
+    }
+}
+
+// hidden += all_reduce(partial)   (one exchange per sub-block)
+void Model::reduce_residual(float* partial, cudaStream_t s) {
+    NT_CHECK(comm_ != nullptr, "tensor-parallel model without a communicator");
+    comm_->all_reduce_sum(partial, (size_t)cfg_.hidden_size, s);
+    add_inplace(hidden_, partial, cfg_.hidden_size, s);
+}
+
+void Model::step_body(cudaStream_t s) {
+    const int hidden = cfg_.hidden_size, hd = cfg_.head_dim, max_seq = cfg_.max_seq_len;
+    const float scale = 1.0f / sqrtf((float)hd);                         // attention.cpp:21
+    const size_t kv_stride = (size_t)max_seq * nkv_l_ * hd;               // transformer.cpp:629
+    const int* pos_dev = step_dev_ + 1;
+    embed_rows(hidden_, embd_.ptr, embd_.dtype, step_dev_, 1, hidden, s);
+    for (int i = 0; i < cfg_.n_layers; i++) {
+        const LayerWeights& L = layers_[(size_t)i];
+        uint16_t* kc = static_cast<uint16_t*>(kc_) + (size_t)i * kv_stride;
+        uint16_t* vc = static_cast<uint16_t*>(vc_) + (size_t)i * kv_stride;
+        // --- attention sub-block ---
+        rmsnorm_xq(xnorm_, xq_h_, hidden_, L.attn_norm, hidden, cfg_.norm_eps, s);
+        { const Weight* ws[3] = {&L.wq, &L.wk, &L.wv}; float* ys[3] = {q_, k_, v_}; matvec(ws, ys, 3, xnorm_, xq_h_, GEMV_STORE, s); }
+        rope_kv_decode(q_, k_, v_, kc, vc, pos_dev, nh_l_, nkv_l_, hd, cfg_.rope_theta, cfg_.rope_freq_scale, max_seq, s);
+        attention_decode_dyn(attn_, q_, kc, vc, pos_dev, max_seq, nh_l_, nkv_l_, hd, scale, attn_scratch_, s);
+        quantize_x(attn_, xq_a_, nh_l_ * hd, s);
+        { const Weight* ws[1] = {&L.wo};
+          if (tp_size_ == 1) { float* ys[1] = {hidden_}; matvec(ws, ys, 1, attn_, xq_a_, GEMV_ADD, s); }
+          else { float* ys[1] = {part_}; matvec(ws, ys, 1, attn_, xq_a_, GEMV_STORE, s); reduce_residual(part_, s); } }
+        // --- FFN sub-block ---
+        rmsnorm_xq(xnorm_, xq_h_, hidden_, L.ffn_norm, hidden, cfg_.norm_eps, s);
+        { const Weight* ws[2] = {&L.gate, &L.up}; float* ys[2] = {act_, up_}; matvec(ws, ys, 2, xnorm_, xq_h_, GEMV_SWIGLU, s); }
+        quantize_x(act_, xq_i_, inter_l_, s);
+        { const Weight* ws[1] = {&L.down};
+          if (tp_size_ == 1) { float* ys[1] = {hidden_}; matvec(ws, ys, 1, act_, xq_i_, GEMV_ADD, s); }
+          else { float* ys[1] = {part_}; matvec(ws, ys, 1, act_, xq_i_, GEMV_STORE, s); reduce_residual(part_, s); } }
+    }
+}
+
+void Model::step_head(cudaStream_t s) {
+    const int hidden = cfg_.hidden_size;
+    rmsnorm_xq(xnorm_, xq_h_, hidden_, out_norm_, hidden, cfg_.norm_eps, s);      // transformer.cpp:657-659
+    const Weight* ws[1] = {&head_};
+    if (tp_size_ == 1) {
+        float* ys[1] = {logits_};
+        matvec(ws, ys, 1, xnorm_, xq_h_, GEMV_STORE, s);
+    } else {
+        float* ys[1] = {logits_l_};
+        if (head_.rows > 0) matvec(ws, ys, 1, xnorm_, xq_h_, GEMV_STORE, s);
+        comm_->all_gather(logits_l_, logits_, (size_t)vocab_l_, s);
+    }
+}
+
+void Model::run_step(bool with_head) {
+    if (!use_graph_) {
+        step_body(stream_);
+        if (with_head) step_head(stream_);
+        return;
+    }
+    cudaGraphExec_t& g = with_head ? g_full_ : g_body_;
+    int& n_kernels = with_head ? n_full_ : n_body_;
+    if (!g) {
+        cudaGraph_t graph = nullptr;
+        const unsigned long long before = launch_count();
+        NT_CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        step_body(stream_);
+        if (with_head) step_head(stream_);
+        NT_CUDA_CHECK(cudaStreamEndCapture(stream_, &graph));
+        NT_CUDA_CHECK(cudaGraphInstantiate(&g, graph, 0));
+        NT_CUDA_CHECK(cudaGraphDestroy(graph));
+        n_kernels = (int)(launch_count() - before);   // counted once during capture == the first replay below
+        NT_CUDA_CHECK(cudaGraphLaunch(g, stream_));
+        return;
+    }
+    NT_CUDA_CHECK(cudaGraphLaunch(g, stream_));
+    count_launch(n_kernels);                           // a replay re-runs every captured kernel
+}
+
+void Model::forward_async(const int* tokens, int seq_len, int start_pos) {
+    NT_CHECK(finalized_, "Model::forward before finalize/load");
+    NT_CHECK(seq_len >= 1, "forward: empty token list");
+    NT_CHECK(start_pos >= 0 && start_pos + seq_len <= cfg_.max_seq_len, "forward: position beyond the KV cache (max_seq_len)");
+    for (int t = 0; t < seq_len; t++) {
+        int tok = tokens[t];
+        NT_CHECK(tok >= 0 && tok < cfg_.vocab_size, "token id out of range");
+        set_step_kernel<<<1, 1, 0, stream_>>>(step_dev_, tok, start_pos + t);
+        count_launch();
+        run_step(t == seq_len - 1);
+    }
+}
+
+float* Model::forward(const int* tokens, int seq_len, int start_pos) {
+    forward_async(tokens, seq_len, start_pos);
+    NT_CUDA_CHECK(cudaStreamSynchronize(stream_));                           // transformer.cpp:667
+    return logits_;
+}
+
+int Model::argmax_last() {
+    argmax_kernel<<<1, 1024, 0, stream_>>>(logits_, cfg_.vocab_size, argmax_dev_);
+    NT_CUDA_CHECK(cudaMemcpyAsync(argmax_host_, argmax_dev_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    return *argmax_host_;
+}
+
+}}  // namespace nt::b200

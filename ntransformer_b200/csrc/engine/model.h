@@ -1,0 +1,112 @@
+// model.h — resident Llama-family forward on one GPU (or one tensor-parallel rank).
+//
+// Host-side counterpart of the reference's nt::Transformer resident branch
+// (src/model/transformer.cpp:59-126 load, :286-391 layers/buffers, :604-669 forward) with the per-layer
+// launch sequence of Attention::forward (src/model/attention.cpp:120-211) and FFN::forward
+// (src/model/ffn.cpp:85-134) re-expressed as fused sm_100a launches captured in a CUDA graph:
+//   reference: 15 launches / layer / token, CPU embedding dequant, 2 sync H2D + 1 sync D2H per token;
+//   here:      10 launches / layer / token in one graph replay, embedding gathered on the GPU.
+// The streaming / tiered / speculative branches of the reference are out of scope.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../kernels_internal.h"
+#include "gguf.h"
+
+namespace nt { namespace b200 {
+
+class TPComm;    // NCCL communicator (engine/tp_comm.cpp); null when tp_size == 1
+
+struct Weight {
+    const void* ptr = nullptr;   // device, GGUF block layout, this rank's shard
+    DType dtype = DType::F32;
+    int rows = 0, cols = 0;      // shard shape (out_features, in_features)
+    size_t pitch = 0;            // bytes between rows
+    bool owned = false;
+    size_t bytes() const { return (size_t)rows * dtype_row_size(dtype, (size_t)cols); }   // algorithmic bytes
+};
+
+struct LayerWeights {
+    const float* attn_norm = nullptr;
+    const float* ffn_norm = nullptr;
+    Weight wq, wk, wv, wo, gate, up, down;
+};
+
+class Model {
+public:
+    Model() = default;
+    ~Model();
+    Model(const Model&) = delete;
+    Model& operator=(const Model&) = delete;
+
+    // (a) from a GGUF file: parse, shard for (tp_rank, tp_size), upload, allocate, capture.
+    bool load_gguf(const std::string& path, int max_context, int tp_rank = 0, int tp_size = 1);
+    // (b) from caller-owned device tensors (synthetic benchmarks): init -> set_tensor* -> finalize.
+    void init(const ModelConfig& cfg, int tp_rank = 0, int tp_size = 1);
+    bool set_tensor(const std::string& gguf_name, const void* dev_ptr, DType dtype, size_t row_pitch = 0);
+    bool finalize();
+
+    void set_comm(TPComm* comm) { comm_ = comm; }
+
+    // Runs seq_len tokens at positions start_pos.. and returns DEVICE logits [vocab] of the last token
+    // (same contract as Transformer::forward, transformer.cpp:604-669; synchronises the stream).
+    float* forward(const int* tokens, int seq_len, int start_pos);
+    // Asynchronous variant used by the benchmark: no host sync.
+    void forward_async(const int* tokens, int seq_len, int start_pos);
+    // Greedy next token computed on the GPU from the last logits (argmax, lowest index on ties like Sampler::argmax).
+    int argmax_last();
+
+    const ModelConfig& config() const { return cfg_; }
+    const GGUFVocab& vocab() const { return vocab_; }
+    cudaStream_t stream() const { return stream_; }
+    float* logits_device() const { return logits_; }
+    int tp_rank() const { return tp_rank_; }
+    int tp_size() const { return tp_size_; }
+    // Algorithmic bytes this rank reads per decoded token at context length ctx (SURVEY §8d B_tok).
+    size_t bytes_per_token(int ctx) const;
+    size_t weight_bytes() const;
+    void set_use_graph(bool on) { use_graph_ = on; }
+    void clear_kv();
+
+private:
+    void step_body(cudaStream_t s);      // embedding + all layers for the token/position in step_dev_
+    void step_head(cudaStream_t s);      // final norm + LM head (+ all-gather under TP)
+    void run_step(bool with_head);
+    void matvec(const Weight* const* ws, float* const* ys, int n, const float* x_f32, const void* xq, GemvEpilogue ep,
+                cudaStream_t s);
+    void reduce_residual(float* partial, cudaStream_t s);
+    const void* upload(const GGUFFile& f, const std::string& name, Weight* w, int split /*0 none,1 rows,2 cols*/);
+    void release_graphs();
+
+    ModelConfig cfg_;
+    GGUFVocab vocab_;
+    int tp_rank_ = 0, tp_size_ = 1;
+    int nh_l_ = 0, nkv_l_ = 0;           // local heads
+    int inter_l_ = 0, vocab_l_ = 0;      // local FFN columns / vocab rows
+    TPComm* comm_ = nullptr;
+
+    Weight embd_, head_;
+    const float* out_norm_ = nullptr;
+    std::vector<LayerWeights> layers_;
+    std::vector<void*> owned_;
+
+    // device buffers
+    cudaStream_t stream_ = nullptr;
+    float *hidden_ = nullptr, *xnorm_ = nullptr, *q_ = nullptr, *k_ = nullptr, *v_ = nullptr, *attn_ = nullptr;
+    float *act_ = nullptr, *up_ = nullptr, *part_ = nullptr, *logits_ = nullptr, *logits_l_ = nullptr, *attn_scratch_ = nullptr;
+    void *xq_h_ = nullptr, *xq_a_ = nullptr, *xq_i_ = nullptr;
+    void *kc_ = nullptr, *vc_ = nullptr;
+    int* step_dev_ = nullptr;            // [0] token, [1] position
+    int* step_host_ = nullptr;           // pinned staging, ring of 64 (token, pos) pairs
+    int step_slot_ = 0;
+    int* argmax_dev_ = nullptr;
+    int* argmax_host_ = nullptr;
+
+    bool use_graph_ = true;
+    cudaGraphExec_t g_full_ = nullptr, g_body_ = nullptr;
+    int n_full_ = 0, n_body_ = 0;        // kernels per graph replay
+    bool finalized_ = false;
+};
+
+}}  // namespace nt::b200

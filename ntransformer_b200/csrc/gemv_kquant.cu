@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
         }
         const KqMat& m = p.mat[mi];
         int nbc = min(BS, p.NB - chunk * BS);
-        uint32_t bytes = (uint32_t)(nbc * m.blk_bytes);
+        // copy size rounded up to 16 B (a 210-byte Q6_K tail may spill into the row's padding; checked on the host)
+        uint32_t bytes = ((uint32_t)(nbc * m.blk_bytes) + 15u) & ~15u;
         uint64_t* bar = bars + slot;
         mbar_expect_tx(bar, bytes * RG);
         uint8_t* dst = ring + (size_t)slot * p.slot_bytes;
@@ -405,7 +406,11 @@ bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K) {
         if (f < 0 || mats[i].out <= 0) return false;
         size_t pitch = mats[i].row_pitch ? mats[i].row_pitch : dtype_row_size(mats[i].dtype, K);
         if ((reinterpret_cast<uintptr_t>(mats[i].W) & 15) || (pitch & 15)) return false;
-        if (K / 256 > BS && (BS * dtype_size(mats[i].dtype)) % 16 != 0) return false;
+        // the last chunk of a row is copied in 16-byte units and must stay inside the row pitch
+        const size_t blk = dtype_size(mats[i].dtype);
+        const int NB = K / 256, NC = (NB + BS - 1) / BS, last = NB - (NC - 1) * BS;
+        const size_t tail_end = (size_t)(NC - 1) * BS * blk + ((last * blk + 15) & ~(size_t)15);
+        if (tail_end > pitch) return false;
     }
     return true;
 }

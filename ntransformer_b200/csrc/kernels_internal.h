@@ -65,6 +65,14 @@ void attention_decode(float* out, const float* q, const void* kc, const void* vc
                       int n_kv, int hd, int max_seq, float scale, cudaStream_t s);
 void attention_prefill(float* out, const float* Q, const void* kc, const void* vc, int seq_len, int start_pos,
                        int n_heads, int n_kv, int hd, int max_seq, float scale, cudaStream_t s);
+// CUDA-graph friendly decode attention: context length = *pos_dev + 1 is read on the device.
+int attention_decode_dyn_splits(int max_seq, int n_heads, int n_kv);
+size_t attention_decode_dyn_scratch_floats(int max_seq, int n_heads, int n_kv, int hd);
+void attention_decode_dyn(float* out, const float* q, const void* kc, const void* vc, const int* pos_dev, int max_seq,
+                          int n_heads, int n_kv, int hd, float scale, float* scratch, cudaStream_t s);
+// Fused RoPE (q, k in place; reference rotary.cu:16-62, non-interleaved pairs) + F16 KV-cache write at *pos_dev.
+void rope_kv_decode(float* q, float* k, const float* v, void* kc, void* vc, const int* pos_dev, int n_heads, int n_kv,
+                    int hd, float theta, float freq_scale, int max_seq, cudaStream_t s);
 // Embedding-row gather + dequant on the GPU (reference does this on the CPU, transformer.cpp:419-599).
 void embed_rows(float* out, const void* table, DType dt, const int* tokens_dev, int n_tokens, int hidden, cudaStream_t s);
 

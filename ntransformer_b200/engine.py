@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference's nt::Transformer surface (src/model/transformer.h:31-61) over the native
+engine's C-ABI (include/nt_b200_engine.h): load / forward(tokens, start_pos) -> logits.
+
+torch is used only to own device memory for synthetic weights and for torch.distributed plumbing (exchange
+of the NCCL id under tensor parallelism)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._engine_sigs import ModelConfigC
+from ._lib import lib
+from .dtypes import DType
+from .model_spec import LlamaConfig, tensor_table
+
+
+class Model:
+    def __init__(self, handle, cfg: LlamaConfig, keep=None, tp_rank=0, tp_size=1):
+        self._h = handle
+        self.cfg = cfg
+        self._keep = keep          # device tensors backing borrowed weights
+        self.tp_rank, self.tp_size = tp_rank, tp_size
+        self._logits_host = np.empty(cfg.vocab_size, dtype=np.float32)
+
+    # ---- construction ----
+    @classmethod
+    def load(cls, gguf_path: str, max_context: int = 4096, tp_rank: int = 0, tp_size: int = 1) -> "Model":
+        h = lib().nt_model_load_gguf(str(gguf_path).encode(), max_context, tp_rank, tp_size)
+        if not h:
+            raise RuntimeError(f"failed to load {gguf_path}")
+        c = ModelConfigC()
+        lib().nt_model_get_config(h, C.byref(c))
+        cfg = LlamaConfig(**{n: getattr(c, n) for n, _ in ModelConfigC._fields_})
+        return cls(h, cfg, tp_rank=tp_rank, tp_size=tp_size)
+
+    @classmethod
+    def from_device_tensors(cls, cfg: LlamaConfig, tensors: dict, tp_rank: int = 0, tp_size: int = 1) -> "Model":
+        """tensors: gguf name -> (torch uint8/float32 CUDA tensor, DType); shapes already sharded for tp_rank."""
+        c = ModelConfigC(**cfg.dict())
+        h = lib().nt_model_create(C.byref(c), tp_rank, tp_size)
+        for name, (t, dt) in tensors.items():
+            rc = lib().nt_model_set_tensor(h, name.encode(), t.data_ptr(), int(dt), 0)
+            if rc != 0:
+                raise ValueError(f"engine rejected tensor {name}")
+        if lib().nt_model_finalize(h) != 0:
+            lib().nt_model_free(h)
+            raise RuntimeError("model is missing tensors")
+        return cls(h, cfg, keep=tensors, tp_rank=tp_rank, tp_size=tp_size)
+
+    @classmethod
+    def synthetic(cls, cfg: LlamaConfig, mix: str, seed: int = 1234, tp_rank: int = 0, tp_size: int = 1, device="cuda") -> "Model":
+        """Random valid GGUF blocks generated directly on the GPU (no checkpoint or file involved)."""
+        import torch
+
+        from .synth import random_blocks_cuda
+
+        tensors = {}
+        for idx, (name, dt, rows, cols) in enumerate(tensor_table(cfg, mix, tp_rank, tp_size)):
+            # replicated tensors share a seed across ranks, shards get rank-specific seeds
+            replicated = name.endswith("norm.weight") or name == "token_embd.weight"
+            s = seed + idx * 16 + (0 if replicated else tp_rank)
+            if name.endswith("norm.weight"):
+                g = torch.Generator(device=device)
+                g.manual_seed(s)
+                t = 1.0 + 0.1 * torch.randn(cols, generator=g, device=device, dtype=torch.float32)
+            else:
+                t = random_blocks_cuda(dt, max(rows, 1), cols, s, device=device)
+            tensors[name] = (t.contiguous(), dt)
+        torch.cuda.synchronize()
+        return cls.from_device_tensors(cfg, tensors, tp_rank, tp_size)
+
+    # ---- tensor parallel ----
+    def init_tp(self):
+        """Collective: exchanges the NCCL unique id over torch.distributed and builds the communicator."""
+        import torch
+        import torch.distributed as dist
+
+        buf = (C.c_ubyte * 128)()
+        if self.tp_rank == 0 and lib().nt_tp_unique_id(buf) != 0:
+            raise RuntimeError("ncclGetUniqueId failed")
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, src=0)
+        idb = (C.c_ubyte * 128)(*t.cpu().tolist())
+        rc = lib().nt_tp_init(self._h, idb, self.tp_rank, self.tp_size)
+        if rc != 0:
+            raise RuntimeError(f"nt_tp_init failed ({rc})")
+
+    # ---- inference ----
+    def forward(self, tokens, start_pos: int, want_logits: bool = True):
+        """Runs the tokens at positions start_pos.. and returns HOST logits [vocab] of the last one."""
+        toks = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = self._logits_host.ctypes.data_as(C.c_void_p) if want_logits else None
+        rc = lib().nt_model_forward(self._h, toks.ctypes.data_as(C.c_void_p), len(toks), start_pos, out)
+        assert rc == 0
+        return self._logits_host if want_logits else None
+
+    def forward_async(self, tokens, start_pos: int):
+        toks = np.ascontiguousarray(tokens, dtype=np.int32)
+        lib().nt_model_forward_async(self._h, toks.ctypes.data_as(C.c_void_p), len(toks), start_pos)
+
+    def sync(self):
+        rc = lib().nt_model_sync(self._h)
+        if rc != 0:
+            raise RuntimeError(f"CUDA error {rc} on the model stream")
+
+    def argmax(self) -> int:
+        return lib().nt_model_argmax(self._h)
+
+    def clear_kv(self):
+        lib().nt_model_clear_kv(self._h)
+
+    def use_graph(self, on: bool):
+        lib().nt_model_use_graph(self._h, int(on))
+
+    @property
+    def stream(self) -> int:
+        return lib().nt_model_stream(self._h)
+
+    @property
+    def logits_device_ptr(self) -> int:
+        return lib().nt_model_logits_device(self._h)
+
+    def bytes_per_token(self, ctx: int) -> int:
+        return int(lib().nt_model_bytes_per_token(self._h, ctx))
+
+    def close(self):
+        if self._h:
+            lib().nt_model_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """include/ntransformer.h through ctypes (the reference declares this C API but never implements it)."""
+
+    def __init__(self):
+        self._h = lib().nt_engine_create()
+
+    def load(self, path: str) -> bool:
+        return lib().nt_engine_load(self._h, str(path).encode()) == 0
+
+    def generate(self, prompt: str, max_tokens=32, temperature=0.0, top_k=40, top_p=0.9) -> str:
+        p = lib().nt_engine_generate(self._h, prompt.encode(), max_tokens, temperature, top_k, top_p)
+        if not p:
+            raise RuntimeError("generate failed")
+        s = C.cast(p, C.c_char_p).value.decode(errors="replace")
+        lib().nt_free(p)
+        return s
+
+    @property
+    def vocab_size(self):
+        return lib().nt_engine_vocab_size(self._h)
+
+    @property
+    def n_layers(self):
+        return lib().nt_engine_n_layers(self._h)
+
+    @property
+    def hidden_size(self):
+        return lib().nt_engine_hidden_size(self._h)
+
+    def close(self):
+        if self._h:
+            lib().nt_engine_destroy(self._h)
+            self._h = None
+
+
+def smoke():
+    """One tiny decode through the native engine on cuda:0, checked against the CPU oracle."""
+    import torch
+
+    from .model_spec import TINY
+    from oracle import oracle as O
+
+    m = Model.synthetic(TINY, "Q4_K_M", seed=7)
+    host = {n: (t.cpu().numpy(), int(dt)) for n, (t, dt) in m._keep.items()}
+    om = O.Model(TINY.dict(), host)
+    toks = [1, 17, 300, 5]
+    got = m.forward(toks, 0).copy()
+    want = om.forward(toks, 0)
+    err = float(np.abs(got - want).max() / np.abs(want).max())
+    assert err < 1e-3, err
+    nxt = int(np.argmax(want))
+    assert m.argmax() == nxt
+    got2 = m.forward([nxt], len(toks)).copy()
+    want2 = om.forward([nxt], len(toks))
+    assert float(np.abs(got2 - want2).max() / np.abs(want2).max()) < 1e-3
+    m.close()
+    torch.cuda.synchronize()

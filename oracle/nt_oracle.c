@@ -512,7 +512,7 @@ int nto_model_forward(nto_model* m, const int* tokens, int seq_len, int start_po
     int hidden = c->hidden_size, inter = c->intermediate_size;
     int nh = c->n_heads, nkv = c->n_kv_heads, hd = c->head_dim, max_seq = c->max_seq_len;
     int q_dim = nh * hd, kv_dim = nkv * hd;
-    if (n_layers_run <= 0 || n_layers_run > c->n_layers) n_layers_run = c->n_layers;
+    if (n_layers_run < 0 || n_layers_run > c->n_layers) n_layers_run = c->n_layers;
 
     size_t attn_ws = (size_t)seq_len * (2 * q_dim + 2 * kv_dim);     /* attention.cpp:106-118 */
     size_t ffn_ws = (size_t)2 * seq_len * inter;                       /* ffn.cpp:85-90 */

@@ -106,8 +106,8 @@ void nto_model_set_globals(nto_model* m, const void* token_embd, int dt_embd,
                            const float* output_norm);
 void nto_model_set_layer(nto_model* m, int i, const nto_layer* l);
 /* Runs seq_len tokens starting at start_pos; writes vocab logits of the last
- * token.  n_layers_run <= 0 means all layers (bench's bounded cpu sample runs
- * fewer). Returns 0 on success. */
+ * token.  n_layers_run < 0 means all layers; 0..n runs that many (bench's bounded
+ * cpu sample runs fewer). Returns 0 on success. */
 int nto_model_forward(nto_model* m, const int* tokens, int seq_len,
                       int start_pos, float* logits, int n_layers_run);
 int nto_num_threads(void);

@@ -168,7 +168,7 @@ class Model:
                 setattr(L, "dt_" + {"wq": "q", "wk": "k", "wv": "v", "wo": "o", "w_gate": "gate", "w_up": "up", "w_down": "down"}[field], dt)
             lib().nto_model_set_layer(self.h, i, C.byref(L))
 
-    def forward(self, tokens, start_pos: int, n_layers_run: int = 0) -> np.ndarray:
+    def forward(self, tokens, start_pos: int, n_layers_run: int = -1) -> np.ndarray:
         toks = np.ascontiguousarray(tokens, dtype=np.int32)
         logits = np.empty(self.cfg.vocab_size, dtype=np.float32)
         rc = lib().nto_model_forward(self.h, _ptr(toks), len(toks), start_pos, _ptr(logits), n_layers_run)
