@@ -119,6 +119,8 @@ def run_ours(args, rank, world):
     from ntransformer_b200.model_spec import bytes_per_token, tensor_table
 
     shape, mix, prompt_len, max_seq = WORKLOADS[args.workload]
+    if args.prompt_tokens is not None:
+        prompt_len = args.prompt_tokens
     cfg = shape_cfg(shape, max_seq)
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -409,6 +411,7 @@ def main():
     ap.add_argument("--workload", default="llama3-70b-q4_k_m-decode", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prompt-tokens", type=int, default=None, help="override the workload's prompt length (profiling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))

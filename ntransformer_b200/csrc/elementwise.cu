@@ -7,6 +7,7 @@
 // lower to the same approximate instructions: greedy-token parity depends on it.
 // Anything that must stay IEEE uses explicit *_rn intrinsics.
 #include "kernels_internal.h"
+#include "xquant.cuh"
 #include <cuda_fp16.h>
 #include <cfloat>
 #include <atomic>
@@ -49,27 +50,19 @@ __device__ float block_max(float v, float* red) {
     return warp_max(t);
 }
 
-// Quantise the 32-element block held one element per lane (see kernels_internal.h "xq").
+// Quantise the 32-element block held one element per lane into the global xq layout.
 __device__ __forceinline__ void quantize_block32(float v, int blk, int lane, int8_t* xq, int K) {
-    float amax = warp_max(fabsf(v));
-    float s = __fdiv_rn(amax, 127.0f);
-    float t = (amax > 0.f) ? __fdiv_rn(v, s) : 0.f;
-    float q1 = rintf(t);
-    float r1 = __fmul_rn(__fsub_rn(t, q1), 128.0f);
-    float q2 = rintf(r1);
-    float r2 = __fmul_rn(__fsub_rn(r1, q2), 128.0f);
-    float q3 = rintf(r2);
+    int q1, q2, q3;
+    float sc, s16;
+    quantize_lane32(v, q1, q2, q3, sc, s16);
     const int e = blk * 32 + lane;
-    xq[e] = (int8_t)(int)q1;
-    xq[K + e] = (int8_t)(int)q2;
-    xq[2 * K + e] = (int8_t)(int)q3;
+    xq[e] = (int8_t)q1;
+    xq[K + e] = (int8_t)q2;
+    xq[2 * K + e] = (int8_t)q3;
     float* scale = reinterpret_cast<float*>(xq + 3 * (size_t)K);
     float* sum16 = scale + K / 32;
-    float sh = v;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) sh = __fadd_rn(sh, __shfl_xor_sync(0xFFFFFFFFu, sh, o));
-    if (lane == 0) scale[blk] = __fmul_rn(s, 1.0f / 16384.0f);
-    if ((lane & 15) == 0) sum16[blk * 2 + (lane >> 4)] = sh;
+    if (lane == 0) scale[blk] = sc;
+    if ((lane & 15) == 0) sum16[blk * 2 + (lane >> 4)] = s16;
 }
 
 __global__ void quantize_x_kernel(const float* __restrict__ x, int8_t* __restrict__ xq, int K) {

@@ -254,23 +254,37 @@ size_t Model::bytes_per_token(int ctx) const {
     return weight_bytes() + (size_t)2 * cfg_.n_layers * ctx * nkv_l_ * cfg_.head_dim * 2;
 }
 
-// y_i = W_i . x for n matrices sharing x; picks the fused TMA/dp4a kernel when every matrix qualifies.
-void Model::matvec(const Weight* const* ws, float* const* ys, int n, const float* x_f32, const void* xq, GemvEpilogue ep,
+// y_i = W_i . x' for n matrices sharing x' = norm_w ? rmsnorm(x, norm_w) : x.
+// When every matrix qualifies, one fused launch does (RMSNorm +) activation quantisation in its prologue, the TMA/dp4a
+// GEMV and the epilogue; otherwise the pieces run as separate launches like the reference's sequence.
+void Model::matvec(const Weight* const* ws, float* const* ys, int n, const float* x, const float* norm_w, GemvEpilogue ep,
                    cudaStream_t s) {
     GemvMat mats[3];
     const int K = ws[0]->cols;
     for (int i = 0; i < n; i++) { mats[i].W = ws[i]->ptr; mats[i].y = ys[i]; mats[i].out = ws[i]->rows; mats[i].dtype = ws[i]->dtype; mats[i].row_pitch = ws[i]->pitch; }
-    if (gemv_kq_supported(mats, n, K)) { gemv_kq(mats, n, K, xq, ep, s); return; }
-    if (ep == GEMV_SWIGLU) {           // unfused fallback: gate -> ys[0], up -> ys[1], then silu_mul in place
+    GemvInput in;
+    if (gemv_kq_supported(mats, n, K)) {
+        if (!norm_w && K > 16384) {            // long vectors (ffn_down): quantise once in a wide kernel, not per CTA
+            quantize_x(x, xq_i_, K, s);
+            in.xq = xq_i_;
+        } else {
+            in.x = x; in.norm_w = norm_w; in.eps = cfg_.norm_eps;
+        }
+        gemv_kq(mats, n, K, in, ep, s);
+        return;
+    }
+    const float* xf = x;
+    if (norm_w) { rmsnorm(xnorm_, x, norm_w, 1, K, cfg_.norm_eps, s); xf = xnorm_; }
+    if (ep == GEMV_SWIGLU) {                   // unfused fallback: gate -> ys[0], up -> ys[1], then silu_mul in place
         const Weight* g = ws[0]; const Weight* u = ws[1];
-        matvec(&g, &ys[0], 1, x_f32, xq, GEMV_STORE, s);
-        matvec(&u, &ys[1], 1, x_f32, xq, GEMV_STORE, s);
+        matvec(&g, &ys[0], 1, xf, nullptr, GEMV_STORE, s);
+        matvec(&u, &ys[1], 1, xf, nullptr, GEMV_STORE, s);
         silu_mul(ys[0], ys[0], ys[1], ws[0]->rows, s);
         return;
     }
     for (int i = 0; i < n; i++) {
-        if (gemv_kq_supported(&mats[i], 1, K)) gemv_kq(&mats[i], 1, K, xq, ep, s);
-        else gemv_generic(ys[i], ws[i]->ptr, x_f32, ws[i]->rows, K, ws[i]->dtype, ws[i]->pitch, ep, s);
+        if (gemv_kq_supported(&mats[i], 1, K)) { in.x = xf; gemv_kq(&mats[i], 1, K, in, ep, s); }
+        else gemv_generic(ys[i], ws[i]->ptr, xf, ws[i]->rows, K, ws[i]->dtype, ws[i]->pitch, ep, s);
     }
 }
 
@@ -292,34 +306,28 @@ void Model::step_body(cudaStream_t s) {
         uint16_t* kc = static_cast<uint16_t*>(kc_) + (size_t)i * kv_stride;
         uint16_t* vc = static_cast<uint16_t*>(vc_) + (size_t)i * kv_stride;
         // --- attention sub-block ---
-        rmsnorm_xq(xnorm_, xq_h_, hidden_, L.attn_norm, hidden, cfg_.norm_eps, s);
-        { const Weight* ws[3] = {&L.wq, &L.wk, &L.wv}; float* ys[3] = {q_, k_, v_}; matvec(ws, ys, 3, xnorm_, xq_h_, GEMV_STORE, s); }
+        { const Weight* ws[3] = {&L.wq, &L.wk, &L.wv}; float* ys[3] = {q_, k_, v_}; matvec(ws, ys, 3, hidden_, L.attn_norm, GEMV_STORE, s); }
         rope_kv_decode(q_, k_, v_, kc, vc, pos_dev, nh_l_, nkv_l_, hd, cfg_.rope_theta, cfg_.rope_freq_scale, max_seq, s);
         attention_decode_dyn(attn_, q_, kc, vc, pos_dev, max_seq, nh_l_, nkv_l_, hd, scale, attn_scratch_, s);
-        quantize_x(attn_, xq_a_, nh_l_ * hd, s);
         { const Weight* ws[1] = {&L.wo};
-          if (tp_size_ == 1) { float* ys[1] = {hidden_}; matvec(ws, ys, 1, attn_, xq_a_, GEMV_ADD, s); }
-          else { float* ys[1] = {part_}; matvec(ws, ys, 1, attn_, xq_a_, GEMV_STORE, s); reduce_residual(part_, s); } }
+          if (tp_size_ == 1) { float* ys[1] = {hidden_}; matvec(ws, ys, 1, attn_, nullptr, GEMV_ADD, s); }
+          else { float* ys[1] = {part_}; matvec(ws, ys, 1, attn_, nullptr, GEMV_STORE, s); reduce_residual(part_, s); } }
         // --- FFN sub-block ---
-        rmsnorm_xq(xnorm_, xq_h_, hidden_, L.ffn_norm, hidden, cfg_.norm_eps, s);
-        { const Weight* ws[2] = {&L.gate, &L.up}; float* ys[2] = {act_, up_}; matvec(ws, ys, 2, xnorm_, xq_h_, GEMV_SWIGLU, s); }
-        quantize_x(act_, xq_i_, inter_l_, s);
+        { const Weight* ws[2] = {&L.gate, &L.up}; float* ys[2] = {act_, up_}; matvec(ws, ys, 2, hidden_, L.ffn_norm, GEMV_SWIGLU, s); }
         { const Weight* ws[1] = {&L.down};
-          if (tp_size_ == 1) { float* ys[1] = {hidden_}; matvec(ws, ys, 1, act_, xq_i_, GEMV_ADD, s); }
-          else { float* ys[1] = {part_}; matvec(ws, ys, 1, act_, xq_i_, GEMV_STORE, s); reduce_residual(part_, s); } }
+          if (tp_size_ == 1) { float* ys[1] = {hidden_}; matvec(ws, ys, 1, act_, nullptr, GEMV_ADD, s); }
+          else { float* ys[1] = {part_}; matvec(ws, ys, 1, act_, nullptr, GEMV_STORE, s); reduce_residual(part_, s); } }
     }
 }
 
 void Model::step_head(cudaStream_t s) {
-    const int hidden = cfg_.hidden_size;
-    rmsnorm_xq(xnorm_, xq_h_, hidden_, out_norm_, hidden, cfg_.norm_eps, s);      // transformer.cpp:657-659
-    const Weight* ws[1] = {&head_};
+    const Weight* ws[1] = {&head_};                                               // final norm fused: transformer.cpp:657-665
     if (tp_size_ == 1) {
         float* ys[1] = {logits_};
-        matvec(ws, ys, 1, xnorm_, xq_h_, GEMV_STORE, s);
+        matvec(ws, ys, 1, hidden_, out_norm_, GEMV_STORE, s);
     } else {
         float* ys[1] = {logits_l_};
-        if (head_.rows > 0) matvec(ws, ys, 1, xnorm_, xq_h_, GEMV_STORE, s);
+        if (head_.rows > 0) matvec(ws, ys, 1, hidden_, out_norm_, GEMV_STORE, s);
         comm_->all_gather(logits_l_, logits_, (size_t)vocab_l_, s);
     }
 }

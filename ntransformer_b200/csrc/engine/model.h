@@ -73,7 +73,7 @@ private:
     void step_body(cudaStream_t s);      // embedding + all layers for the token/position in step_dev_
     void step_head(cudaStream_t s);      // final norm + LM head (+ all-gather under TP)
     void run_step(bool with_head);
-    void matvec(const Weight* const* ws, float* const* ys, int n, const float* x_f32, const void* xq, GemvEpilogue ep,
+    void matvec(const Weight* const* ws, float* const* ys, int n, const float* x, const float* norm_w, GemvEpilogue ep,
                 cudaStream_t s);
     void reduce_residual(float* partial, cudaStream_t s);
     const void* upload(const GGUFFile& f, const std::string& name, Weight* w, int split /*0 none,1 rows,2 cols*/);

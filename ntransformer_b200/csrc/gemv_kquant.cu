@@ -15,9 +15,12 @@
 //   * math: IDP.4A on the 4/5/6-bit codes (exact integer partial sums), one F32 scale per 16/32 weights,
 //     6-bit scale unpack amortised over a 128-weight half super-block per lane;
 //   * reduction: a 4-row transpose-reduce (6 shuffles) once per row-group.
+// The kernel is specialised per block format (compile-time block size / row pitch: no address IMADs) and
+// the CTA width (4..8 warps) is chosen per launch to minimise rounds x warps (tail quantisation).
 // No tensor cores: the path is HBM-bound (BASELINE.json north_star).
 #include "kernels_internal.h"
 #include "ring.cuh"
+#include "xquant.cuh"
 #include <cuda_fp16.h>
 
 namespace nt { namespace b200 {
@@ -28,203 +31,307 @@ constexpr int RG = 4;            // rows per warp stage
 constexpr int BS = 16;           // super-blocks per stage chunk (two lanes per super-block)
 constexpr int MAX_MATS = 3;
 
+template <int FMT> struct Fmt;
+template <> struct Fmt<0> { static constexpr int BLK = 144; };   // Q4_K
+template <> struct Fmt<1> { static constexpr int BLK = 176; };   // Q5_K
+template <> struct Fmt<2> { static constexpr int BLK = 210; };   // Q6_K
+
 struct KqMat {
     const uint8_t* W;
     float* y;
     int out;
     int groups;        // ceil(out / RG)
-    int blk_bytes;     // 144 / 176 / 210
-    int fmt;           // 0 = Q4_K, 1 = Q5_K, 2 = Q6_K
+    int fmt;           // 0 Q4_K, 1 Q5_K, 2 Q6_K
     long long row_pitch;
 };
 struct KqParams {
     KqMat mat[MAX_MATS];
     int n_mat;
     int K, NB, NC;             // elements, super-blocks per row, chunks per row
-    const int8_t* xq;
+    const int8_t* xq;          // pre-quantised activations, or null:
+    const float* x_f32;        //   F32 activations quantised in the prologue,
+    const float* norm_w;       //   optionally RMS-normalised first (x * rsqrt(mean(x^2) + eps) * norm_w)
+    float eps;
     int total_groups;          // SWIGLU: groups of mat[0]
     int n_seg;                 // segments (matrices) per task: 2 for SWIGLU else 1
     int epilogue;
     int stages;                // ring depth per warp
-    int slot_bytes;            // RG * BS * max blk_bytes
 };
 
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ int4 lds128(uint32_t addr) {
-    int4 v;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ float h2f(uint32_t h16) { return __half2float(__ushort_as_half((unsigned short)h16)); }
+__device__ __forceinline__ int combine3(int s0, int s1, int s2) { return (s0 * 128 + s1) * 128 + s2; }
 
-// Byte offset of element e inside an x plane: 16-byte columns are XORed with the half-block index so
-// that the 8 lanes of a quarter-warp (8 consecutive half-blocks, 128 B apart) hit 8 different columns.
-__device__ __forceinline__ uint32_t xswz(uint32_t e) { return e ^ (((e >> 7) & 7u) << 4); }
+// Stage cursor: (task, segment, chunk) advanced without divisions.
+struct Cursor {
+    int g;        // global row-group index of the current task (gw + task * nw)
+    int seg, chunk;
+    int mi, gl;   // matrix index and row-group inside that matrix
+};
 
-__device__ __forceinline__ int combine3(const int s[3]) { return (s[0] * 128 + s[1]) * 128 + s[2]; }
-
-// ---- one 64-weight pass of a Q4_K / Q5_K half super-block for RG rows --------------------------
-// xr[p][0..7] = x terms for the low sub-block (32 elements), xr[p][8..15] for the high sub-block.
+// One stage (RG rows x up to BS super-blocks) of format FMT: this lane's half super-block against its x terms.
 template <int FMT>
-__device__ __forceinline__ void pass_q45(const int (&xr)[3][16], float sx_lo, float sx_hi, float sum_lo, float sum_hi,
-                                         uint32_t q_addr, uint32_t qh_addr, int row_pitch, int cg /* chunk 0..3 */,
-                                         const uint32_t (&sc4)[RG], const uint32_t (&m4)[RG], int cc,
-                                         float (&A)[RG], float (&B)[RG]) {
+__device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_base, int blk, int h, uint32_t hb,
+                                              const uint8_t* __restrict__ xs, int K, const float* __restrict__ xscale,
+                                              const float* __restrict__ xsum16, float (&acc)[RG]) {
+    constexpr int BLK = Fmt<FMT>::BLK;
+    constexpr int ROWP = BS * BLK;            // row pitch inside a stage slot
+    const uint8_t* base = slot_base + blk * BLK;
+    const uint8_t* xh = xs + hb * 128u;
+    const uint32_t sw = hb & 7u;
+    if (FMT <= 1) {
+        // ---------------- Q4_K / Q5_K ----------------
+        constexpr int QS = (FMT == 0) ? 16 : 48;
+        uint32_t sc4[RG], m4[RG];
+        float d[RG], dmin[RG];
 #pragma unroll
-    for (int r = 0; r < RG; r++) {
-        int4 qa = lds128(q_addr + r * row_pitch);
-        int4 qb = lds128(q_addr + r * row_pitch + 16);
-        uint32_t q[8] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w,
-                         (uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w};
-        uint32_t qh[8];
-        if (FMT == 1) {
-            int4 ha = lds128(qh_addr + r * row_pitch);
-            int4 hb = lds128(qh_addr + r * row_pitch + 16);
-            qh[0] = ha.x; qh[1] = ha.y; qh[2] = ha.z; qh[3] = ha.w;
-            qh[4] = hb.x; qh[5] = hb.y; qh[6] = hb.z; qh[7] = hb.w;
+        for (int r = 0; r < RG; r++) {
+            const int4 hd = *reinterpret_cast<const int4*>(base + r * ROWP);
+            const uint32_t w0 = hd.y, w1 = hd.z, w2 = hd.w;
+            d[r] = h2f((uint32_t)hd.x & 0xFFFFu);
+            dmin[r] = h2f((uint32_t)hd.x >> 16);
+            const uint32_t sa = w0 & 0x3F3F3F3Fu, ma = w1 & 0x3F3F3F3Fu;
+            const uint32_t sb = (w2 & 0x0F0F0F0Fu) | ((w0 >> 2) & 0x30303030u);
+            const uint32_t mb = ((w2 >> 4) & 0x0F0F0F0Fu) | ((w1 >> 2) & 0x30303030u);
+            sc4[r] = h ? sb : sa;
+            m4[r] = h ? mb : ma;
         }
-        int slo[3] = {0, 0, 0}, shi[3] = {0, 0, 0};
+        float A[RG] = {0.f, 0.f, 0.f, 0.f}, B[RG] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int w = 0; w < 8; w++) {
-            uint32_t lo = q[w] & 0x0F0F0F0Fu;
-            uint32_t hi = (q[w] >> 4) & 0x0F0F0F0Fu;
-            if (FMT == 1) {
-                uint32_t t = qh[w] >> (2 * cg);             // bit0 -> low sub-block, bit1 -> high sub-block
-                lo |= (t << 4) & 0x10101010u;
-                hi |= (t << 3) & 0x10101010u;
+        for (int c2 = 0; c2 < 2; c2++) {
+            int xr[3][16];
+#pragma unroll
+            for (int pl = 0; pl < 3; pl++) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int4 v = *reinterpret_cast<const int4*>(xh + pl * K + (((uint32_t)(c2 * 4 + i) ^ sw) << 4));
+                    xr[pl][4 * i + 0] = v.x; xr[pl][4 * i + 1] = v.y; xr[pl][4 * i + 2] = v.z; xr[pl][4 * i + 3] = v.w;
+                }
+            }
+            const int b32 = hb * 4 + c2 * 2, b16 = hb * 8 + c2 * 4;
+            const float sx_lo = xscale[b32], sx_hi = xscale[b32 + 1];
+            const float sum_lo = xsum16[b16] + xsum16[b16 + 1], sum_hi = xsum16[b16 + 2] + xsum16[b16 + 3];
+            const int cg = 2 * h + c2;
+            // fetch the codes of all RG rows first (independent 16-byte loads in flight together)
+            int4 qa[RG], qb[RG], ha[RG], hbv[RG];
+#pragma unroll
+            for (int r = 0; r < RG; r++) {
+                const uint8_t* qp = base + r * ROWP + QS + h * 64 + c2 * 32;
+                qa[r] = *reinterpret_cast<const int4*>(qp);
+                qb[r] = *reinterpret_cast<const int4*>(qp + 16);
+                if (FMT == 1) {
+                    ha[r] = *reinterpret_cast<const int4*>(base + r * ROWP + 16);
+                    hbv[r] = *reinterpret_cast<const int4*>(base + r * ROWP + 32);
+                }
             }
 #pragma unroll
-            for (int p = 0; p < 3; p++) {
-                slo[p] = dp4a_us(lo, xr[p][w], slo[p]);
-                shi[p] = dp4a_us(hi, xr[p][8 + w], shi[p]);
+            for (int r = 0; r < RG; r++) {
+                const uint32_t q[8] = {(uint32_t)qa[r].x, (uint32_t)qa[r].y, (uint32_t)qa[r].z, (uint32_t)qa[r].w,
+                                       (uint32_t)qb[r].x, (uint32_t)qb[r].y, (uint32_t)qb[r].z, (uint32_t)qb[r].w};
+                uint32_t qh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (FMT == 1) {
+                    qh[0] = ha[r].x; qh[1] = ha[r].y; qh[2] = ha[r].z; qh[3] = ha[r].w;
+                    qh[4] = hbv[r].x; qh[5] = hbv[r].y; qh[6] = hbv[r].z; qh[7] = hbv[r].w;
+                }
+                int l0 = 0, l1 = 0, l2 = 0, h0 = 0, h1 = 0, h2 = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    uint32_t lo = q[w] & 0x0F0F0F0Fu;
+                    uint32_t hi = (q[w] >> 4) & 0x0F0F0F0Fu;
+                    if (FMT == 1) {
+                        const uint32_t t = qh[w] >> (2 * cg);     // bit0 -> low sub-block, bit1 -> high sub-block
+                        lo |= (t << 4) & 0x10101010u;
+                        hi |= (t << 3) & 0x10101010u;
+                    }
+                    l0 = dp4a_us(lo, xr[0][w], l0); l1 = dp4a_us(lo, xr[1][w], l1); l2 = dp4a_us(lo, xr[2][w], l2);
+                    h0 = dp4a_us(hi, xr[0][8 + w], h0); h1 = dp4a_us(hi, xr[1][8 + w], h1); h2 = dp4a_us(hi, xr[2][8 + w], h2);
+                }
+                const float flo = (float)combine3(l0, l1, l2) * sx_lo;
+                const float fhi = (float)combine3(h0, h1, h2) * sx_hi;
+                const uint32_t s2 = sc4[r] >> (16 * c2), m2 = m4[r] >> (16 * c2);
+                A[r] = fmaf((float)(s2 & 0xFFu), flo, fmaf((float)((s2 >> 8) & 0xFFu), fhi, A[r]));
+                B[r] = fmaf((float)(m2 & 0xFFu), sum_lo, fmaf((float)((m2 >> 8) & 0xFFu), sum_hi, B[r]));
             }
         }
-        float flo = (float)combine3(slo) * sx_lo;
-        float fhi = (float)combine3(shi) * sx_hi;
-        float sc_lo = (float)((sc4[r] >> (16 * cc)) & 0xFFu), sc_hi = (float)((sc4[r] >> (16 * cc + 8)) & 0xFFu);
-        float m_lo = (float)((m4[r] >> (16 * cc)) & 0xFFu), m_hi = (float)((m4[r] >> (16 * cc + 8)) & 0xFFu);
-        A[r] = fmaf(sc_lo, flo, fmaf(sc_hi, fhi, A[r]));
-        B[r] = fmaf(m_lo, sum_lo, fmaf(m_hi, sum_hi, B[r]));
+#pragma unroll
+        for (int r = 0; r < RG; r++) acc[r] += d[r] * A[r] - dmin[r] * B[r];
+    } else {
+        // ---------------- Q6_K (210-byte blocks: 2-byte aligned, realigned with PRMT) ----------------
+        const uint32_t mis = (uint32_t)(blk & 1) * 2u;           // (blk * 210) & 2
+        const uint32_t sel = mis ? 0x5432u : 0x3210u;
+        const uint8_t* ab = base - mis;                            // 4-byte aligned view of the block
+        uint32_t scw[RG][2];
+        float d[RG];
+#pragma unroll
+        for (int r = 0; r < RG; r++) {
+            const uint32_t* sp = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 192 + 8 * h);
+            const uint32_t a0 = sp[0], a1 = sp[1], a2 = sp[2];
+            scw[r][0] = __byte_perm(a0, a1, sel);
+            scw[r][1] = __byte_perm(a1, a2, sel);
+            const uint32_t dw = *reinterpret_cast<const uint32_t*>(ab + r * ROWP + 208);
+            d[r] = h2f(mis ? (dw >> 16) : (dw & 0xFFFFu));
+        }
+        float A[RG] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+            int xr[3][16];
+            float sx[4], c32[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++) {
+                    const int4 v = *reinterpret_cast<const int4*>(xh + pl * K + (((uint32_t)(2 * j + kk) ^ sw) << 4));
+                    xr[pl][4 * j + 0] = v.x; xr[pl][4 * j + 1] = v.y; xr[pl][4 * j + 2] = v.z; xr[pl][4 * j + 3] = v.w;
+                }
+                sx[j] = xscale[hb * 4 + j];
+                c32[j] = 32.0f * xsum16[hb * 8 + 2 * j + kk];
+            }
+#pragma unroll
+            for (int r = 0; r < RG; r++) {
+                const uint32_t* pa = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 64 * h + 16 * kk);          // ql[l]
+                const uint32_t* pb = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 64 * h + 32 + 16 * kk);     // ql[l+32]
+                const uint32_t* ph = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 128 + 32 * h + 16 * kk);    // qh[l]
+                uint32_t ra[5], rb[5], rh[5];
+#pragma unroll
+                for (int i = 0; i < 5; i++) { ra[i] = pa[i]; rb[i] = pb[i]; rh[i] = ph[i]; }
+                int s[4][3] = {};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t qa = __byte_perm(ra[i], ra[i + 1], sel), qb = __byte_perm(rb[i], rb[i + 1], sel);
+                    const uint32_t hh = __byte_perm(rh[i], rh[i + 1], sel);
+                    const uint32_t q1 = (qa & 0x0F0F0F0Fu) | ((hh << 4) & 0x30303030u);
+                    const uint32_t q2 = (qb & 0x0F0F0F0Fu) | ((hh << 2) & 0x30303030u);
+                    const uint32_t q3 = ((qa >> 4) & 0x0F0F0F0Fu) | (hh & 0x30303030u);
+                    const uint32_t q4 = ((qb >> 4) & 0x0F0F0F0Fu) | ((hh >> 2) & 0x30303030u);
+#pragma unroll
+                    for (int pl = 0; pl < 3; pl++) {
+                        s[0][pl] = dp4a_us(q1, xr[pl][0 + i], s[0][pl]);
+                        s[1][pl] = dp4a_us(q2, xr[pl][4 + i], s[1][pl]);
+                        s[2][pl] = dp4a_us(q3, xr[pl][8 + i], s[2][pl]);
+                        s[3][pl] = dp4a_us(q4, xr[pl][12 + i], s[3][pl]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int b = 2 * j + kk;                      // scale index inside the half
+                    const int sc = (int)(signed char)((scw[r][b >> 2] >> (8 * (b & 3))) & 0xFFu);
+                    // sum over 16 weights of sc * (q - 32) * x = sc * (S * sx - 32 * sum16)
+                    A[r] = fmaf((float)sc, fmaf((float)combine3(s[j][0], s[j][1], s[j][2]), sx[j], -c32[j]), A[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RG; r++) acc[r] = fmaf(d[r], A[r], acc[r]);
     }
 }
 
-// Load n+1 aligned words starting at (addr & ~3) and funnel them into n words starting at addr
-// (addr is 2-byte aligned: Q6_K super-blocks are 210 B).
-template <int N>
-__device__ __forceinline__ void lds_funnel(uint32_t addr, uint32_t sel, uint32_t (&out)[N]) {
-    uint32_t a = addr & ~3u;
-    uint32_t prev = lds32(a);
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        uint32_t next = lds32(a + 4 * (i + 1));
-        out[i] = __byte_perm(prev, next, sel);
-        prev = next;
-    }
-}
+__host__ __device__ constexpr int max_blk(int mask) { return (mask & 4) ? 210 : (mask & 2) ? 176 : 144; }
 
-// ---- one pass (kk = 0/1: l in [16kk, 16kk+16)) of a Q6_K half super-block for RG rows -----------
-// xr[p][4*j + i]: x terms for run j (elements j*32 + 16kk + 4i ..), j = 0..3.
-__device__ __forceinline__ void pass_q6(const int (&xr)[3][16], const float (&sx)[4], const float (&c32)[4],
-                                        uint32_t half_addr /* ql half base of row 0 */, uint32_t qh_addr, int row_pitch,
-                                        uint32_t sel, int kk, const uint32_t (&scw)[RG][2], float (&A)[RG]) {
-#pragma unroll
-    for (int r = 0; r < RG; r++) {
-        uint32_t qa[4], qb[4], qh[4];
-        lds_funnel<4>(half_addr + r * row_pitch + 16 * kk, sel, qa);        // ql[l]
-        lds_funnel<4>(half_addr + r * row_pitch + 32 + 16 * kk, sel, qb);   // ql[l + 32]
-        lds_funnel<4>(qh_addr + r * row_pitch + 16 * kk, sel, qh);
-        int s[4][3] = {};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint32_t h = qh[i];
-            uint32_t q1 = (qa[i] & 0x0F0F0F0Fu) | ((h << 4) & 0x30303030u);
-            uint32_t q2 = (qb[i] & 0x0F0F0F0Fu) | ((h << 2) & 0x30303030u);
-            uint32_t q3 = ((qa[i] >> 4) & 0x0F0F0F0Fu) | (h & 0x30303030u);
-            uint32_t q4 = ((qb[i] >> 4) & 0x0F0F0F0Fu) | ((h >> 2) & 0x30303030u);
-#pragma unroll
-            for (int p = 0; p < 3; p++) {
-                s[0][p] = dp4a_us(q1, xr[p][0 + i], s[0][p]);
-                s[1][p] = dp4a_us(q2, xr[p][4 + i], s[1][p]);
-                s[2][p] = dp4a_us(q3, xr[p][8 + i], s[2][p]);
-                s[3][p] = dp4a_us(q4, xr[p][12 + i], s[3][p]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int b = 2 * j + kk;                                   // scale index inside the half
-            int sc = (int)(signed char)((scw[r][b >> 2] >> (8 * (b & 3))) & 0xFFu);
-            // sum over the 16 weights of sc * (q - 32) * x = sc * (S * sx - 32 * sum16)
-            A[r] = fmaf((float)sc, fmaf((float)combine3(s[j]), sx[j], -c32[j]), A[r]);
-        }
-    }
-}
-
-template <int WARPS>
+// MASK: bit f set <=> matrices of format f may appear in this launch (mixed Q4_K_M projections share one launch).
+template <int MASK, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_constant__ KqParams p) {
+    constexpr int SLOT = RG * BS * max_blk(MASK);
     extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ float red[32];
     const int K = p.K;
     // smem carve-up: [x planes 3K][scale K/32 f32][sum16 K/16 f32][pad to 128][rings][mbarriers]
     uint8_t* xs = smem;
     float* xscale = reinterpret_cast<float*>(smem + 3 * (size_t)K);
     float* xsum16 = xscale + K / 32;
-    size_t ring_off = (3 * (size_t)K + (size_t)(K / 32) * 4 + (size_t)(K / 16) * 4 + 127) & ~(size_t)127;
+    const size_t ring_off = (3 * (size_t)K + (size_t)(K / 32) * 4 + (size_t)(K / 16) * 4 + 127) & ~(size_t)127;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* ring = smem + ring_off + (size_t)warp * p.stages * p.slot_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ring_off + (size_t)WARPS * p.stages * p.slot_bytes) + warp * p.stages;
+    const int stages = p.stages;
+    uint8_t* ring = smem + ring_off + (size_t)warp * stages * SLOT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ring_off + (size_t)WARPS * stages * SLOT) + warp * stages;
 
     const int gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
     const int n_tasks = (gw < p.total_groups) ? (p.total_groups - gw + nw - 1) / nw : 0;
-    const int per_task = p.n_seg * p.NC;
-    const int n_stages_total = n_tasks * per_task;
+    const int NC = p.NC, NB = p.NB, n_seg = p.n_seg;
+    const int n_stages_total = n_tasks * n_seg * NC;
 
-    // ---- producer: issue the copies of flattened stage s into ring slot ----
-    auto issue = [&](int s, int slot) {
-        int task = s / per_task, rem = s - task * per_task;
-        int seg = rem / p.NC, chunk = rem - seg * p.NC;
-        int g = gw + task * nw;
-        int mi = seg;
-        if (p.n_seg == 1) {
-            mi = 0;
-            while (mi + 1 < p.n_mat && g >= p.mat[mi].groups) { g -= p.mat[mi].groups; mi++; }
+    auto locate = [&](Cursor& c) {            // matrix lookup for the cursor's task
+        if (n_seg == 2) { c.mi = c.seg; c.gl = c.g; return; }
+        int g = c.g, mi = 0;
+        while (mi + 1 < p.n_mat && g >= p.mat[mi].groups) { g -= p.mat[mi].groups; mi++; }
+        c.mi = mi; c.gl = g;
+    };
+    auto advance = [&](Cursor& c) {
+        if (++c.chunk == NC) {
+            c.chunk = 0;
+            if (++c.seg == n_seg) { c.seg = 0; c.g += nw; }
+            locate(c);
         }
-        const KqMat& m = p.mat[mi];
-        int nbc = min(BS, p.NB - chunk * BS);
-        // copy size rounded up to 16 B (a 210-byte Q6_K tail may spill into the row's padding; checked on the host)
-        uint32_t bytes = ((uint32_t)(nbc * m.blk_bytes) + 15u) & ~15u;
+    };
+    auto issue = [&](const Cursor& c, int slot) {   // lane 0: TMA copies of one stage into ring slot
+        const KqMat& m = p.mat[c.mi];
+        const int nbc = min(BS, NB - c.chunk * BS);
+        const int blkb = (MASK == 1) ? 144 : (MASK == 2) ? 176 : (MASK == 4) ? 210 : (m.fmt == 0 ? 144 : m.fmt == 1 ? 176 : 210);
+        // copy size rounded up to 16 B (a 210-byte Q6_K tail may spill into row padding; checked on the host)
+        const uint32_t bytes = ((uint32_t)(nbc * blkb) + 15u) & ~15u;
         uint64_t* bar = bars + slot;
         mbar_expect_tx(bar, bytes * RG);
-        uint8_t* dst = ring + (size_t)slot * p.slot_bytes;
+        uint8_t* dst = ring + (size_t)slot * SLOT;
+        const uint8_t* src = m.W + (long long)c.chunk * (BS * blkb);
 #pragma unroll
         for (int r = 0; r < RG; r++) {
-            int row = min(g * RG + r, m.out - 1);
-            bulk_g2s(dst + r * (BS * m.blk_bytes), m.W + (long long)row * m.row_pitch + (long long)chunk * BS * m.blk_bytes,
-                     bytes, bar);
+            const int row = min(c.gl * RG + r, m.out - 1);
+            bulk_g2s(dst + r * (BS * blkb), src + (long long)row * m.row_pitch, bytes, bar);
         }
     };
 
     if (lane == 0) {
-        for (int s = 0; s < p.stages; s++) mbar_init(bars + s, 1);
+        for (int s = 0; s < stages; s++) mbar_init(bars + s, 1);
         mbar_fence_init();
     }
     __syncwarp();
+    Cursor pc{gw, 0, 0, 0, 0};                 // producer cursor (runs `stages` ahead of the consumer)
+    locate(pc);
+    int issued = 0;
     // Weights do not depend on the previous kernel: start streaming before touching x.
     if (lane == 0) {
-        for (int s = 0; s < p.stages && s < n_stages_total; s++) issue(s, s);
+        for (; issued < stages && issued < n_stages_total; issued++) { issue(pc, issued); advance(pc); }
     }
     pdl_wait();   // no-op unless launched with programmatic stream serialization
 
-    // ---- stage xq into shared memory (swizzled planes) ----
-    {
+    if (p.x_f32) {
+        // ---- fused prologue: (RMSNorm +) block-scaled int8x3 quantisation straight into shared memory ----
+        // Replaces the reference's separate rmsnorm launch (rmsnorm.cu:17-70) for the consumer GEMV; every CTA
+        // recomputes it from the L2-resident hidden state while its first weight stages are in flight.
+        float rms_inv = 1.0f;
+        if (p.norm_w) {
+            float ss = 0.f;
+            for (int i = threadIdx.x; i < K; i += WARPS * 32) { const float v = p.x_f32[i]; ss += v * v; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+            if (lane == 0) red[warp] = ss;
+            __syncthreads();
+            float t = (lane < WARPS) ? red[lane] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+            const float mean_sq = t / K;
+            rms_inv = rsqrtf(mean_sq + p.eps);
+        }
+        for (int b = warp; b < K / 32; b += WARPS) {
+            const int e = b * 32 + lane;
+            float v = p.x_f32[e];
+            if (p.norm_w) v = v * rms_inv * p.norm_w[e];
+            int q1, q2, q3;
+            float sc, s16;
+            quantize_lane32(v, q1, q2, q3, sc, s16);
+            const uint32_t se = xq_swizzle((uint32_t)e);
+            xs[se] = (uint8_t)q1;
+            xs[K + se] = (uint8_t)q2;
+            xs[2 * K + se] = (uint8_t)q3;
+            if (lane == 0) xscale[b] = sc;
+            if ((lane & 15) == 0) xsum16[2 * b + (lane >> 4)] = s16;
+        }
+    } else {
+        // ---- stage pre-quantised xq into shared memory (swizzled planes) ----
         const int n16 = 3 * K / 16;
         const int4* src = reinterpret_cast<const int4*>(p.xq);
         for (int i = threadIdx.x; i < n16; i += WARPS * 32) {
-            uint32_t byte = (uint32_t)i * 16u;
-            uint32_t plane = byte / (uint32_t)K, e = byte - plane * (uint32_t)K;
-            *reinterpret_cast<int4*>(xs + plane * (uint32_t)K + xswz(e)) = __ldg(src + i);
+            const uint32_t byte = (uint32_t)i * 16u;
+            const uint32_t plane = byte / (uint32_t)K, e = byte - plane * (uint32_t)K;
+            *reinterpret_cast<int4*>(xs + plane * (uint32_t)K + (e ^ (((e >> 7) & 7u) << 4))) = __ldg(src + i);
         }
         const float* fsrc = reinterpret_cast<const float*>(p.xq + 3 * (size_t)K);
         const int nf = K / 32 + K / 16;
@@ -233,132 +340,52 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     __syncthreads();
     pdl_launch_dependents();
 
-    const uint32_t xs_a = smem_u32(xs);
     const int blk = lane >> 1, h = lane & 1;
     float acc[RG] = {0.f, 0.f, 0.f, 0.f};
     float gate_keep = 0.f;
+    Cursor cc{gw, 0, 0, 0, 0};
+    locate(cc);
+    int slot = 0;
+    uint32_t parity = 0;
 
     for (int s = 0; s < n_stages_total; s++) {
-        const int slot = s % p.stages;
-        const uint32_t parity = (uint32_t)((s / p.stages) & 1);
-        int task = s / per_task, rem = s - task * per_task;
-        int seg = rem / p.NC, chunk = rem - seg * p.NC;
-        int g = gw + task * nw;
-        int mi = seg;
-        if (p.n_seg == 1) {
-            mi = 0;
-            while (mi + 1 < p.n_mat && g >= p.mat[mi].groups) { g -= p.mat[mi].groups; mi++; }
-        }
-        const KqMat& m = p.mat[mi];
-        const int nbc = min(BS, p.NB - chunk * BS);
-        const int row_pitch = BS * m.blk_bytes;
-
+        const int nbc = min(BS, NB - cc.chunk * BS);
         mbar_wait(bars + slot, parity);
 
         if (blk < nbc) {
-            const uint32_t base = smem_u32(ring + (size_t)slot * p.slot_bytes) + blk * m.blk_bytes;
-            const uint32_t hb = (uint32_t)((chunk * BS + blk) * 2 + h);      // global half-block index
-            if (m.fmt <= 1) {
-                // ---------------- Q4_K / Q5_K ----------------
-                const uint32_t qs_off = (m.fmt == 0) ? 16u : 48u;
-                uint32_t sc4[RG], m4[RG];
-                float d[RG], dmin[RG];
-#pragma unroll
-                for (int r = 0; r < RG; r++) {
-                    int4 hd = lds128(base + r * row_pitch);
-                    uint32_t w0 = hd.y, w1 = hd.z, w2 = hd.w;
-                    d[r] = h2f((uint32_t)hd.x & 0xFFFFu);
-                    dmin[r] = h2f((uint32_t)hd.x >> 16);
-                    if (h == 0) {
-                        sc4[r] = w0 & 0x3F3F3F3Fu;
-                        m4[r] = w1 & 0x3F3F3F3Fu;
-                    } else {
-                        sc4[r] = (w2 & 0x0F0F0F0Fu) | ((w0 >> 2) & 0x30303030u);
-                        m4[r] = ((w2 >> 4) & 0x0F0F0F0Fu) | ((w1 >> 2) & 0x30303030u);
-                    }
-                }
-                float A[RG] = {0.f, 0.f, 0.f, 0.f}, B[RG] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int cc = 0; cc < 2; cc++) {
-                    int xr[3][16];
-#pragma unroll
-                    for (int pl = 0; pl < 3; pl++) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            uint32_t col = (uint32_t)(cc * 4 + i) ^ (hb & 7u);
-                            int4 v = lds128(xs_a + pl * K + hb * 128u + col * 16u);
-                            xr[pl][4 * i + 0] = v.x; xr[pl][4 * i + 1] = v.y; xr[pl][4 * i + 2] = v.z; xr[pl][4 * i + 3] = v.w;
-                        }
-                    }
-                    const int b32 = hb * 4 + cc * 2, b16 = hb * 8 + cc * 4;
-                    float sx_lo = xscale[b32], sx_hi = xscale[b32 + 1];
-                    float sum_lo = xsum16[b16] + xsum16[b16 + 1], sum_hi = xsum16[b16 + 2] + xsum16[b16 + 3];
-                    if (m.fmt == 0)
-                        pass_q45<0>(xr, sx_lo, sx_hi, sum_lo, sum_hi, base + qs_off + h * 64 + cc * 32, 0, row_pitch,
-                                    2 * h + cc, sc4, m4, cc, A, B);
-                    else
-                        pass_q45<1>(xr, sx_lo, sx_hi, sum_lo, sum_hi, base + qs_off + h * 64 + cc * 32, base + 16, row_pitch,
-                                    2 * h + cc, sc4, m4, cc, A, B);
-                }
-#pragma unroll
-                for (int r = 0; r < RG; r++) acc[r] += d[r] * A[r] - dmin[r] * B[r];
-            } else {
-                // ---------------- Q6_K ----------------
-                const uint32_t sel = (base & 2u) ? 0x5432u : 0x3210u;
-                uint32_t scw[RG][2];
-                float d[RG];
-#pragma unroll
-                for (int r = 0; r < RG; r++) {
-                    lds_funnel<2>(base + r * row_pitch + 192 + 8 * h, sel, scw[r]);
-                    uint32_t da = base + r * row_pitch + 208;
-                    uint32_t w = lds32(da & ~3u);
-                    d[r] = h2f((da & 2u) ? (w >> 16) : (w & 0xFFFFu));
-                }
-                float A[RG] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int kk = 0; kk < 2; kk++) {
-                    int xr[3][16];
-                    float sx[4], c32[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        uint32_t col = (uint32_t)(2 * j + kk) ^ (hb & 7u);
-#pragma unroll
-                        for (int pl = 0; pl < 3; pl++) {
-                            int4 v = lds128(xs_a + pl * K + hb * 128u + col * 16u);
-                            xr[pl][4 * j + 0] = v.x; xr[pl][4 * j + 1] = v.y; xr[pl][4 * j + 2] = v.z; xr[pl][4 * j + 3] = v.w;
-                        }
-                        sx[j] = xscale[hb * 4 + j];
-                        c32[j] = 32.0f * xsum16[hb * 8 + 2 * j + kk];
-                    }
-                    pass_q6(xr, sx, c32, base + 64 * h, base + 128 + 32 * h, row_pitch, sel, kk, scw, A);
-                }
-#pragma unroll
-                for (int r = 0; r < RG; r++) acc[r] = fmaf(d[r], A[r], acc[r]);
-            }
+            const uint8_t* slot_base = ring + (size_t)slot * SLOT;
+            const uint32_t hb = (uint32_t)((cc.chunk * BS + blk) * 2 + h);      // global half-block index
+            const int fmt = (MASK == 1) ? 0 : (MASK == 2) ? 1 : (MASK == 4) ? 2 : p.mat[cc.mi].fmt;
+            if ((MASK & 1) && fmt == 0) process_stage<0>(slot_base, blk, h, hb, xs, K, xscale, xsum16, acc);
+            if ((MASK & 2) && fmt == 1) process_stage<1>(slot_base, blk, h, hb, xs, K, xscale, xsum16, acc);
+            if ((MASK & 4) && fmt == 2) process_stage<2>(slot_base, blk, h, hb, xs, K, xscale, xsum16, acc);
         }
         __syncwarp();
-        if (lane == 0 && s + p.stages < n_stages_total) issue(s + p.stages, slot);
+        if (lane == 0 && issued < n_stages_total) { issue(pc, slot); advance(pc); }
+        issued++;
 
-        if (chunk == p.NC - 1) {
+        if (cc.chunk == NC - 1) {
             // ---- 4-row transpose-reduce: lanes with (lane & 7) == 0 end up holding one row each ----
             const bool b4 = lane & 16, b3 = lane & 8;
-            float s0 = b4 ? acc[0] : acc[2], s1 = b4 ? acc[1] : acc[3];
+            const float s0 = b4 ? acc[0] : acc[2], s1 = b4 ? acc[1] : acc[3];
             float k0 = b4 ? acc[2] : acc[0], k1 = b4 ? acc[3] : acc[1];
             k0 += __shfl_xor_sync(0xFFFFFFFFu, s0, 16);
             k1 += __shfl_xor_sync(0xFFFFFFFFu, s1, 16);
-            float sv = b3 ? k0 : k1, kv = b3 ? k1 : k0;
+            const float sv = b3 ? k0 : k1;
+            float kv = b3 ? k1 : k0;
             kv += __shfl_xor_sync(0xFFFFFFFFu, sv, 8);
             kv += __shfl_xor_sync(0xFFFFFFFFu, kv, 4);
             kv += __shfl_xor_sync(0xFFFFFFFFu, kv, 2);
             kv += __shfl_xor_sync(0xFFFFFFFFu, kv, 1);
-            const int row = g * RG + (b4 ? 2 : 0) + (b3 ? 1 : 0);
+            const KqMat& m = p.mat[cc.mi];
+            const int row = cc.gl * RG + (b4 ? 2 : 0) + (b3 ? 1 : 0);
             if ((lane & 7) == 0) {
                 if (p.epilogue == GEMV_SWIGLU) {
-                    if (seg == 0) {
+                    if (cc.seg == 0) {
                         gate_keep = kv;
                     } else if (row < m.out) {
                         // silu(g) * u with the reference's fast-math expression (gemm.cu:713-725)
-                        float gv = gate_keep;
+                        const float gv = gate_keep;
                         p.mat[0].y[row] = __fdividef(gv, 1.0f + __expf(-gv)) * kv;
                     }
                 } else if (row < m.out) {
@@ -367,6 +394,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
             }
             acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
         }
+        advance(cc);
+        if (++slot == stages) { slot = 0; parity ^= 1u; }
     }
 }
 
@@ -382,18 +411,50 @@ int num_sms() {
     return g_num_sms;
 }
 
-template <int WARPS>
+constexpr size_t SMEM_CAP = 227 * 1024 - 256;    // static __shared__ red[] counts against the cap
+
+template <int MASK, int WARPS>
 void launch_kq(const KqParams& p, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        NT_CUDA_CHECK(cudaFuncSetAttribute(gemv_kq_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NT_CUDA_CHECK(cudaFuncSetAttribute(gemv_kq_kernel<MASK, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
         configured = true;
     }
     int grid = num_sms();
-    int need = (p.total_groups + WARPS - 1) / WARPS;
+    const int need = (p.total_groups + WARPS - 1) / WARPS;
     if (need < grid) grid = need;
-    gemv_kq_kernel<WARPS><<<grid, WARPS * 32, smem, s>>>(p);
+    gemv_kq_kernel<MASK, WARPS><<<grid, WARPS * 32, smem, s>>>(p);
     count_launch();
+}
+
+template <int MASK>
+void launch_fmt(KqParams& p, cudaStream_t s) {
+    constexpr int SLOT = RG * BS * max_blk(MASK);
+    const size_t xq_sz = ((size_t)3 * p.K + (size_t)(p.K / 32) * 4 + (size_t)(p.K / 16) * 4 + 127) & ~(size_t)127;
+    const size_t budget = SMEM_CAP - xq_sz - 256;
+    // CTA width: among the widths that afford a 2-deep ring, minimise rounds x warps (tail quantisation when
+    // the SM is issue-bound), preferring wider CTAs on ties.
+    const int sms = num_sms();
+    int best_w = 0;
+    long best_cost = 0;
+    for (int w = 8; w >= 4; w--) {
+        if ((size_t)w * 2 * (SLOT + 8) > budget) continue;
+        const long rounds = (p.total_groups + (long)sms * w - 1) / ((long)sms * w);
+        const long cost = rounds * w;
+        if (!best_w || cost < best_cost) { best_w = w; best_cost = cost; }
+    }
+    NT_CHECK(best_w != 0, "gemv_kq: shared memory budget exceeded");
+    int stages = (int)(budget / ((size_t)best_w * (SLOT + 8)));
+    if (stages > 4) stages = 4;
+    p.stages = stages;
+    const size_t smem = xq_sz + (size_t)best_w * stages * (SLOT + 8);
+    switch (best_w) {
+        case 8: launch_kq<MASK, 8>(p, smem, s); break;
+        case 7: launch_kq<MASK, 7>(p, smem, s); break;
+        case 6: launch_kq<MASK, 6>(p, smem, s); break;
+        case 5: launch_kq<MASK, 5>(p, smem, s); break;
+        default: launch_kq<MASK, 4>(p, smem, s); break;
+    }
 }
 
 }  // namespace
@@ -402,9 +463,9 @@ bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K) {
     if (n_mat < 1 || n_mat > MAX_MATS || K % 256 != 0 || K <= 0) return false;
     if (3.375 * K > 120 * 1024) return false;   // xq must leave room for the rings
     for (int i = 0; i < n_mat; i++) {
-        int f = fmt_of(mats[i].dtype);
+        const int f = fmt_of(mats[i].dtype);
         if (f < 0 || mats[i].out <= 0) return false;
-        size_t pitch = mats[i].row_pitch ? mats[i].row_pitch : dtype_row_size(mats[i].dtype, K);
+        const size_t pitch = mats[i].row_pitch ? mats[i].row_pitch : dtype_row_size(mats[i].dtype, K);
         if ((reinterpret_cast<uintptr_t>(mats[i].W) & 15) || (pitch & 15)) return false;
         // the last chunk of a row is copied in 16-byte units and must stay inside the row pitch
         const size_t blk = dtype_size(mats[i].dtype);
@@ -415,48 +476,47 @@ bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K) {
     return true;
 }
 
-void gemv_kq(const GemvMat* mats, int n_mat, int K, const void* xq, GemvEpilogue ep, cudaStream_t s) {
+void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpilogue ep, cudaStream_t s) {
     NT_CHECK(gemv_kq_supported(mats, n_mat, K), "gemv_kq: unsupported shape/dtype/alignment");
+    NT_CHECK((in.xq != nullptr) != (in.x != nullptr), "gemv_kq: exactly one of xq / x must be given");
+    if (ep == GEMV_SWIGLU)
+        NT_CHECK(n_mat == 2 && mats[0].out == mats[1].out && mats[0].dtype == mats[1].dtype,
+                 "gemv_kq: SWIGLU needs gate and up of equal rows and dtype");
     KqParams p{};
-    p.n_mat = n_mat;
     p.K = K; p.NB = K / 256; p.NC = (p.NB + BS - 1) / BS;
-    p.xq = static_cast<const int8_t*>(xq);
+    p.xq = static_cast<const int8_t*>(in.xq);
+    p.x_f32 = in.x; p.norm_w = in.norm_w; p.eps = in.eps;
     p.epilogue = (int)ep;
-    int max_blk = 0, total = 0;
+    p.n_mat = n_mat;
+    int total = 0, mask = 0;
     for (int i = 0; i < n_mat; i++) {
         KqMat& m = p.mat[i];
         m.W = static_cast<const uint8_t*>(mats[i].W);
         m.y = mats[i].y;
         m.out = mats[i].out;
         m.groups = (mats[i].out + RG - 1) / RG;
-        m.blk_bytes = (int)dtype_size(mats[i].dtype);
         m.fmt = fmt_of(mats[i].dtype);
         m.row_pitch = (long long)(mats[i].row_pitch ? mats[i].row_pitch : dtype_row_size(mats[i].dtype, K));
-        if (m.blk_bytes > max_blk) max_blk = m.blk_bytes;
         total += m.groups;
+        mask |= 1 << m.fmt;
     }
-    if (ep == GEMV_SWIGLU) {
-        NT_CHECK(n_mat == 2 && mats[0].out == mats[1].out, "gemv_kq: SWIGLU needs gate and up of equal rows");
-        p.n_seg = 2;
-        p.total_groups = p.mat[0].groups;
-    } else {
-        p.n_seg = 1;
-        p.total_groups = total;
+    if (ep == GEMV_SWIGLU) { p.n_seg = 2; p.total_groups = p.mat[0].groups; }
+    else { p.n_seg = 1; p.total_groups = total; }
+    switch (mask) {
+        case 1: launch_fmt<1>(p, s); break;
+        case 2: launch_fmt<2>(p, s); break;
+        case 4: launch_fmt<4>(p, s); break;
+        case 3: launch_fmt<3>(p, s); break;
+        case 5: launch_fmt<5>(p, s); break;
+        case 6: launch_fmt<6>(p, s); break;
+        default: launch_fmt<7>(p, s); break;
     }
-    p.slot_bytes = RG * BS * max_blk;
-    const size_t xq_sz = ((size_t)3 * K + (size_t)(K / 32) * 4 + (size_t)(K / 16) * 4 + 127) & ~(size_t)127;
-    const size_t budget = 227 * 1024 - xq_sz - 256;
-    // pick the widest CTA that still affords a 2-deep ring, then the deepest ring (<= 4)
-    int warps = 8;
-    while (warps > 4 && (size_t)warps * 2 * (p.slot_bytes + 8) > budget) warps -= 2;
-    int stages = (int)(budget / ((size_t)warps * (p.slot_bytes + 8)));
-    if (stages > 4) stages = 4;
-    NT_CHECK(stages >= 1, "gemv_kq: shared memory budget exceeded");
-    p.stages = stages;
-    size_t smem = xq_sz + (size_t)warps * stages * (p.slot_bytes + 8);
-    if (warps == 8) launch_kq<8>(p, smem, s);
-    else if (warps == 6) launch_kq<6>(p, smem, s);
-    else launch_kq<4>(p, smem, s);
+}
+
+void gemv_kq(const GemvMat* mats, int n_mat, int K, const void* xq, GemvEpilogue ep, cudaStream_t s) {
+    GemvInput in;
+    in.xq = xq;
+    gemv_kq(mats, n_mat, K, in, ep, s);
 }
 
 }}  // namespace nt::b200

@@ -32,7 +32,16 @@ enum GemvEpilogue { GEMV_STORE = 0, GEMV_ADD = 1 /* y += W.x (residual) */, GEMV
 
 // Fused K-quant GEMV over up to 3 matrices sharing one activation vector (already in xq form).
 // All matrices must be Q4_K / Q5_K / Q6_K with 16-byte aligned W and row pitch.
+// Where the shared activation vector comes from: either pre-quantised `xq`, or an F32 vector `x` that the
+// kernel quantises in its prologue, optionally RMS-normalised first (x * rsqrt(mean(x^2) + eps) * norm_w).
+struct GemvInput {
+    const void* xq = nullptr;
+    const float* x = nullptr;
+    const float* norm_w = nullptr;
+    float eps = 0.f;
+};
 bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K);
+void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpilogue ep, cudaStream_t s);
 void gemv_kq(const GemvMat* mats, int n_mat, int K, const void* xq, GemvEpilogue ep, cudaStream_t s);
 
 // Generic GEMV for every dtype / any alignment, F32 activations (Q8_0, Q4_0, F16, F32 and
@@ -40,8 +49,6 @@ void gemv_kq(const GemvMat* mats, int n_mat, int K, const void* xq, GemvEpilogue
 void gemv_generic(float* y, const void* W, const float* x, int out, int in, DType dt, size_t row_pitch,
                   GemvEpilogue ep, cudaStream_t s);
 
-// Scratch activations for the stateless launch_gemv entry point (one per device+stream).
-void* gemv_scratch_xq(int K, cudaStream_t s);
 
 // ---- elementwise / norm / rope / kv / attention (reference kernels K10-K21) ----
 void rmsnorm(float* y, const float* x, const float* w, int rows, int hidden, float eps, cudaStream_t s);

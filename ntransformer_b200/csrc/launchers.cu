@@ -6,38 +6,17 @@
 // Launchers are fire-and-forget like the reference's (no error returned, unsupported dtype -> stderr + no-op).
 #include "kernels_internal.h"
 #include "../../include/nt_b200.h"
-#include <map>
-#include <mutex>
 
 namespace nt { namespace b200 {
-
-// One xq scratch per (device, stream): launch_gemv has no workspace argument (kernels.h:34-36).
-void* gemv_scratch_xq(int K, cudaStream_t s) {
-    struct Slot { void* p = nullptr; size_t bytes = 0; };
-    static std::map<std::pair<int, cudaStream_t>, Slot> slots;
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    Slot& sl = slots[{dev, s}];
-    size_t need = xq_bytes(K);
-    if (need > sl.bytes) {
-        if (sl.p) { cudaStreamSynchronize(s); cudaFree(sl.p); }
-        size_t want = need < (512u << 10) ? (512u << 10) : need;      // 512 KiB covers K <= 155k
-        NT_CUDA_CHECK(cudaMalloc(&sl.p, want));
-        sl.bytes = want;
-    }
-    return sl.p;
-}
 
 static void gemv_dispatch(float* y, const void* W, const float* x, int out, int in, DType dt, GemvEpilogue ep, cudaStream_t s) {
     if (out <= 0 || in <= 0) return;
     GemvMat m;
     m.W = W; m.y = y; m.out = out; m.dtype = dt; m.row_pitch = 0;
     if ((dt == DType::Q4_K_M || dt == DType::Q5_K || dt == DType::Q6_K) && gemv_kq_supported(&m, 1, in)) {
-        void* xq = gemv_scratch_xq(in, s);
-        quantize_x(x, xq, in, s);
-        gemv_kq(&m, 1, in, xq, ep, s);
+        GemvInput gi;                 // F32 activations are quantised inside the kernel prologue: one launch, no state
+        gi.x = x;
+        gemv_kq(&m, 1, in, gi, ep, s);
     } else {
         gemv_generic(y, W, x, out, in, dt, 0, ep, s);
     }

@@ -1,0 +1,33 @@
+// xquant.cuh — the block-scaled int8x3 activation quantiser (see kernels_internal.h "xq"), shared by the
+// stand-alone quantise/rmsnorm kernels (global layout) and the GEMV's fused prologue (swizzled shared layout).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nt { namespace b200 {
+
+// Quantises the 32 values held one per lane. Returns the three int8 terms of this lane; *scale_out is
+// absmax/127/16384 (valid in all lanes), *sum16_out the exact F32 sum of this lane's 16-element half.
+__device__ __forceinline__ void quantize_lane32(float v, int& q1, int& q2, int& q3, float& scale_out, float& sum16_out) {
+    float amax = fabsf(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+    const float s = __fdiv_rn(amax, 127.0f);
+    const float t = (amax > 0.f) ? __fdiv_rn(v, s) : 0.f;
+    const float f1 = rintf(t);
+    const float r1 = __fmul_rn(__fsub_rn(t, f1), 128.0f);
+    const float f2 = rintf(r1);
+    const float r2 = __fmul_rn(__fsub_rn(r1, f2), 128.0f);
+    const float f3 = rintf(r2);
+    q1 = (int)f1; q2 = (int)f2; q3 = (int)f3;
+    float sh = v;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) sh = __fadd_rn(sh, __shfl_xor_sync(0xFFFFFFFFu, sh, o));
+    scale_out = __fmul_rn(s, 1.0f / 16384.0f);
+    sum16_out = sh;
+}
+
+// XOR swizzle of a byte offset inside an x plane in shared memory (16-byte columns ^ half-block index).
+__device__ __forceinline__ uint32_t xq_swizzle(uint32_t e) { return e ^ (((e >> 7) & 7u) << 4); }
+
+}}  // namespace nt::b200

@@ -120,7 +120,7 @@ def test_c_api_engine_and_cli(gguf_case):
     e.close()
     cli = ROOT / "ntransformer_b200" / "ntransformer"
     r = subprocess.run([str(cli), "-m", str(path), "-p", "Hello", "-n", "8", "-t", "0", "--repeat-penalty", "1.0", "-c", "64"],
-                       capture_output=True, text=True, timeout=120)
+                       capture_output=True, text=True, errors="replace", timeout=120)
     assert r.returncode == 0 and "Decode: 7 tokens" in r.stderr, r.stderr[-500:]
-    r2 = subprocess.run([str(cli), "-m", str(path), "--streaming"], capture_output=True, text=True, timeout=60)
+    r2 = subprocess.run([str(cli), "-m", str(path), "--streaming"], capture_output=True, text=True, errors="replace", timeout=60)
     assert r2.returncode == 1 and "not supported" in r2.stderr
