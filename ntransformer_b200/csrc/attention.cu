@@ -12,6 +12,7 @@
 //     products are reduced with a transpose-reduce (GC-1 + log2(32/GC) shuffles instead of 5*GC).
 // Compiled with --use_fast_math (expf -> ex2.approx path, as the reference build).
 #include "kernels_internal.h"
+#include "ring.cuh"
 #include <cuda_fp16.h>
 #include <cfloat>
 #include <mutex>
@@ -160,6 +161,8 @@ __global__ void __launch_bounds__(AW * 32) decode_kernel(float* __restrict__ out
                                                          const int* __restrict__ pos_dev) {
     constexpr int HD = DPL * 32;
     extern __shared__ float smem_dyn[];
+    pdl_launch_dependents();
+    pdl_wait();
     if (pos_dev) {                       // CUDA-graph replay: context length lives in device memory
         seq_len = *pos_dev + 1;
         split_len = (seq_len + n_splits - 1) / n_splits;
@@ -194,6 +197,8 @@ __global__ void __launch_bounds__(AW * 32) decode_kernel(float* __restrict__ out
 __global__ void decode_combine_kernel(float* __restrict__ out, const float* __restrict__ scratch, int n_heads, int hd,
                                       int n_splits, int seq_len, int split_len, const int* __restrict__ pos_dev) {
     const int h = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (pos_dev) { seq_len = *pos_dev + 1; split_len = (seq_len + n_splits - 1) / n_splits; }
     const float* ml = scratch + (size_t)n_heads * n_splits * hd + (size_t)h * n_splits * 2;
     const int used = (seq_len + split_len - 1) / split_len;
@@ -286,9 +291,9 @@ void launch_decode_dyn(float* out, const float* q, const __half* kc, const __hal
         NT_CUDA_CHECK(cudaFuncSetAttribute(decode_kernel<DPL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_MAX_DYN_SMEM));
         configured = true;
     }
-    decode_kernel<DPL, GC><<<dim3(groups, n_splits), AW * 32, smem, s>>>(out, q, kc, vc, 0, n_heads, n_kv, scale, n_splits, 0,
-                                                                        scratch, pos_dev);
-    decode_combine_kernel<<<n_heads, 128, 0, s>>>(out, scratch, n_heads, HD, n_splits, 0, 0, pos_dev);
+    launch_k(decode_kernel<DPL, GC>, dim3(groups, n_splits), dim3(AW * 32), smem, s, out, q, kc, vc, 0, n_heads, n_kv, scale,
+             n_splits, 0, scratch, pos_dev);
+    launch_k(decode_combine_kernel, dim3(n_heads), dim3(128), 0, s, out, (const float*)scratch, n_heads, HD, n_splits, 0, 0, pos_dev);
     count_launch(2);
 }
 

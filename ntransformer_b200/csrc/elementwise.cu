@@ -8,6 +8,7 @@
 // Anything that must stay IEEE uses explicit *_rn intrinsics.
 #include "kernels_internal.h"
 #include "xquant.cuh"
+#include "ring.cuh"
 #include <cuda_fp16.h>
 #include <cfloat>
 #include <atomic>
@@ -17,6 +18,9 @@ namespace nt { namespace b200 {
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long launch_count() { return g_launches.load(); }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
+static std::atomic<bool> g_pdl{false};
+void set_pdl(bool on) { g_pdl.store(on); }
+bool pdl_enabled() { return g_pdl.load(); }
 
 namespace {
 
@@ -66,6 +70,8 @@ __device__ __forceinline__ void quantize_block32(float v, int blk, int lane, int
 }
 
 __global__ void quantize_x_kernel(const float* __restrict__ x, int8_t* __restrict__ xq, int K) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (blk * 32 >= K) return;
     quantize_block32(x[blk * 32 + lane], blk, lane, xq, K);
@@ -75,6 +81,8 @@ __global__ void quantize_x_kernel(const float* __restrict__ x, int8_t* __restric
 template <bool HALF_OUT, bool XQ_OUT>
 __global__ void __launch_bounds__(1024) rmsnorm_kernel(void* __restrict__ yv, int8_t* __restrict__ xq, const float* __restrict__ xin,
                                                        const float* __restrict__ w, int hidden, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[32];
     const float* x = xin + (size_t)blockIdx.x * hidden;
     float ss = 0.f;
@@ -92,6 +100,26 @@ __global__ void __launch_bounds__(1024) rmsnorm_kernel(void* __restrict__ yv, in
         }
         if (XQ_OUT) quantize_block32(v, i >> 5, threadIdx.x & 31, xq, hidden);
     }
+}
+
+// Multi-CTA RMSNorm + activation quantiser for the decode step: every CTA recomputes the (cheap, L2-resident)
+// sum of squares in the same order, so all CTAs derive the bit-identical rms_inv, then quantises 8 of the
+// row's 32-element blocks.  ~3 us instead of the 13.7 us of the single-CTA form on hidden = 8192.
+__global__ void __launch_bounds__(256) rmsnorm_xq_kernel(float* __restrict__ y, int8_t* __restrict__ xq, const float* __restrict__ x,
+                                                         const float* __restrict__ w, int hidden, float eps) {
+    __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < hidden; i += 256) { float v = x[i]; ss += v * v; }
+    ss = block_sum(ss, red);
+    const float rms_inv = rsqrtf(ss / hidden + eps);
+    const int blk = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (blk * 32 >= hidden) return;
+    const int e = blk * 32 + lane;
+    const float v = x[e] * rms_inv * w[e];
+    if (y) y[e] = v;
+    quantize_block32(v, blk, lane, xq, hidden);
 }
 
 // ---- RoPE (rotary.cu:16-107) ----
@@ -133,6 +161,8 @@ __global__ void kv_write_kernel(__half* __restrict__ kc, __half* __restrict__ vc
 __global__ void rope_kv_decode_kernel(float* __restrict__ q, float* __restrict__ k, const float* __restrict__ v,
                                       __half* __restrict__ kc, __half* __restrict__ vc, const int* __restrict__ pos_dev,
                                       int n_heads, int n_kv, int head_dim, float theta_base, float freq_scale, int max_seq) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int half_dim = head_dim / 2;
     const int total_q = n_heads * half_dim, total_k = n_kv * half_dim;
@@ -159,10 +189,14 @@ __global__ void rope_kv_decode_kernel(float* __restrict__ q, float* __restrict__
 }
 
 __global__ void silu_mul_kernel(float* __restrict__ out, const float* __restrict__ gate, const float* __restrict__ up, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { float g = gate[i]; float silu = g / (1.0f + expf(-g)); out[i] = silu * up[i]; }
 }
 __global__ void add_kernel(float* out, const float* a, const float* b, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] + b[i];
 }
@@ -266,6 +300,8 @@ __device__ float dequant_at(const uint8_t* row, int dt, int i) {
 }
 __global__ void embed_kernel(float* __restrict__ out, const uint8_t* __restrict__ table, int dt, size_t row_bytes,
                              const int* __restrict__ tokens, int hidden) {
+    pdl_launch_dependents();
+    pdl_wait();
     const uint8_t* row = table + (size_t)tokens[blockIdx.x] * row_bytes;
     for (int i = threadIdx.x; i < hidden; i += blockDim.x) out[(size_t)blockIdx.x * hidden + i] = dequant_at(row, dt, i);
 }
@@ -276,7 +312,7 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 void quantize_x(const float* x, void* xq, int K, cudaStream_t s) {
     NT_CHECK(K % 32 == 0, "quantize_x: K must be a multiple of 32");
-    quantize_x_kernel<<<cdiv(K, 256), 256, 0, s>>>(x, static_cast<int8_t*>(xq), K);
+    launch_k(quantize_x_kernel, dim3(cdiv(K, 256)), dim3(256), 0, s, x, static_cast<int8_t*>(xq), K);
     count_launch();
 }
 
@@ -284,7 +320,7 @@ static int norm_threads(int hidden) { return hidden <= 1024 ? 256 : hidden <= 40
 
 void rmsnorm(float* y, const float* x, const float* w, int rows, int hidden, float eps, cudaStream_t s) {
     if (rows <= 0) return;
-    rmsnorm_kernel<false, false><<<rows, norm_threads(hidden), 0, s>>>(y, nullptr, x, w, hidden, eps);
+    launch_k(rmsnorm_kernel<false, false>, dim3(rows), dim3(norm_threads(hidden)), 0, s, (void*)y, (int8_t*)nullptr, x, w, hidden, eps);
     count_launch();
 }
 void rmsnorm_f16(void* y, const float* x, const float* w, int rows, int hidden, float eps, cudaStream_t s) {
@@ -294,7 +330,7 @@ void rmsnorm_f16(void* y, const float* x, const float* w, int rows, int hidden, 
 }
 void rmsnorm_xq(float* y, void* xq, const float* x, const float* w, int hidden, float eps, cudaStream_t s) {
     NT_CHECK(hidden % 32 == 0, "rmsnorm_xq: hidden must be a multiple of 32");
-    rmsnorm_kernel<false, true><<<1, norm_threads(hidden), 0, s>>>(y, static_cast<int8_t*>(xq), x, w, hidden, eps);
+    launch_k(rmsnorm_xq_kernel, dim3(cdiv(hidden / 32, 8)), dim3(256), 0, s, y, static_cast<int8_t*>(xq), x, w, hidden, eps);
     count_launch();
 }
 void rope(float* q, float* k, const int* positions, int seq_len, int n_heads, int n_kv_heads, int head_dim,
@@ -316,18 +352,18 @@ void copy_to_kv_cache(void* kc, void* vc, const float* k, const float* v, int se
 void rope_kv_decode(float* q, float* k, const float* v, void* kc, void* vc, const int* pos_dev, int n_heads, int n_kv,
                     int hd, float theta, float freq_scale, int max_seq, cudaStream_t s) {
     int total = (n_heads + n_kv) * (hd / 2);
-    rope_kv_decode_kernel<<<cdiv(total, 256), 256, 0, s>>>(q, k, v, static_cast<__half*>(kc), static_cast<__half*>(vc), pos_dev,
-                                                          n_heads, n_kv, hd, theta, freq_scale, max_seq);
+    launch_k(rope_kv_decode_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, q, k, v, static_cast<__half*>(kc),
+             static_cast<__half*>(vc), pos_dev, n_heads, n_kv, hd, theta, freq_scale, max_seq);
     count_launch();
 }
 void silu_mul(float* out, const float* gate, const float* up, int n, cudaStream_t s) {
     if (n <= 0) return;
-    silu_mul_kernel<<<cdiv(n, 256), 256, 0, s>>>(out, gate, up, n);
+    launch_k(silu_mul_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, out, gate, up, n);
     count_launch();
 }
 void add(float* out, const float* a, const float* b, int n, cudaStream_t s) {
     if (n <= 0) return;
-    add_kernel<<<cdiv(n, 256), 256, 0, s>>>(out, a, b, n);
+    launch_k(add_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, out, a, b, n);
     count_launch();
 }
 void add_inplace(float* a, const float* b, int n, cudaStream_t s) { add(a, a, b, n, s); }
@@ -359,8 +395,8 @@ void gemm_f32(float* C, const float* A, const float* B, int M, int N, int K, cud
 }
 void embed_rows(float* out, const void* table, DType dt, const int* tokens_dev, int n_tokens, int hidden, cudaStream_t s) {
     if (n_tokens <= 0) return;
-    embed_kernel<<<n_tokens, 256, 0, s>>>(out, static_cast<const uint8_t*>(table), (int)dt, dtype_row_size(dt, (size_t)hidden),
-                                          tokens_dev, hidden);
+    launch_k(embed_kernel, dim3(n_tokens), dim3(256), 0, s, out, static_cast<const uint8_t*>(table), (int)dt,
+             dtype_row_size(dt, (size_t)hidden), tokens_dev, hidden);
     count_launch();
 }
 

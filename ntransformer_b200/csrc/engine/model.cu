@@ -6,6 +6,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace nt { namespace b200 {
 
@@ -264,12 +265,12 @@ void Model::matvec(const Weight* const* ws, float* const* ys, int n, const float
     for (int i = 0; i < n; i++) { mats[i].W = ws[i]->ptr; mats[i].y = ys[i]; mats[i].out = ws[i]->rows; mats[i].dtype = ws[i]->dtype; mats[i].row_pitch = ws[i]->pitch; }
     GemvInput in;
     if (gemv_kq_supported(mats, n, K)) {
-        if (!norm_w && K > 16384) {            // long vectors (ffn_down): quantise once in a wide kernel, not per CTA
-            quantize_x(x, xq_i_, K, s);
-            in.xq = xq_i_;
-        } else {
-            in.x = x; in.norm_w = norm_w; in.eps = cfg_.norm_eps;
-        }
+        // (RMSNorm +) quantisation as one small multi-CTA launch: measured cheaper than redoing it in the prologue
+        // of each of the 148 GEMV CTAs (profiles/r01_*), and PDL overlaps it with the neighbouring kernels.
+        void* xq = (K == cfg_.hidden_size) ? xq_h_ : (K == inter_l_) ? xq_i_ : xq_a_;
+        if (norm_w) rmsnorm_xq(nullptr, xq, x, norm_w, K, cfg_.norm_eps, s);
+        else quantize_x(x, xq, K, s);
+        in.xq = xq;
         gemv_kq(mats, n, K, in, ep, s);
         return;
     }
@@ -344,8 +345,10 @@ void Model::run_step(bool with_head) {
         cudaGraph_t graph = nullptr;
         const unsigned long long before = launch_count();
         NT_CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        set_pdl(use_pdl_ && !getenv("NT_B200_NO_PDL"));   // programmatic edges between the step's kernels
         step_body(stream_);
         if (with_head) step_head(stream_);
+        set_pdl(false);
         NT_CUDA_CHECK(cudaStreamEndCapture(stream_, &graph));
         NT_CUDA_CHECK(cudaGraphInstantiate(&g, graph, 0));
         NT_CUDA_CHECK(cudaGraphDestroy(graph));

@@ -67,6 +67,7 @@ public:
     size_t bytes_per_token(int ctx) const;
     size_t weight_bytes() const;
     void set_use_graph(bool on) { use_graph_ = on; }
+    void set_use_pdl(bool on) { use_pdl_ = on; }
     void clear_kv();
 
 private:
@@ -104,6 +105,7 @@ private:
     int* argmax_host_ = nullptr;
 
     bool use_graph_ = true;
+    bool use_pdl_ = true;
     cudaGraphExec_t g_full_ = nullptr, g_body_ = nullptr;
     int n_full_ = 0, n_body_ = 0;        // kernels per graph replay
     bool finalized_ = false;

@@ -6,6 +6,7 @@
 // read through L1 (ld.global.nc); 18/34/210-byte blocks are only 2-byte aligned so codes are fetched as
 // 16-bit words.  F32 accumulate, warp-shuffle reduction.
 #include "kernels_internal.h"
+#include "ring.cuh"
 #include <cuda_fp16.h>
 
 namespace nt { namespace b200 {
@@ -177,6 +178,8 @@ __global__ void __launch_bounds__(GW * 32) gemv_generic_kernel(float* __restrict
                                                                size_t pitch, int ep) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = (blockIdx.x * GW + warp) * RPW;
+    pdl_launch_dependents();
+    pdl_wait();
 #pragma unroll
     for (int r = 0; r < RPW; r++) {
         int row = row0 + r;
@@ -194,7 +197,7 @@ void gemv_generic(float* y, const void* W, const float* x, int out, int in, DTyp
     size_t pitch = row_pitch ? row_pitch : dtype_row_size(dt, (size_t)in);
     const uint8_t* w = static_cast<const uint8_t*>(W);
     int grid = (out + GW * RPW - 1) / (GW * RPW);
-#define NT_LAUNCH(DTV) gemv_generic_kernel<(int)DTV><<<grid, GW * 32, 0, s>>>(y, w, x, out, in, pitch, (int)ep)
+#define NT_LAUNCH(DTV) launch_k(gemv_generic_kernel<(int)DTV>, dim3(grid), dim3(GW * 32), 0, s, y, w, x, out, in, pitch, (int)ep)
     switch (dt) {
         case DType::F32: NT_LAUNCH(DType::F32); break;
         case DType::F16: NT_LAUNCH(DType::F16); break;

@@ -310,19 +310,34 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
             const float mean_sq = t / K;
             rms_inv = rsqrtf(mean_sq + p.eps);
         }
-        for (int b = warp; b < K / 32; b += WARPS) {
-            const int e = b * 32 + lane;
-            float v = p.x_f32[e];
-            if (p.norm_w) v = v * rms_inv * p.norm_w[e];
-            int q1, q2, q3;
-            float sc, s16;
-            quantize_lane32(v, q1, q2, q3, sc, s16);
-            const uint32_t se = xq_swizzle((uint32_t)e);
-            xs[se] = (uint8_t)q1;
-            xs[K + se] = (uint8_t)q2;
-            xs[2 * K + se] = (uint8_t)q3;
-            if (lane == 0) xscale[b] = sc;
-            if ((lane & 15) == 0) xsum16[2 * b + (lane >> 4)] = s16;
+        // batches of PB 32-element blocks per warp: the PB loads are issued together (one L2 latency per batch)
+        constexpr int PB = 8;
+        const int nblk = K / 32;
+        for (int b0 = warp; b0 < nblk; b0 += WARPS * PB) {
+            float v[PB], w[PB];
+#pragma unroll
+            for (int j = 0; j < PB; j++) {
+                const int b = b0 + j * WARPS;
+                const int e = min(b, nblk - 1) * 32 + lane;
+                v[j] = p.x_f32[e];
+                w[j] = p.norm_w ? p.norm_w[e] : 1.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < PB; j++) {
+                const int b = b0 + j * WARPS;
+                if (b >= nblk) break;                          // warp-uniform
+                const int e = b * 32 + lane;
+                const float x = p.norm_w ? v[j] * rms_inv * w[j] : v[j];
+                int q1, q2, q3;
+                float sc, s16;
+                quantize_lane32(x, q1, q2, q3, sc, s16);
+                const uint32_t se = xq_swizzle((uint32_t)e);
+                xs[se] = (uint8_t)q1;
+                xs[K + se] = (uint8_t)q2;
+                xs[2 * K + se] = (uint8_t)q3;
+                if (lane == 0) xscale[b] = sc;
+                if ((lane & 15) == 0) xsum16[2 * b + (lane >> 4)] = s16;
+            }
         }
     } else {
         // ---- stage pre-quantised xq into shared memory (swizzled planes) ----
@@ -423,7 +438,7 @@ void launch_kq(const KqParams& p, size_t smem, cudaStream_t s) {
     int grid = num_sms();
     const int need = (p.total_groups + WARPS - 1) / WARPS;
     if (need < grid) grid = need;
-    gemv_kq_kernel<MASK, WARPS><<<grid, WARPS * 32, smem, s>>>(p);
+    launch_k(gemv_kq_kernel<MASK, WARPS>, dim3(grid), dim3(WARPS * 32), smem, s, p);
     count_launch();
 }
 

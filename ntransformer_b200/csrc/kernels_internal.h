@@ -83,6 +83,23 @@ void rope_kv_decode(float* q, float* k, const float* v, void* kc, void* vc, cons
 // Embedding-row gather + dequant on the GPU (reference does this on the CPU, transformer.cpp:419-599).
 void embed_rows(float* out, const void* table, DType dt, const int* tokens_dev, int n_tokens, int hidden, cudaStream_t s);
 
+// Programmatic dependent launch (PDL): when enabled, kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so that a kernel's prologue (barrier init, TMA weight
+// prefetch) overlaps the tail of its predecessor; every kernel executes griddepcontrol.wait before it touches
+// data produced upstream, so ordering is unchanged.  Off by default; the engine turns it on for decode graphs.
+void set_pdl(bool on);
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    NT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 // Number of kernels launched by this library since load (bench.py's gpu_launches claim).
 unsigned long long launch_count();
 void count_launch(int n = 1);
