@@ -202,7 +202,7 @@ def run_ours(args, rank, world):
     roof = None
     if rank == 0:
         names = [(f"blk.{i}.ffn_gate.weight", f"blk.{i}.ffn_up.weight") for i in range(cfg.n_layers)]
-        g0, dt0 = model._keep[names[0][0]]
+        g0, dt0 = model._keep[names[0][0]][:2]
         if dt0 in (DType.Q4_K_M, DType.Q5_K, DType.Q6_K):
             inter_l = cfg.intermediate_size // world
             x = torch.randn(cfg.hidden_size, device="cuda")
@@ -257,6 +257,9 @@ def run_ours(args, rank, world):
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     model.close()
     if world > 1:
         dist.destroy_process_group()
@@ -273,11 +276,11 @@ def cpu_baseline(model, cfg, mix, world):
     picks = [hi, lo] if n > 1 else [0]
     host = {}
     for name in ("token_embd.weight", "output.weight", "output_norm.weight"):
-        t, dt = model._keep[name]
+        t, dt = model._keep[name][:2]
         host[name] = (t.cpu().numpy(), int(dt))
     for j, li in enumerate(picks):
         for suffix in ("attn_norm", "attn_q", "attn_k", "attn_v", "attn_output", "ffn_norm", "ffn_gate", "ffn_up", "ffn_down"):
-            t, dt = model._keep[f"blk.{li}.{suffix}.weight"]
+            t, dt = model._keep[f"blk.{li}.{suffix}.weight"][:2]
             host[f"blk.{j}.{suffix}.weight"] = (t.cpu().numpy(), int(dt))
     for j in range(len(picks), n):          # unused layer slots alias the first sample (never run)
         for suffix in ("attn_norm", "attn_q", "attn_k", "attn_v", "attn_output", "ffn_norm", "ffn_gate", "ffn_up", "ffn_down"):

@@ -10,8 +10,8 @@ using namespace nt::b200;
 
 namespace {
 struct ModelHandle {
+    std::unique_ptr<TPComm> comm;     // declared first => destroyed last: the model's graphs reference the communicator
     Model model;
-    std::unique_ptr<TPComm> comm;
 };
 ModelHandle* H(nt_model_t m) { return static_cast<ModelHandle*>(m); }
 }  // namespace
@@ -154,6 +154,17 @@ int nt_tp_init(nt_model_t m, const void* id128, int rank, int size) {
     if (!m) return -1;
     auto c = std::make_unique<TPComm>();
     if (!c->init(id128, rank, size)) return -2;
+    {   // NCCL builds its channels lazily on the first collective (allocations, IPC handles): do that here, eagerly,
+        // so that nothing of the sort happens inside the decode step's CUDA-graph capture.
+        cudaStream_t st = H(m)->model.stream();
+        float* tmp = nullptr;
+        NT_CUDA_CHECK(cudaMalloc(&tmp, sizeof(float) * 1024 * (size_t)(size + 1)));
+        NT_CUDA_CHECK(cudaMemsetAsync(tmp, 0, sizeof(float) * 1024 * (size_t)(size + 1), st));
+        c->all_reduce_sum(tmp, 1024, st);
+        c->all_gather(tmp, tmp + 1024, 1024, st);
+        NT_CUDA_CHECK(cudaStreamSynchronize(st));
+        NT_CUDA_CHECK(cudaFree(tmp));
+    }
     H(m)->model.set_comm(c.get());
     H(m)->comm = std::move(c);
     return 0;

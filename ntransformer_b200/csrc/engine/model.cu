@@ -52,6 +52,7 @@ size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
 }  // namespace
 
 Model::~Model() {
+    if (stream_) cudaStreamSynchronize(stream_);
     release_graphs();
     for (void* p : owned_) cudaFree(p);
     for (void* p : {(void*)hidden_, (void*)xnorm_, (void*)q_, (void*)k_, (void*)v_, (void*)attn_, (void*)act_, (void*)up_, (void*)part_,
@@ -334,7 +335,7 @@ void Model::step_head(cudaStream_t s) {
 }
 
 void Model::run_step(bool with_head) {
-    if (!use_graph_) {
+    if (!use_graph_ || getenv("NT_B200_NO_GRAPH")) {
         step_body(stream_);
         if (with_head) step_head(stream_);
         return;
@@ -344,7 +345,7 @@ void Model::run_step(bool with_head) {
     if (!g) {
         cudaGraph_t graph = nullptr;
         const unsigned long long before = launch_count();
-        NT_CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        NT_CUDA_CHECK(cudaStreamBeginCapture(stream_, tp_size_ > 1 ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
         set_pdl(use_pdl_ && !getenv("NT_B200_NO_PDL"));   // programmatic edges between the step's kernels
         step_body(stream_);
         if (with_head) step_head(stream_);

@@ -13,6 +13,7 @@ from ._engine_sigs import ModelConfigC
 from ._lib import lib
 from .dtypes import DType
 from .model_spec import LlamaConfig, tensor_table
+from .tp import split_kind
 
 
 class Model:
@@ -39,8 +40,10 @@ class Model:
         """tensors: gguf name -> (torch uint8/float32 CUDA tensor, DType); shapes already sharded for tp_rank."""
         c = ModelConfigC(**cfg.dict())
         h = lib().nt_model_create(C.byref(c), tp_rank, tp_size)
-        for name, (t, dt) in tensors.items():
-            rc = lib().nt_model_set_tensor(h, name.encode(), t.data_ptr(), int(dt), 0)
+        for name, spec in tensors.items():
+            t, dt = spec[0], spec[1]
+            pitch = spec[2] if len(spec) > 2 else 0          # bytes between rows (0 = dense GGUF rows)
+            rc = lib().nt_model_set_tensor(h, name.encode(), t.data_ptr(), int(dt), pitch)
             if rc != 0:
                 raise ValueError(f"engine rejected tensor {name}")
         if lib().nt_model_finalize(h) != 0:
@@ -66,7 +69,15 @@ class Model:
                 t = 1.0 + 0.1 * torch.randn(cols, generator=g, device=device, dtype=torch.float32)
             else:
                 t = random_blocks_cuda(dt, max(rows, 1), cols, s, device=device)
-            tensors[name] = (t.contiguous(), dt)
+            t = t.contiguous()
+            if tp_size > 1 and split_kind(name) == "cols" and t.shape[1] % 16:
+                # column shards: pad the row pitch to 16 B so rows stay TMA-aligned (what the GGUF loader does too)
+                pitch = (t.shape[1] + 15) // 16 * 16
+                padded = torch.zeros((t.shape[0], pitch), dtype=torch.uint8, device=device)
+                padded[:, : t.shape[1]] = t
+                tensors[name] = (padded, dt, pitch)
+            else:
+                tensors[name] = (t, dt)
         torch.cuda.synchronize()
         return cls.from_device_tensors(cfg, tensors, tp_rank, tp_size)
 
@@ -179,7 +190,7 @@ def smoke():
     from oracle import oracle as O
 
     m = Model.synthetic(TINY, "Q4_K_M", seed=7)
-    host = {n: (t.cpu().numpy(), int(dt)) for n, (t, dt) in m._keep.items()}
+    host = {n: (v[0].cpu().numpy(), int(v[1])) for n, v in m._keep.items()}
     om = O.Model(TINY.dict(), host)
     toks = [1, 17, 300, 5]
     got = m.forward(toks, 0).copy()

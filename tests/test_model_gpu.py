@@ -101,7 +101,7 @@ def test_vs_reference_transformer_forward(ref_lib, gguf_case):
 
 def test_synthetic_device_tensor_path_matches_oracle():
     m = Model.synthetic(TINY, "Q4_K_M", seed=3)
-    host = {n: (t.cpu().numpy(), int(dt)) for n, (t, dt) in m._keep.items()}
+    host = {n: (v[0].cpu().numpy(), int(v[1])) for n, v in m._keep.items()}
     om = O.Model(TINY.dict(), host)
     toks = [1, 100, 200, 300]
     assert rel(m.forward(toks, 0), om.forward(toks, 0)) <= 1e-3

@@ -43,7 +43,7 @@ def test_tp_matches_single_gpu(tmp_path, mix, world):
     out = tmp_path / "tp.npz"
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
                         "127.0.0.1", "--master-port", str(port), str(ROOT / "tests" / "tp_worker.py"), str(path), str(out),
-                        str(CFG.max_seq_len)], capture_output=True, text=True, errors="replace", timeout=600)
+                        str(CFG.max_seq_len)], capture_output=True, text=True, errors="replace", timeout=240)
     assert r.returncode == 0, r.stderr[-3000:]
     got = np.load(out)
     assert list(got["ids"]) == ids

@@ -17,8 +17,10 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 m = Model.load(path, max_ctx, tp_rank=rank, tp_size=world)
 m.init_tp()
+print(f"[rank {rank}] tp comm ready", flush=True)
 prompt = [1, 17, 300, 5, 44, 9]
 logits = [m.forward(prompt, 0).copy()]
+print(f"[rank {rank}] prefill done", flush=True)
 ids, tok, pos = [], int(np.argmax(logits[0])), len(prompt)
 for _ in range(12):
     ids.append(tok)
@@ -33,5 +35,8 @@ dist.broadcast(ref, src=0)
 assert torch.equal(t, ref), "ranks diverged"
 if rank == 0:
     np.savez(out, logits=np.stack(logits), ids=np.array(ids))
+dist.barrier()
+torch.cuda.synchronize()
 m.close()
+print(f"[rank {rank}] closed", flush=True)
 dist.destroy_process_group()
