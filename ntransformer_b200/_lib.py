@@ -4,7 +4,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libnt_b200.so"
+import os
+
+# NT_B200_LIB overrides the library path (A/B runs of kernel variants); the default is the in-tree build.
+LIB_PATH = Path(os.environ.get("NT_B200_LIB") or (Path(__file__).resolve().parent / "libnt_b200.so"))
 _lib = None
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t

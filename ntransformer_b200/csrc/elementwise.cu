@@ -59,7 +59,9 @@ __device__ __forceinline__ void quantize_block32(float v, int blk, int lane, int
     int q1, q2, q3;
     float sc, s16;
     quantize_lane32(v, q1, q2, q3, sc, s16);
-    const int e = blk * 32 + lane;
+    // planes are stored in the GEMV's shared-memory order (16-byte columns XOR-swizzled inside each 128-byte line)
+    // so the consumer stages them with one TMA bulk copy
+    const int e = (int)xq_swizzle((uint32_t)(blk * 32 + lane));
     xq[e] = (int8_t)q1;
     xq[K + e] = (int8_t)q2;
     xq[2 * K + e] = (int8_t)q3;
@@ -311,7 +313,7 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 }  // namespace
 
 void quantize_x(const float* x, void* xq, int K, cudaStream_t s) {
-    NT_CHECK(K % 32 == 0, "quantize_x: K must be a multiple of 32");
+    NT_CHECK(K % 128 == 0, "quantize_x: K must be a multiple of 128");
     launch_k(quantize_x_kernel, dim3(cdiv(K, 256)), dim3(256), 0, s, x, static_cast<int8_t*>(xq), K);
     count_launch();
 }
@@ -329,7 +331,7 @@ void rmsnorm_f16(void* y, const float* x, const float* w, int rows, int hidden, 
     count_launch();
 }
 void rmsnorm_xq(float* y, void* xq, const float* x, const float* w, int hidden, float eps, cudaStream_t s) {
-    NT_CHECK(hidden % 32 == 0, "rmsnorm_xq: hidden must be a multiple of 32");
+    NT_CHECK(hidden % 128 == 0, "rmsnorm_xq: hidden must be a multiple of 128");
     launch_k(rmsnorm_xq_kernel, dim3(cdiv(hidden / 32, 8)), dim3(256), 0, s, y, static_cast<int8_t*>(xq), x, w, hidden, eps);
     count_launch();
 }

@@ -29,7 +29,7 @@ namespace nt { namespace b200 {
 namespace {
 
 constexpr int RG = 4;            // rows per warp stage
-constexpr int BS = 8;            // super-blocks per stage chunk (four lanes per super-block)
+constexpr int BS = 16;           // super-blocks per stage chunk (two lanes per super-block)
 constexpr int MAX_MATS = 3;
 
 template <int FMT> struct Fmt;
@@ -69,135 +69,159 @@ struct Cursor {
     int mi, gl;   // matrix index and row-group inside that matrix
 };
 
-// Swizzle of a byte offset inside an x plane: XORs the 16-byte column (address bits 4..6) with S(hb & 3), hb = the
-// 128-element half-block index, S = {0,3,6,5}.  Both lane->data mappings below (8 lanes of an LDS.128 phase = 4
-// half-blocks x 2 quarters) then touch 8 distinct 16-byte columns: conflict-free for Q4_K/Q5_K and for Q6_K.
-__device__ __forceinline__ uint32_t xplane_swz(uint32_t e) {
-    const uint32_t hbits = (e >> 7) & 3u;
-    return e ^ (((hbits ^ (hbits << 1)) & 7u) << 4);
-}
-
-// One stage (RG rows x up to BS super-blocks) of format FMT.  Lane <-> one 64-weight quarter of a super-block:
-// (blk, q) with qb = global quarter index.  x terms for the quarter live in 48 registers and serve all RG rows.
+// One stage (RG rows x up to BS super-blocks) of format FMT: this lane's half super-block against its x terms.
 template <int FMT>
-__device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_base, int blk, int q, uint32_t qb,
+__device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_base, int blk, int h, uint32_t hb,
                                               const uint8_t* __restrict__ xs, int K, const float* __restrict__ xscale,
                                               const float* __restrict__ xsum16, float (&acc)[RG]) {
     constexpr int BLK = Fmt<FMT>::BLK;
     constexpr int ROWP = BS * BLK;            // row pitch inside a stage slot
     const uint8_t* base = slot_base + blk * BLK;
-    const uint32_t hb = qb >> 1;
-    const uint32_t sw = (((hb & 3u) ^ ((hb & 3u) << 1)) & 7u) << 4;
-    int xr[3][16];
+    const uint8_t* xh = xs + hb * 128u;
+    const uint32_t sw = hb & 7u;
     if (FMT <= 1) {
-        // ---------------- Q4_K / Q5_K: quarter q = 64-weight chunk q (sub-blocks 2q, 2q+1) ----------------
+        // ---------------- Q4_K / Q5_K ----------------
         constexpr int QS = (FMT == 0) ? 16 : 48;
-#pragma unroll
-        for (int pl = 0; pl < 3; pl++) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int4 v = *reinterpret_cast<const int4*>(xs + pl * K + ((qb * 64u + 16u * i) ^ sw));
-                xr[pl][4 * i + 0] = v.x; xr[pl][4 * i + 1] = v.y; xr[pl][4 * i + 2] = v.z; xr[pl][4 * i + 3] = v.w;
-            }
-        }
-        const float sx_lo = xscale[qb * 2], sx_hi = xscale[qb * 2 + 1];
-        const float sum_lo = xsum16[qb * 4] + xsum16[qb * 4 + 1], sum_hi = xsum16[qb * 4 + 2] + xsum16[qb * 4 + 3];
-        const int sh16 = 16 * (q & 1);
+        uint32_t sc4[RG], m4[RG];
+        float d[RG], dmin[RG];
 #pragma unroll
         for (int r = 0; r < RG; r++) {
             const int4 hd = *reinterpret_cast<const int4*>(base + r * ROWP);
-            const int4 qa = *reinterpret_cast<const int4*>(base + r * ROWP + QS + q * 32);
-            const int4 qv = *reinterpret_cast<const int4*>(base + r * ROWP + QS + q * 32 + 16);
             const uint32_t w0 = hd.y, w1 = hd.z, w2 = hd.w;
-            uint32_t s4, m4;                                       // packed 6-bit scales / mins of this lane's half
-            if (q < 2) { s4 = w0 & 0x3F3F3F3Fu; m4 = w1 & 0x3F3F3F3Fu; }
-            else { s4 = (w2 & 0x0F0F0F0Fu) | ((w0 >> 2) & 0x30303030u); m4 = ((w2 >> 4) & 0x0F0F0F0Fu) | ((w1 >> 2) & 0x30303030u); }
-            const uint32_t s2 = s4 >> sh16, m2 = m4 >> sh16;
-            const uint32_t qw[8] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w,
-                                    (uint32_t)qv.x, (uint32_t)qv.y, (uint32_t)qv.z, (uint32_t)qv.w};
-            uint32_t qh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (FMT == 1) {
-                const int4 ha = *reinterpret_cast<const int4*>(base + r * ROWP + 16);
-                const int4 hv = *reinterpret_cast<const int4*>(base + r * ROWP + 32);
-                qh[0] = ha.x; qh[1] = ha.y; qh[2] = ha.z; qh[3] = ha.w; qh[4] = hv.x; qh[5] = hv.y; qh[6] = hv.z; qh[7] = hv.w;
-            }
-            int l0 = 0, l1 = 0, l2 = 0, h0 = 0, h1 = 0, h2 = 0;
-#pragma unroll
-            for (int w = 0; w < 8; w++) {
-                uint32_t lo = qw[w] & 0x0F0F0F0Fu;
-                uint32_t hi = (qw[w] >> 4) & 0x0F0F0F0Fu;
-                if (FMT == 1) {
-                    const uint32_t t = qh[w] >> (2 * q);          // bit0 -> low sub-block, bit1 -> high sub-block
-                    lo |= (t << 4) & 0x10101010u;
-                    hi |= (t << 3) & 0x10101010u;
-                }
-                l0 = dp4a_us(lo, xr[0][w], l0); l1 = dp4a_us(lo, xr[1][w], l1); l2 = dp4a_us(lo, xr[2][w], l2);
-                h0 = dp4a_us(hi, xr[0][8 + w], h0); h1 = dp4a_us(hi, xr[1][8 + w], h1); h2 = dp4a_us(hi, xr[2][8 + w], h2);
-            }
-            const float flo = (float)combine3(l0, l1, l2) * sx_lo;
-            const float fhi = (float)combine3(h0, h1, h2) * sx_hi;
-            const float A = fmaf((float)(s2 & 0xFFu), flo, (float)((s2 >> 8) & 0xFFu) * fhi);
-            const float B = fmaf((float)(m2 & 0xFFu), sum_lo, (float)((m2 >> 8) & 0xFFu) * sum_hi);
-            acc[r] += h2f((uint32_t)hd.x & 0xFFFFu) * A - h2f((uint32_t)hd.x >> 16) * B;
+            d[r] = h2f((uint32_t)hd.x & 0xFFFFu);
+            dmin[r] = h2f((uint32_t)hd.x >> 16);
+            const uint32_t sa = w0 & 0x3F3F3F3Fu, ma = w1 & 0x3F3F3F3Fu;
+            const uint32_t sb = (w2 & 0x0F0F0F0Fu) | ((w0 >> 2) & 0x30303030u);
+            const uint32_t mb = ((w2 >> 4) & 0x0F0F0F0Fu) | ((w1 >> 2) & 0x30303030u);
+            sc4[r] = h ? sb : sa;
+            m4[r] = h ? mb : ma;
         }
+        float A[RG] = {0.f, 0.f, 0.f, 0.f}, B[RG] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c2 = 0; c2 < 2; c2++) {
+            int xr[3][16];
+#pragma unroll
+            for (int pl = 0; pl < 3; pl++) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int4 v = *reinterpret_cast<const int4*>(xh + pl * K + (((uint32_t)(c2 * 4 + i) ^ sw) << 4));
+                    xr[pl][4 * i + 0] = v.x; xr[pl][4 * i + 1] = v.y; xr[pl][4 * i + 2] = v.z; xr[pl][4 * i + 3] = v.w;
+                }
+            }
+            const int b32 = hb * 4 + c2 * 2, b16 = hb * 8 + c2 * 4;
+            const float sx_lo = xscale[b32], sx_hi = xscale[b32 + 1];
+            const float sum_lo = xsum16[b16] + xsum16[b16 + 1], sum_hi = xsum16[b16 + 2] + xsum16[b16 + 3];
+            const int cg = 2 * h + c2;
+            // fetch the codes of all RG rows first (independent 16-byte loads in flight together)
+            int4 qa[RG], qb[RG], ha[RG], hbv[RG];
+#pragma unroll
+            for (int r = 0; r < RG; r++) {
+                const uint8_t* qp = base + r * ROWP + QS + h * 64 + c2 * 32;
+                qa[r] = *reinterpret_cast<const int4*>(qp);
+                qb[r] = *reinterpret_cast<const int4*>(qp + 16);
+                if (FMT == 1) {
+                    ha[r] = *reinterpret_cast<const int4*>(base + r * ROWP + 16);
+                    hbv[r] = *reinterpret_cast<const int4*>(base + r * ROWP + 32);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RG; r++) {
+                const uint32_t q[8] = {(uint32_t)qa[r].x, (uint32_t)qa[r].y, (uint32_t)qa[r].z, (uint32_t)qa[r].w,
+                                       (uint32_t)qb[r].x, (uint32_t)qb[r].y, (uint32_t)qb[r].z, (uint32_t)qb[r].w};
+                uint32_t qh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (FMT == 1) {
+                    qh[0] = ha[r].x; qh[1] = ha[r].y; qh[2] = ha[r].z; qh[3] = ha[r].w;
+                    qh[4] = hbv[r].x; qh[5] = hbv[r].y; qh[6] = hbv[r].z; qh[7] = hbv[r].w;
+                }
+                int l0 = 0, l1 = 0, l2 = 0, h0 = 0, h1 = 0, h2 = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    uint32_t lo = q[w] & 0x0F0F0F0Fu;
+                    uint32_t hi = (q[w] >> 4) & 0x0F0F0F0Fu;
+                    if (FMT == 1) {
+                        const uint32_t t = qh[w] >> (2 * cg);     // bit0 -> low sub-block, bit1 -> high sub-block
+                        lo |= (t << 4) & 0x10101010u;
+                        hi |= (t << 3) & 0x10101010u;
+                    }
+                    l0 = dp4a_us(lo, xr[0][w], l0); l1 = dp4a_us(lo, xr[1][w], l1); l2 = dp4a_us(lo, xr[2][w], l2);
+                    h0 = dp4a_us(hi, xr[0][8 + w], h0); h1 = dp4a_us(hi, xr[1][8 + w], h1); h2 = dp4a_us(hi, xr[2][8 + w], h2);
+                }
+                const float flo = (float)combine3(l0, l1, l2) * sx_lo;
+                const float fhi = (float)combine3(h0, h1, h2) * sx_hi;
+                const uint32_t s2 = sc4[r] >> (16 * c2), m2 = m4[r] >> (16 * c2);
+                A[r] = fmaf((float)(s2 & 0xFFu), flo, fmaf((float)((s2 >> 8) & 0xFFu), fhi, A[r]));
+                B[r] = fmaf((float)(m2 & 0xFFu), sum_lo, fmaf((float)((m2 >> 8) & 0xFFu), sum_hi, B[r]));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RG; r++) acc[r] += d[r] * A[r] - dmin[r] * B[r];
     } else {
-        // ---------------- Q6_K: quarter q = (half h = q >> 1, kk = q & 1): weights l in [16kk, 16kk+16) of runs 0..3 ----
-        // 210-byte blocks are only 2-byte aligned: read 4-byte aligned words and realign with PRMT.
-        const int h = q >> 1, kk = q & 1;
+        // ---------------- Q6_K (210-byte blocks: 2-byte aligned, realigned with PRMT) ----------------
         const uint32_t mis = (uint32_t)(blk & 1) * 2u;           // (blk * 210) & 2
         const uint32_t sel = mis ? 0x5432u : 0x3210u;
         const uint8_t* ab = base - mis;                            // 4-byte aligned view of the block
-        float sx[4], c32[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-#pragma unroll
-            for (int pl = 0; pl < 3; pl++) {
-                const int4 v = *reinterpret_cast<const int4*>(xs + pl * K + ((hb * 128u + 32u * j + 16u * kk) ^ sw));
-                xr[pl][4 * j + 0] = v.x; xr[pl][4 * j + 1] = v.y; xr[pl][4 * j + 2] = v.z; xr[pl][4 * j + 3] = v.w;
-            }
-            sx[j] = xscale[hb * 4 + j];
-            c32[j] = 32.0f * xsum16[hb * 8 + 2 * j + kk];
-        }
+        uint32_t scw[RG][2];
+        float d[RG];
 #pragma unroll
         for (int r = 0; r < RG; r++) {
             const uint32_t* sp = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 192 + 8 * h);
             const uint32_t a0 = sp[0], a1 = sp[1], a2 = sp[2];
-            const uint32_t sc0 = __byte_perm(a0, a1, sel), sc1 = __byte_perm(a1, a2, sel);
+            scw[r][0] = __byte_perm(a0, a1, sel);
+            scw[r][1] = __byte_perm(a1, a2, sel);
             const uint32_t dw = *reinterpret_cast<const uint32_t*>(ab + r * ROWP + 208);
-            const float d = h2f(mis ? (dw >> 16) : (dw & 0xFFFFu));
-            const uint32_t* pa = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 64 * h + 16 * kk);          // ql[l]
-            const uint32_t* pb = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 64 * h + 32 + 16 * kk);     // ql[l+32]
-            const uint32_t* ph = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 128 + 32 * h + 16 * kk);    // qh[l]
-            uint32_t ra[5], rb[5], rh[5];
+            d[r] = h2f(mis ? (dw >> 16) : (dw & 0xFFFFu));
+        }
+        float A[RG] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 5; i++) { ra[i] = pa[i]; rb[i] = pb[i]; rh[i] = ph[i]; }
-            int s[4][3] = {};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t qa = __byte_perm(ra[i], ra[i + 1], sel), qv = __byte_perm(rb[i], rb[i + 1], sel);
-                const uint32_t hh = __byte_perm(rh[i], rh[i + 1], sel);
-                const uint32_t q1 = (qa & 0x0F0F0F0Fu) | ((hh << 4) & 0x30303030u);
-                const uint32_t q2 = (qv & 0x0F0F0F0Fu) | ((hh << 2) & 0x30303030u);
-                const uint32_t q3 = ((qa >> 4) & 0x0F0F0F0Fu) | (hh & 0x30303030u);
-                const uint32_t q4 = ((qv >> 4) & 0x0F0F0F0Fu) | ((hh >> 2) & 0x30303030u);
-#pragma unroll
-                for (int pl = 0; pl < 3; pl++) {
-                    s[0][pl] = dp4a_us(q1, xr[pl][0 + i], s[0][pl]);
-                    s[1][pl] = dp4a_us(q2, xr[pl][4 + i], s[1][pl]);
-                    s[2][pl] = dp4a_us(q3, xr[pl][8 + i], s[2][pl]);
-                    s[3][pl] = dp4a_us(q4, xr[pl][12 + i], s[3][pl]);
-                }
-            }
-            float A = 0.f;
+        for (int kk = 0; kk < 2; kk++) {
+            int xr[3][16];
+            float sx[4], c32[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int b = 2 * j + kk;                      // scale index inside the half
-                const int sc = (int)(signed char)(((b < 4 ? sc0 : sc1) >> (8 * (b & 3))) & 0xFFu);
-                // sum over 16 weights of sc * (q - 32) * x = sc * (S * sx - 32 * sum16)
-                A = fmaf((float)sc, fmaf((float)combine3(s[j][0], s[j][1], s[j][2]), sx[j], -c32[j]), A);
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++) {
+                    const int4 v = *reinterpret_cast<const int4*>(xh + pl * K + (((uint32_t)(2 * j + kk) ^ sw) << 4));
+                    xr[pl][4 * j + 0] = v.x; xr[pl][4 * j + 1] = v.y; xr[pl][4 * j + 2] = v.z; xr[pl][4 * j + 3] = v.w;
+                }
+                sx[j] = xscale[hb * 4 + j];
+                c32[j] = 32.0f * xsum16[hb * 8 + 2 * j + kk];
             }
-            acc[r] = fmaf(d, A, acc[r]);
+#pragma unroll
+            for (int r = 0; r < RG; r++) {
+                const uint32_t* pa = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 64 * h + 16 * kk);          // ql[l]
+                const uint32_t* pb = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 64 * h + 32 + 16 * kk);     // ql[l+32]
+                const uint32_t* ph = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 128 + 32 * h + 16 * kk);    // qh[l]
+                uint32_t ra[5], rb[5], rh[5];
+#pragma unroll
+                for (int i = 0; i < 5; i++) { ra[i] = pa[i]; rb[i] = pb[i]; rh[i] = ph[i]; }
+                int s[4][3] = {};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t qa = __byte_perm(ra[i], ra[i + 1], sel), qb = __byte_perm(rb[i], rb[i + 1], sel);
+                    const uint32_t hh = __byte_perm(rh[i], rh[i + 1], sel);
+                    const uint32_t q1 = (qa & 0x0F0F0F0Fu) | ((hh << 4) & 0x30303030u);
+                    const uint32_t q2 = (qb & 0x0F0F0F0Fu) | ((hh << 2) & 0x30303030u);
+                    const uint32_t q3 = ((qa >> 4) & 0x0F0F0F0Fu) | (hh & 0x30303030u);
+                    const uint32_t q4 = ((qb >> 4) & 0x0F0F0F0Fu) | ((hh >> 2) & 0x30303030u);
+#pragma unroll
+                    for (int pl = 0; pl < 3; pl++) {
+                        s[0][pl] = dp4a_us(q1, xr[pl][0 + i], s[0][pl]);
+                        s[1][pl] = dp4a_us(q2, xr[pl][4 + i], s[1][pl]);
+                        s[2][pl] = dp4a_us(q3, xr[pl][8 + i], s[2][pl]);
+                        s[3][pl] = dp4a_us(q4, xr[pl][12 + i], s[3][pl]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int b = 2 * j + kk;                      // scale index inside the half
+                    const int sc = (int)(signed char)((scw[r][b >> 2] >> (8 * (b & 3))) & 0xFFu);
+                    // sum over 16 weights of sc * (q - 32) * x = sc * (S * sx - 32 * sum16)
+                    A[r] = fmaf((float)sc, fmaf((float)combine3(s[j][0], s[j][1], s[j][2]), sx[j], -c32[j]), A[r]);
+                }
+            }
         }
+#pragma unroll
+        for (int r = 0; r < RG; r++) acc[r] = fmaf(d[r], A[r], acc[r]);
     }
 }
 
@@ -255,11 +279,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
         }
     };
 
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + ring_off + (size_t)WARPS * stages * SLOT) + WARPS * stages;
     if (lane == 0) {
         for (int s = 0; s < stages; s++) mbar_init(bars + s, 1);
+        if (warp == 0) mbar_init(xbar, 1);
         mbar_fence_init();
     }
-    __syncwarp();
+    __syncthreads();
     Cursor pc{gw, 0, 0, 0, 0};                 // producer cursor (runs `stages` ahead of the consumer)
     locate(pc);
     int issued = 0;
@@ -308,7 +334,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
                 int q1, q2, q3;
                 float sc, s16;
                 quantize_lane32(x, q1, q2, q3, sc, s16);
-                const uint32_t se = xplane_swz((uint32_t)e);
+                const uint32_t se = xq_swizzle((uint32_t)e);
                 xs[se] = (uint8_t)q1;
                 xs[K + se] = (uint8_t)q2;
                 xs[2 * K + se] = (uint8_t)q3;
@@ -316,23 +342,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
                 if ((lane & 15) == 0) xsum16[2 * b + (lane >> 4)] = s16;
             }
         }
+        __syncthreads();
     } else {
-        // ---- stage pre-quantised xq into shared memory (swizzled planes) ----
-        const int n16 = 3 * K / 16;
-        const int4* src = reinterpret_cast<const int4*>(p.xq);
-        for (int i = threadIdx.x; i < n16; i += WARPS * 32) {
-            const uint32_t byte = (uint32_t)i * 16u;
-            const uint32_t plane = byte / (uint32_t)K, e = byte - plane * (uint32_t)K;
-            *reinterpret_cast<int4*>(xs + plane * (uint32_t)K + xplane_swz(e)) = __ldg(src + i);
+        // ---- pre-quantised xq: the producer kernel already wrote the planes in the swizzled order, so staging is a
+        //      plain TMA bulk copy (<= 32 KB pieces) tracked by one CTA-level mbarrier: no per-thread loads/stores ----
+        if (threadIdx.x == 0) {
+            const uint32_t total = (uint32_t)(3 * (size_t)K + (size_t)(K / 32) * 4 + (size_t)(K / 16) * 4);
+            mbar_expect_tx(xbar, total);
+            for (uint32_t off = 0; off < total; off += 32768u) {
+                const uint32_t n = min(32768u, total - off);
+                bulk_g2s(xs + off, p.xq + off, n, xbar);
+            }
         }
-        const float* fsrc = reinterpret_cast<const float*>(p.xq + 3 * (size_t)K);
-        const int nf = K / 32 + K / 16;
-        for (int i = threadIdx.x; i < nf; i += WARPS * 32) xscale[i] = __ldg(fsrc + i);
+        mbar_wait(xbar, 0);
     }
-    __syncthreads();
     pdl_launch_dependents();
 
-    const int blk = lane >> 2, q = lane & 3;
+    const int blk = lane >> 1, h = lane & 1;
     float acc[RG] = {0.f, 0.f, 0.f, 0.f};
     float gate_keep = 0.f;
     Cursor cc{gw, 0, 0, 0, 0};
@@ -346,11 +372,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
 
         if (blk < nbc) {
             const uint8_t* slot_base = ring + (size_t)slot * SLOT;
-            const uint32_t qb = (uint32_t)((cc.chunk * BS + blk) * 4 + q);      // global quarter-block index
+            const uint32_t hb = (uint32_t)((cc.chunk * BS + blk) * 2 + h);      // global half-block index
             const int fmt = (MASK == 1) ? 0 : (MASK == 2) ? 1 : (MASK == 4) ? 2 : p.mat[cc.mi].fmt;
-            if ((MASK & 1) && fmt == 0) process_stage<0>(slot_base, blk, q, qb, xs, K, xscale, xsum16, acc);
-            if ((MASK & 2) && fmt == 1) process_stage<1>(slot_base, blk, q, qb, xs, K, xscale, xsum16, acc);
-            if ((MASK & 4) && fmt == 2) process_stage<2>(slot_base, blk, q, qb, xs, K, xscale, xsum16, acc);
+            if ((MASK & 1) && fmt == 0) process_stage<0>(slot_base, blk, h, hb, xs, K, xscale, xsum16, acc);
+            if ((MASK & 2) && fmt == 1) process_stage<1>(slot_base, blk, h, hb, xs, K, xscale, xsum16, acc);
+            if ((MASK & 4) && fmt == 2) process_stage<2>(slot_base, blk, h, hb, xs, K, xscale, xsum16, acc);
         }
         __syncwarp();
         if (lane == 0 && issued < n_stages_total) { issue(pc, slot); advance(pc); }
@@ -423,35 +449,32 @@ template <int MASK>
 void launch_fmt(KqParams& p, cudaStream_t s) {
     constexpr int SLOT = RG * BS * max_blk(MASK);
     const size_t xq_sz = ((size_t)3 * p.K + (size_t)(p.K / 32) * 4 + (size_t)(p.K / 16) * 4 + 127) & ~(size_t)127;
-    const size_t budget = SMEM_CAP - xq_sz - 256;
-    // CTA width: 16 warps (4 per scheduler) hide the dp4a / shared-memory latencies that 8 could not
-    // (profiles/r01: issue slots 52% busy at 7 warps).  Take the widest CTA that affords a 2-deep ring, then
-    // trade down to an even split of the row-groups when that removes a tail round (rounds x warps).
+    const size_t budget = SMEM_CAP - xq_sz - 512;
+    // CTA width: among the widths that afford a 2-deep ring, minimise rounds x warps (tail quantisation when
+    // the SM is issue-bound), preferring wider CTAs on ties.
     const int sms = num_sms();
-    static const int kWidths[] = {16, 14, 12, 10, 8, 6, 4};
     int best_w = 0;
     long best_cost = 0;
-    for (int w : kWidths) {
+    for (int w = 12; w >= 4; w--) {
+        if (w == 11 || w == 9) continue;
         if ((size_t)w * 2 * (SLOT + 8) > budget) continue;
-        if (best_w && w < best_w - 4) break;
         const long rounds = (p.total_groups + (long)sms * w - 1) / ((long)sms * w);
         const long cost = rounds * w;
         if (!best_w || cost < best_cost) { best_w = w; best_cost = cost; }
     }
-    const char* force = getenv("NT_B200_GEMV_WARPS");                 // tuning aid
-    if (force && atoi(force) >= 4) { int fw = atoi(force) & ~1; if ((size_t)fw * 2 * (SLOT + 8) <= budget && fw <= 16) best_w = fw; }
+    { const char* f = getenv("NT_B200_GEMV_WARPS"); if (f && atoi(f) >= 4 && (size_t)atoi(f) * 2 * (SLOT + 8) <= budget) best_w = atoi(f); }
     NT_CHECK(best_w != 0, "gemv_kq: shared memory budget exceeded");
     int stages = (int)(budget / ((size_t)best_w * (SLOT + 8)));
     if (stages > 4) stages = 4;
     p.stages = stages;
-    const size_t smem = xq_sz + (size_t)best_w * stages * (SLOT + 8);
+    const size_t smem = xq_sz + (size_t)best_w * stages * (SLOT + 8) + 16;
     switch (best_w) {
-        case 16: launch_kq<MASK, 16>(p, smem, s); break;
-        case 14: launch_kq<MASK, 14>(p, smem, s); break;
         case 12: launch_kq<MASK, 12>(p, smem, s); break;
         case 10: launch_kq<MASK, 10>(p, smem, s); break;
         case 8: launch_kq<MASK, 8>(p, smem, s); break;
+        case 7: launch_kq<MASK, 7>(p, smem, s); break;
         case 6: launch_kq<MASK, 6>(p, smem, s); break;
+        case 5: launch_kq<MASK, 5>(p, smem, s); break;
         default: launch_kq<MASK, 4>(p, smem, s); break;
     }
 }

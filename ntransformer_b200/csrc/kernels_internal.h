@@ -14,7 +14,8 @@ namespace nt { namespace b200 {
 // with q1 in [-127,127], q2,q3 in [-64,64]: |error| <= 2^-22 of the 32-block absmax, i.e. F32-class.
 // Integer dot products against the 4/5/6/8-bit weight codes are exact (IDP.4A), the float work is
 // one scale per 16/32 weights instead of one convert + FMA per weight.
-//   layout for K elements (K % 32 == 0):  [q1: K][q2: K][q3: K][scale: K/32 f32][sum16: K/16 f32]
+//   layout for K elements (K % 128 == 0): [q1: K][q2: K][q3: K][scale: K/32 f32][sum16: K/16 f32]; inside each plane
+//   element e lives at byte e ^ (((e >> 7) & 7) << 4)  (the GEMV's bank-conflict-free shared-memory order)
 // sum16 holds exact F32 sums of x over 16-element groups (for the dmin / -32 offset terms).
 // ---------------------------------------------------------------------------------------------
 inline size_t xq_bytes(int K) { return (size_t)3 * K + (size_t)(K / 32) * 4 + (size_t)(K / 16) * 4; }

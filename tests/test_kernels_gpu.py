@@ -117,7 +117,9 @@ def test_quantize_x_reconstruction():
     K.quantize_x(dev(x), xq, Kn)
     sync()
     raw = xq.cpu().numpy()
-    q = raw[: 3 * Kn].view(np.int8).reshape(3, Kn).astype(np.float64)
+    e = np.arange(Kn)
+    swz = e ^ (((e >> 7) & 7) << 4)                             # planes are stored in the GEMV's swizzled order
+    q = raw[: 3 * Kn].view(np.int8).reshape(3, Kn)[:, swz].astype(np.float64)
     scale = raw[3 * Kn: 3 * Kn + Kn // 32 * 4].view(np.float32).astype(np.float64)
     sum16 = raw[3 * Kn + Kn // 32 * 4:].view(np.float32)
     xhat = np.repeat(scale, 32) * (q[0] * 16384 + q[1] * 128 + q[2])
