@@ -113,7 +113,9 @@ __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_b
 #pragma unroll
                 for (int w = 0; w < 8; w++) {
                     uint32_t lo = q[w] & 0x0F0F0F0Fu;
-                    uint32_t hi = (q[w] >> 4) & 0x0F0F0F0Fu;
+                    // Q4_K: keep the high nibbles in place (codes x16, u8 <= 240) and divide the exact integer sums by 16
+                    // once per sub-block instead of shifting every word; Q5_K needs the shift (5-bit codes x16 overflow u8)
+                    uint32_t hi = (FMT == 0) ? (q[w] & 0xF0F0F0F0u) : ((q[w] >> 4) & 0x0F0F0F0Fu);
                     if (FMT == 1) {
                         const uint32_t t = qh[w] >> (2 * (2 * h + c2));   // bit0 -> low sub-block, bit1 -> high sub-block
                         lo |= (t << 4) & 0x10101010u;
@@ -124,7 +126,8 @@ __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_b
                     h0 = dp4a_us(hi, X.x[0][xh], h0); h1 = dp4a_us(hi, X.x[1][xh], h1); h2 = dp4a_us(hi, X.x[2][xh], h2);
                 }
                 const float flo = (float)combine3(l0, l1, l2) * X.sx[2 * c2];
-                const float fhi = (float)combine3(h0, h1, h2) * X.sx[2 * c2 + 1];
+                const int ihi = (FMT == 0) ? (((h0 * 128 + h1) >> 4) * 128 + (h2 >> 4)) : combine3(h0, h1, h2);
+                const float fhi = (float)ihi * X.sx[2 * c2 + 1];
                 const uint32_t s2 = s4 >> (16 * c2), m2 = m4 >> (16 * c2);
                 A = fmaf((float)(s2 & 0xFFu), flo, fmaf((float)((s2 >> 8) & 0xFFu), fhi, A));
                 B = fmaf((float)(m2 & 0xFFu), X.s16[4 * c2] + X.s16[4 * c2 + 1],
@@ -227,25 +230,35 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
         gl = g;
     };
     const int n_stages_total = n_rounds * n_seg;           // flattened stage index s = round * n_seg + seg
-    auto issue = [&](int s, int slot) {                    // lane 0: TMA copies of stage s into ring slot
-        const int round = s / n_seg, seg = s - round * n_seg;
-        const int g = group_of(round);
+    // Producer cursor (used by lane 0): global row-group and segment of the next stage to fetch.  Kept incremental:
+    // the TMA issue path runs on one lane but costs whole-warp issue slots (profiles/r01: 0.30 instr/weight before).
+    int p_g = group_of(0), p_seg = 0;
+    const int g_stride = (int)gridDim.x * gpc;
+    auto issue_next = [&](int slot) {                      // lane 0: TMA copies of the next stage into ring slot
         uint64_t* bar = bars + slot;
-        if (g >= p.total_groups) { mbar_expect_tx(bar, 0); return; }   // nothing to fetch: just complete the phase
-        int mi, gl;
-        locate(g, seg, mi, gl);
-        const KqMat& m = p.mat[mi];
-        const int blkb = (MASK == 1) ? 144 : (MASK == 2) ? 176 : (MASK == 4) ? 210 : (m.fmt == 0 ? 144 : m.fmt == 1 ? 176 : 210);
-        // copy size rounded up to 16 B (a 210-byte Q6_K tail may spill into row padding; checked on the host)
-        const uint32_t bytes = ((uint32_t)(nbc * blkb) + 15u) & ~15u;
-        mbar_expect_tx(bar, bytes * RG);
-        uint8_t* dst = ring + (size_t)slot * SLOT;
-        const uint8_t* src = m.W + (long long)chunk * (BS * blkb);
+        if (p_g >= p.total_groups) {
+            mbar_expect_tx(bar, 0);                          // nothing to fetch: just complete the phase
+        } else {
+            int mi, gl;
+            locate(p_g, p_seg, mi, gl);
+            const KqMat& m = p.mat[mi];
+            const int blkb = (MASK == 1) ? 144 : (MASK == 2) ? 176 : (MASK == 4) ? 210 : (m.fmt == 0 ? 144 : m.fmt == 1 ? 176 : 210);
+            // copy size rounded up to 16 B (a 210-byte Q6_K tail may spill into row padding; checked on the host)
+            const uint32_t bytes = ((uint32_t)(nbc * blkb) + 15u) & ~15u;
+            mbar_expect_tx(bar, bytes * RG);
+            uint8_t* dst = ring + (size_t)slot * SLOT;
+            const int row0 = gl * RG;
+            const uint8_t* src = m.W + (long long)chunk * (BS * blkb) + (long long)row0 * m.row_pitch;
+            if (row0 + RG <= m.out) {
 #pragma unroll
-        for (int r = 0; r < RG; r++) {
-            const int row = min(gl * RG + r, m.out - 1);
-            bulk_g2s(dst + r * (BS * blkb), src + (long long)row * m.row_pitch, bytes, bar);
+                for (int r = 0; r < RG; r++) bulk_g2s(dst + r * (BS * blkb), src + r * m.row_pitch, bytes, bar);
+            } else {                                         // ragged last group: re-read the last valid row
+#pragma unroll
+                for (int r = 0; r < RG; r++)
+                    bulk_g2s(dst + r * (BS * blkb), src + (long long)min(r, m.out - 1 - row0) * m.row_pitch, bytes, bar);
+            }
         }
+        if (++p_seg == n_seg) { p_seg = 0; p_g += g_stride; }
     };
 
     if (lane == 0) {
@@ -256,7 +269,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     int issued = 0;
     // Weights do not depend on the previous kernel: start streaming before touching x.
     if (lane == 0) {
-        for (; issued < stages && issued < n_stages_total; issued++) issue(issued, issued);
+        for (; issued < stages && issued < n_stages_total; issued++) issue_next(issued);
     }
     pdl_wait();   // no-op unless launched with programmatic stream serialization
 
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
                 if ((MASK & 4) && fmt == 2) process_stage<2>(slot_base, blk, h, X, acc);
             }
             __syncwarp();
-            if (lane == 0 && issued < n_stages_total) issue(issued, slot);
+            if (lane == 0 && issued < n_stages_total) issue_next(slot);
             issued++;
             if (++slot == stages) { slot = 0; parity ^= 1u; }
             res[seg] = reduce4(acc, lane);
