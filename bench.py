@@ -98,6 +98,19 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def ncu_traffic(workload: str, world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture of the same shape (profiles/r01_gemv_gateup_ncu.json); None when no capture exists for this workload."""
+    p = ROOT / "profiles" / "r01_gemv_gateup_ncu.json"
+    if world != 1 or not p.exists():
+        return None
+    try:
+        d = json.load(open(p))
+        return d["dram_bytes_per_launch"] if workload in d.get("workloads", []) else None
+    except Exception:
+        return None
+
+
 def measured_peak_hbm():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -225,7 +238,7 @@ def run_ours(args, rank, world):
             kbytes = 2 * model._keep[names[0][0]][0].numel()
             ach = kbytes / (dur_ms / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": "gemv_kq_kernel (ffn gate+up fused, SwiGLU epilogue)", "achieved": round(ach, 1),
-                    "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                    "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": ncu_traffic(args.workload, world),
                     "bytes_per_launch": kbytes, "avg_launch_us": round(dur_ms * 1e3, 2), "launches_timed": len(evs),
                     "peak_source": peak_src}
         step_ach = b_tok * tok_s / 1e9

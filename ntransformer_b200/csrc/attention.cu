@@ -13,6 +13,7 @@
 // Compiled with --use_fast_math (expf -> ex2.approx path, as the reference build).
 #include "kernels_internal.h"
 #include "ring.cuh"
+#include "xquant.cuh"
 #include <cuda_fp16.h>
 #include <cfloat>
 #include <mutex>
@@ -194,8 +195,11 @@ __global__ void __launch_bounds__(AW * 32) decode_kernel(float* __restrict__ out
 }
 
 // Merge split partials: out[h] = sum_i e^{m_i - m} o_i / sum_i e^{m_i - m} l_i
+// xq_out (optional): also emits the block-scaled int8x3 form of the output vector (kernels_internal.h "xq") that
+// the o-projection GEMV consumes, saving a separate quantise launch.  Requires blockDim.x == 128, hd % 32 == 0.
 __global__ void decode_combine_kernel(float* __restrict__ out, const float* __restrict__ scratch, int n_heads, int hd,
-                                      int n_splits, int seq_len, int split_len, const int* __restrict__ pos_dev) {
+                                      int n_splits, int seq_len, int split_len, const int* __restrict__ pos_dev,
+                                      int8_t* __restrict__ xq_out) {
     const int h = blockIdx.x;
     pdl_launch_dependents();
     pdl_wait();
@@ -207,10 +211,24 @@ __global__ void decode_combine_kernel(float* __restrict__ out, const float* __re
     float l = 0.f;
     for (int i = 0; i < used; i++) l += ml[2 * i + 1] * expf(ml[2 * i] - m);
     const float inv = (l > 0.f) ? 1.0f / l : 0.f;
-    for (int d = threadIdx.x; d < hd; d += blockDim.x) {
+    for (int d = threadIdx.x; d < hd; d += blockDim.x) {       // hd % 32 == 0: whole warps stay together
         float o = 0.f;
         for (int i = 0; i < used; i++) o += scratch[((size_t)h * n_splits + i) * hd + d] * expf(ml[2 * i] - m);
-        out[(size_t)h * hd + d] = o * inv;
+        const float v = o * inv;
+        out[(size_t)h * hd + d] = v;
+        if (xq_out) {
+            const int K = n_heads * hd, e = h * hd + d, lane = threadIdx.x & 31;
+            int q1, q2, q3;
+            float sc, s16;
+            quantize_lane32(v, q1, q2, q3, sc, s16);
+            const int se = (int)xq_swizzle((uint32_t)e);
+            xq_out[se] = (int8_t)q1;
+            xq_out[K + se] = (int8_t)q2;
+            xq_out[2 * K + se] = (int8_t)q3;
+            float* scale = reinterpret_cast<float*>(xq_out + 3 * (size_t)K);
+            if (lane == 0) scale[e >> 5] = sc;
+            if ((lane & 15) == 0) scale[K / 32 + (e >> 4)] = s16;
+        }
     }
 }
 
@@ -271,7 +289,7 @@ void launch_decode(float* out, const float* q, const __half* kc, const __half* v
                                                                         n_splits, split_len, scratch, nullptr);
     count_launch();
     if (n_splits > 1) {
-        decode_combine_kernel<<<n_heads, 128, 0, s>>>(out, scratch, n_heads, HD, n_splits, seq_len, split_len, nullptr);
+        decode_combine_kernel<<<n_heads, 128, 0, s>>>(out, scratch, n_heads, HD, n_splits, seq_len, split_len, nullptr, nullptr);
         count_launch();
     }
 }
@@ -280,7 +298,7 @@ void launch_decode(float* out, const float* q, const __half* kc, const __half* v
 // by max_seq, partials always go through caller-owned scratch (n_heads * n_splits * (HD + 2) floats).
 template <int DPL, int GC>
 void launch_decode_dyn(float* out, const float* q, const __half* kc, const __half* vc, const int* pos_dev, int max_seq,
-                       int n_heads, int n_kv, float scale, float* scratch, int n_splits, cudaStream_t s) {
+                       int n_heads, int n_kv, float scale, float* scratch, int n_splits, int8_t* xq_out, cudaStream_t s) {
     constexpr int HD = DPL * 32;
     const int groups = n_heads / GC;
     const int max_split_len = (max_seq + n_splits - 1) / n_splits;
@@ -293,7 +311,7 @@ void launch_decode_dyn(float* out, const float* q, const __half* kc, const __hal
     }
     launch_k(decode_kernel<DPL, GC>, dim3(groups, n_splits), dim3(AW * 32), smem, s, out, q, kc, vc, 0, n_heads, n_kv, scale,
              n_splits, 0, scratch, pos_dev);
-    launch_k(decode_combine_kernel, dim3(n_heads), dim3(128), 0, s, out, (const float*)scratch, n_heads, HD, n_splits, 0, 0, pos_dev);
+    launch_k(decode_combine_kernel, dim3(n_heads), dim3(128), 0, s, out, (const float*)scratch, n_heads, HD, n_splits, 0, 0, pos_dev, xq_out);
     count_launch(2);
 }
 
@@ -354,11 +372,12 @@ size_t attention_decode_dyn_scratch_floats(int max_seq, int n_heads, int n_kv, i
     return (size_t)n_heads * attention_decode_dyn_splits(max_seq, n_heads, n_kv) * (hd + 2);
 }
 void attention_decode_dyn(float* out, const float* q, const void* kc, const void* vc, const int* pos_dev, int max_seq,
-                          int n_heads, int n_kv, int hd, float scale, float* scratch, cudaStream_t s) {
+                          int n_heads, int n_kv, int hd, float scale, float* scratch, void* xq_out, cudaStream_t s) {
     const __half* k = static_cast<const __half*>(kc);
     const __half* v = static_cast<const __half*>(vc);
     const int n_splits = attention_decode_dyn_splits(max_seq, n_heads, n_kv);
-    NT_DISPATCH_ATTN(launch_decode_dyn, out, q, k, v, pos_dev, max_seq, n_heads, n_kv, scale, scratch, n_splits, s);
+    if (xq_out) NT_CHECK((n_heads * hd) % 128 == 0, "attention_decode_dyn: n_heads * head_dim must be a multiple of 128 for the fused quantiser");
+    NT_DISPATCH_ATTN(launch_decode_dyn, out, q, k, v, pos_dev, max_seq, n_heads, n_kv, scale, scratch, n_splits, static_cast<int8_t*>(xq_out), s);
 }
 
 void attention_prefill(float* out, const float* Q, const void* kc, const void* vc, int seq_len, int start_pos, int n_heads,

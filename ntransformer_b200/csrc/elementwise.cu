@@ -80,8 +80,8 @@ __global__ void quantize_x_kernel(const float* __restrict__ x, int8_t* __restric
 }
 
 // ---- RMSNorm: y = x * rsqrtf(mean(x^2) + eps) * w, one CTA per row (rmsnorm.cu:17-70) ----
-template <bool HALF_OUT, bool XQ_OUT>
-__global__ void __launch_bounds__(1024) rmsnorm_kernel(void* __restrict__ yv, int8_t* __restrict__ xq, const float* __restrict__ xin,
+template <bool HALF_OUT>
+__global__ void __launch_bounds__(1024) rmsnorm_kernel(void* __restrict__ yv, const float* __restrict__ xin,
                                                        const float* __restrict__ w, int hidden, float eps) {
     pdl_launch_dependents();
     pdl_wait();
@@ -92,15 +92,10 @@ __global__ void __launch_bounds__(1024) rmsnorm_kernel(void* __restrict__ yv, in
     ss = block_sum(ss, red);
     float mean_sq = ss / hidden;
     float rms_inv = rsqrtf(mean_sq + eps);
-    // hidden padded up to a multiple of 32 so whole warps enter the quantiser together
-    const int hp = (hidden + 31) & ~31;
-    for (int i = threadIdx.x; i < hp; i += blockDim.x) {
-        float v = (i < hidden) ? x[i] * rms_inv * w[i] : 0.f;
-        if (i < hidden && yv) {
-            if (HALF_OUT) reinterpret_cast<__half*>(yv)[(size_t)blockIdx.x * hidden + i] = __float2half(v);
-            else reinterpret_cast<float*>(yv)[(size_t)blockIdx.x * hidden + i] = v;
-        }
-        if (XQ_OUT) quantize_block32(v, i >> 5, threadIdx.x & 31, xq, hidden);
+    for (int i = threadIdx.x; i < hidden; i += blockDim.x) {
+        const float v = x[i] * rms_inv * w[i];
+        if (HALF_OUT) reinterpret_cast<__half*>(yv)[(size_t)blockIdx.x * hidden + i] = __float2half(v);
+        else reinterpret_cast<float*>(yv)[(size_t)blockIdx.x * hidden + i] = v;
     }
 }
 
@@ -322,12 +317,12 @@ static int norm_threads(int hidden) { return hidden <= 1024 ? 256 : hidden <= 40
 
 void rmsnorm(float* y, const float* x, const float* w, int rows, int hidden, float eps, cudaStream_t s) {
     if (rows <= 0) return;
-    launch_k(rmsnorm_kernel<false, false>, dim3(rows), dim3(norm_threads(hidden)), 0, s, (void*)y, (int8_t*)nullptr, x, w, hidden, eps);
+    launch_k(rmsnorm_kernel<false>, dim3(rows), dim3(norm_threads(hidden)), 0, s, (void*)y, x, w, hidden, eps);
     count_launch();
 }
 void rmsnorm_f16(void* y, const float* x, const float* w, int rows, int hidden, float eps, cudaStream_t s) {
     if (rows <= 0) return;
-    rmsnorm_kernel<true, false><<<rows, norm_threads(hidden), 0, s>>>(y, nullptr, x, w, hidden, eps);
+    rmsnorm_kernel<true><<<rows, norm_threads(hidden), 0, s>>>(y, x, w, hidden, eps);
     count_launch();
 }
 void rmsnorm_xq(float* y, void* xq, const float* x, const float* w, int hidden, float eps, cudaStream_t s) {

@@ -290,6 +290,11 @@ void Model::matvec(const Weight* const* ws, float* const* ys, int n, const float
     }
 }
 
+bool Model::o_xq_fusable(const Weight& wo) const {
+    GemvMat m; m.W = wo.ptr; m.y = nullptr; m.out = wo.rows; m.dtype = wo.dtype; m.row_pitch = wo.pitch;
+    return (nh_l_ * cfg_.head_dim) % 128 == 0 && gemv_kq_supported(&m, 1, wo.cols);
+}
+
 // hidden += all_reduce(partial)   (one exchange per sub-block)
 void Model::reduce_residual(float* partial, cudaStream_t s) {
     NT_CHECK(comm_ != nullptr, "tensor-parallel model without a communicator");
@@ -310,10 +315,18 @@ void Model::step_body(cudaStream_t s) {
         // --- attention sub-block ---
         { const Weight* ws[3] = {&L.wq, &L.wk, &L.wv}; float* ys[3] = {q_, k_, v_}; matvec(ws, ys, 3, hidden_, L.attn_norm, GEMV_STORE, s); }
         rope_kv_decode(q_, k_, v_, kc, vc, pos_dev, nh_l_, nkv_l_, hd, cfg_.rope_theta, cfg_.rope_freq_scale, max_seq, s);
-        attention_decode_dyn(attn_, q_, kc, vc, pos_dev, max_seq, nh_l_, nkv_l_, hd, scale, attn_scratch_, s);
+        const bool o_fused = o_xq_fusable(L.wo);          // attention emits xq for the o-projection directly
+        attention_decode_dyn(attn_, q_, kc, vc, pos_dev, max_seq, nh_l_, nkv_l_, hd, scale, attn_scratch_, o_fused ? xq_a_ : nullptr, s);
         { const Weight* ws[1] = {&L.wo};
-          if (tp_size_ == 1) { float* ys[1] = {hidden_}; matvec(ws, ys, 1, attn_, nullptr, GEMV_ADD, s); }
-          else { float* ys[1] = {part_}; matvec(ws, ys, 1, attn_, nullptr, GEMV_STORE, s); reduce_residual(part_, s); } }
+          float* ys[1] = {tp_size_ == 1 ? hidden_ : part_};
+          const GemvEpilogue ep = tp_size_ == 1 ? GEMV_ADD : GEMV_STORE;
+          if (o_fused) {
+              GemvMat m; m.W = L.wo.ptr; m.y = ys[0]; m.out = L.wo.rows; m.dtype = L.wo.dtype; m.row_pitch = L.wo.pitch;
+              gemv_kq(&m, 1, L.wo.cols, xq_a_, ep, s);
+          } else {
+              matvec(ws, ys, 1, attn_, nullptr, ep, s);
+          }
+          if (tp_size_ > 1) reduce_residual(part_, s); }
         // --- FFN sub-block ---
         { const Weight* ws[2] = {&L.gate, &L.up}; float* ys[2] = {act_, up_}; matvec(ws, ys, 2, hidden_, L.ffn_norm, GEMV_SWIGLU, s); }
         { const Weight* ws[1] = {&L.down};

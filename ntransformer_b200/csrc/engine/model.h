@@ -77,6 +77,7 @@ private:
     void matvec(const Weight* const* ws, float* const* ys, int n, const float* x, const float* norm_w, GemvEpilogue ep,
                 cudaStream_t s);
     void reduce_residual(float* partial, cudaStream_t s);
+    bool o_xq_fusable(const Weight& wo) const;
     const void* upload(const GGUFFile& f, const std::string& name, Weight* w, int split /*0 none,1 rows,2 cols*/);
     void release_graphs();
 
@@ -99,8 +100,6 @@ private:
     void *xq_h_ = nullptr, *xq_a_ = nullptr, *xq_i_ = nullptr;
     void *kc_ = nullptr, *vc_ = nullptr;
     int* step_dev_ = nullptr;            // [0] token, [1] position
-    int* step_host_ = nullptr;           // pinned staging, ring of 64 (token, pos) pairs
-    int step_slot_ = 0;
     int* argmax_dev_ = nullptr;
     int* argmax_host_ = nullptr;
 

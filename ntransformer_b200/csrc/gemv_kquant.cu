@@ -74,6 +74,11 @@ struct XRegs {
 __device__ __forceinline__ float h2f(uint32_t h16) { return __half2float(__ushort_as_half((unsigned short)h16)); }
 __device__ __forceinline__ int combine3(int s0, int s1, int s2) { return (s0 * 128 + s1) * 128 + s2; }
 
+// float(byte IDX of w) without I2F: PRMT the byte under the exponent of 2^23, then subtract 2^23 (exact for 0..255).
+__device__ __forceinline__ float byte_to_float(uint32_t w, int idx) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u + idx)) - 8388608.0f;
+}
+
 // One stage (RG rows x up to BS super-blocks) of format FMT: this lane's half super-block (blk, h) against X.
 template <int FMT>
 __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_base, int blk, int h, const XRegs& X,
@@ -128,10 +133,11 @@ __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_b
                 const float flo = (float)combine3(l0, l1, l2) * X.sx[2 * c2];
                 const int ihi = (FMT == 0) ? (((h0 * 128 + h1) >> 4) * 128 + (h2 >> 4)) : combine3(h0, h1, h2);
                 const float fhi = (float)ihi * X.sx[2 * c2 + 1];
-                const uint32_t s2 = s4 >> (16 * c2), m2 = m4 >> (16 * c2);
-                A = fmaf((float)(s2 & 0xFFu), flo, fmaf((float)((s2 >> 8) & 0xFFu), fhi, A));
-                B = fmaf((float)(m2 & 0xFFu), X.s16[4 * c2] + X.s16[4 * c2 + 1],
-                         fmaf((float)((m2 >> 8) & 0xFFu), X.s16[4 * c2 + 2] + X.s16[4 * c2 + 3], B));
+                // 6-bit scale/min byte -> float on the ALU + FMA pipes (PRMT into a 2^23 mantissa, subtract 2^23): keeps
+                // the conversion unit, which the dp4a stream already saturates, out of the scale path
+                A = fmaf(byte_to_float(s4, 2 * c2), flo, fmaf(byte_to_float(s4, 2 * c2 + 1), fhi, A));
+                B = fmaf(byte_to_float(m4, 2 * c2), X.s16[4 * c2] + X.s16[4 * c2 + 1],
+                         fmaf(byte_to_float(m4, 2 * c2 + 1), X.s16[4 * c2 + 2] + X.s16[4 * c2 + 3], B));
             }
             acc[r] += h2f((uint32_t)hd.x & 0xFFFFu) * A - h2f((uint32_t)hd.x >> 16) * B;
         }

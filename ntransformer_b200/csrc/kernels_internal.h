@@ -76,8 +76,9 @@ void attention_prefill(float* out, const float* Q, const void* kc, const void* v
 // CUDA-graph friendly decode attention: context length = *pos_dev + 1 is read on the device.
 int attention_decode_dyn_splits(int max_seq, int n_heads, int n_kv);
 size_t attention_decode_dyn_scratch_floats(int max_seq, int n_heads, int n_kv, int hd);
+// xq_out (optional): the merged output is also written in xq form for the o-projection GEMV.
 void attention_decode_dyn(float* out, const float* q, const void* kc, const void* vc, const int* pos_dev, int max_seq,
-                          int n_heads, int n_kv, int hd, float scale, float* scratch, cudaStream_t s);
+                          int n_heads, int n_kv, int hd, float scale, float* scratch, void* xq_out, cudaStream_t s);
 // Fused RoPE (q, k in place; reference rotary.cu:16-62, non-interleaved pairs) + F16 KV-cache write at *pos_dev.
 void rope_kv_decode(float* q, float* k, const float* v, void* kc, void* vc, const int* pos_dev, int n_heads, int n_kv,
                     int hd, float theta, float freq_scale, int max_seq, cudaStream_t s);

@@ -180,27 +180,3 @@ class Engine:
         if self._h:
             lib().nt_engine_destroy(self._h)
             self._h = None
-
-
-def smoke():
-    """One tiny decode through the native engine on cuda:0, checked against the CPU oracle."""
-    import torch
-
-    from .model_spec import TINY
-    from oracle import oracle as O
-
-    m = Model.synthetic(TINY, "Q4_K_M", seed=7)
-    host = {n: (v[0].cpu().numpy(), int(v[1])) for n, v in m._keep.items()}
-    om = O.Model(TINY.dict(), host)
-    toks = [1, 17, 300, 5]
-    got = m.forward(toks, 0).copy()
-    want = om.forward(toks, 0)
-    err = float(np.abs(got - want).max() / np.abs(want).max())
-    assert err < 1e-3, err
-    nxt = int(np.argmax(want))
-    assert m.argmax() == nxt
-    got2 = m.forward([nxt], len(toks)).copy()
-    want2 = om.forward([nxt], len(toks))
-    assert float(np.abs(got2 - want2).max() / np.abs(want2).max()) < 1e-3
-    m.close()
-    torch.cuda.synchronize()

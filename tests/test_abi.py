@@ -40,3 +40,15 @@ def test_sass_is_sm100a_with_tma_and_dp4a():
     assert "UBLKCP" in sass, "TMA bulk copies missing from the GEMV"
     assert "IDP.4A" in sass
     assert "SYNCS.ARRIVE.TRANS64" in sass
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under ntransformer_b200/ may import, link or execute it."""
+    pkg = ROOT / "ntransformer_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.h")) + list(pkg.rglob("*.cuh")):
+        if "_build" in f.parts:
+            continue
+        text = f.read_text(errors="replace")
+        assert "nt_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+    out = subprocess.run(["ldd", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "oracle" not in out
