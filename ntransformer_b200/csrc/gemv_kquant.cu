@@ -39,13 +39,14 @@ template <int FMT> struct Fmt;
 template <> struct Fmt<0> { static constexpr int BLK = 144; };   // Q4_K
 template <> struct Fmt<1> { static constexpr int BLK = 176; };   // Q5_K
 template <> struct Fmt<2> { static constexpr int BLK = 210; };   // Q6_K
+template <> struct Fmt<3> { static constexpr int BLK = 272; };   // Q8_0: 8 blocks of 34 B = 256 weights
 
 struct KqMat {
     const uint8_t* W;
     float* y;
     int out;
     int groups;        // ceil(out / RG)
-    int fmt;           // 0 Q4_K, 1 Q5_K, 2 Q6_K
+    int fmt;           // 0 Q4_K, 1 Q5_K, 2 Q6_K, 3 Q8_0 (as groups of 8 blocks)
     long long row_pitch;
 };
 struct KqParams {
@@ -141,6 +142,36 @@ __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_b
             }
             acc[r] += h2f((uint32_t)hd.x & 0xFFFFu) * A - h2f((uint32_t)hd.x >> 16) * B;
         }
+    } else if (FMT == 3) {
+        // ---------------- Q8_0: this lane's 128 weights = 4 blocks of [fp16 d][32 x int8] = 136 bytes (8-byte aligned).
+        // Blocks 0 and 2 start 2 bytes into a word: realign with PRMT; blocks 1 and 3 are word aligned. ----------------
+        const uint8_t* lb = base + h * 136;
+#pragma unroll
+        for (int r = 0; r < RG; r++) {
+            uint32_t w[34];
+#pragma unroll
+            for (int i = 0; i < 17; i++) {
+                const uint2 v = *reinterpret_cast<const uint2*>(lb + r * ROWP + 8 * i);
+                w[2 * i] = v.x; w[2 * i + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int w0 = (j == 0) ? 0 : (j == 1) ? 9 : (j == 2) ? 17 : 26;      // first word holding codes
+                const bool mis = (j & 1) == 0;
+                const float d = h2f((j == 0) ? (w[0] & 0xFFFFu) : (j == 1) ? (w[8] >> 16) : (j == 2) ? (w[17] & 0xFFFFu) : (w[25] >> 16));
+                int s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int q = (int)(mis ? __byte_perm(w[w0 + i], w[w0 + i + 1], 0x5432u) : w[w0 + i]);
+                    s0 = dp4a_ss(q, X.x[0][8 * j + i], s0);
+                    s1 = dp4a_ss(q, X.x[1][8 * j + i], s1);
+                    s2 = dp4a_ss(q, X.x[2][8 * j + i], s2);
+                }
+                // |s0| <= 32*127*127: s0*128+s1 fits s32, the last x128 step is done in F32
+                const float f = fmaf((float)(s0 * 128 + s1), 128.0f, (float)s2);
+                acc[r] = fmaf(d * X.sx[j], f, acc[r]);
+            }
+        }
     } else {
         // ---------------- Q6_K (210-byte blocks: 2-byte aligned, realigned with PRMT) ----------------
         const uint32_t mis = (uint32_t)(blk & 1) * 2u;           // (blk * 210) & 2
@@ -192,7 +223,7 @@ __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_b
     }
 }
 
-__host__ __device__ constexpr int max_blk(int mask) { return (mask & 4) ? 210 : (mask & 2) ? 176 : 144; }
+__host__ __device__ constexpr int max_blk(int mask) { return (mask & 8) ? 272 : (mask & 4) ? 210 : (mask & 2) ? 176 : 144; }
 
 // 4-row transpose-reduce over the warp: on return lanes with (lane & 7) == 0 hold row (lane>>4)*2 + ((lane>>3)&1).
 __device__ __forceinline__ float reduce4(const float (&acc)[RG], int lane) {
@@ -248,7 +279,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
             int mi, gl;
             locate(p_g, p_seg, mi, gl);
             const KqMat& m = p.mat[mi];
-            const int blkb = (MASK == 1) ? 144 : (MASK == 2) ? 176 : (MASK == 4) ? 210 : (m.fmt == 0 ? 144 : m.fmt == 1 ? 176 : 210);
+            const int blkb = (MASK == 1) ? 144 : (MASK == 2) ? 176 : (MASK == 4) ? 210 : (MASK == 8) ? 272 : (m.fmt == 0 ? 144 : m.fmt == 1 ? 176 : 210);
             // copy size rounded up to 16 B (a 210-byte Q6_K tail may spill into row padding; checked on the host)
             const uint32_t bytes = ((uint32_t)(nbc * blkb) + 15u) & ~15u;
             mbar_expect_tx(bar, bytes * RG);
@@ -372,10 +403,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
                 int mi, gl;
                 locate(g, seg, mi, gl);
                 const uint8_t* slot_base = ring + (size_t)slot * SLOT;
-                const int fmt = (MASK == 1) ? 0 : (MASK == 2) ? 1 : (MASK == 4) ? 2 : p.mat[mi].fmt;
+                const int fmt = (MASK == 1) ? 0 : (MASK == 2) ? 1 : (MASK == 4) ? 2 : (MASK == 8) ? 3 : p.mat[mi].fmt;
                 if ((MASK & 1) && fmt == 0) process_stage<0>(slot_base, blk, h, X, acc);
                 if ((MASK & 2) && fmt == 1) process_stage<1>(slot_base, blk, h, X, acc);
                 if ((MASK & 4) && fmt == 2) process_stage<2>(slot_base, blk, h, X, acc);
+                if ((MASK & 8) && fmt == 3) process_stage<3>(slot_base, blk, h, X, acc);
             }
             __syncwarp();
             if (lane == 0 && issued < n_stages_total) issue_next(slot);
@@ -415,7 +447,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     }
 }
 
-int fmt_of(DType dt) { return dt == DType::Q4_K_M ? 0 : dt == DType::Q5_K ? 1 : dt == DType::Q6_K ? 2 : -1; }
+int fmt_of(DType dt) { return dt == DType::Q4_K_M ? 0 : dt == DType::Q5_K ? 1 : dt == DType::Q6_K ? 2 : dt == DType::Q8_0 ? 3 : -1; }
 
 int g_num_sms = 0;
 int num_sms() {
@@ -497,7 +529,7 @@ bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K) {
         const size_t pitch = mats[i].row_pitch ? mats[i].row_pitch : dtype_row_size(mats[i].dtype, K);
         if ((reinterpret_cast<uintptr_t>(mats[i].W) & 15) || (pitch & 15)) return false;
         // the last chunk of a row is copied in 16-byte units and must stay inside the row pitch
-        const size_t blk = dtype_size(mats[i].dtype);
+        const size_t blk = dtype_row_size(mats[i].dtype, 256);     // bytes per 256 weights
         const int last = NB - (NC - 1) * BS;
         const size_t tail_end = (size_t)(NC - 1) * BS * blk + ((last * blk + 15) & ~(size_t)15);
         if (tail_end > pitch) return false;
@@ -512,11 +544,12 @@ void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpi
         NT_CHECK(n_mat == 2 && mats[0].out == mats[1].out, "gemv_kq: SWIGLU needs gate and up of equal rows");
     int mask = 0;
     for (int i = 0; i < n_mat; i++) mask |= 1 << fmt_of(mats[i].dtype);
-    if ((mask == 6 || mask == 7) && ep != GEMV_SWIGLU) {      // rare mixes: one launch per matrix
+    const bool plain = mask == 1 || mask == 2 || mask == 4 || mask == 8 || mask == 3 || mask == 5;
+    if (!plain && ep != GEMV_SWIGLU) {                         // rare mixes: one launch per matrix
         for (int i = 0; i < n_mat; i++) gemv_kq(&mats[i], 1, K, in, ep, s);
         return;
     }
-    NT_CHECK(mask != 6 && mask != 7, "gemv_kq: SWIGLU over a Q5_K+Q6_K mix is not instantiated");
+    NT_CHECK(plain, "gemv_kq: SWIGLU over this format mix is not instantiated");
     KqParams p{};
     p.K = K; p.NB = K / 256; p.NC = (p.NB + BS - 1) / BS;
     p.xq = static_cast<const int8_t*>(in.xq);
@@ -541,6 +574,7 @@ void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpi
         case 2: launch_fmt<2>(p, s); break;
         case 4: launch_fmt<4>(p, s); break;
         case 3: launch_fmt<3>(p, s); break;
+        case 8: launch_fmt<8>(p, s); break;
         default: launch_fmt<5>(p, s); break;
     }
 }

@@ -13,7 +13,7 @@ static void gemv_dispatch(float* y, const void* W, const float* x, int out, int 
     if (out <= 0 || in <= 0) return;
     GemvMat m;
     m.W = W; m.y = y; m.out = out; m.dtype = dt; m.row_pitch = 0;
-    if ((dt == DType::Q4_K_M || dt == DType::Q5_K || dt == DType::Q6_K) && gemv_kq_supported(&m, 1, in)) {
+    if ((dt == DType::Q4_K_M || dt == DType::Q5_K || dt == DType::Q6_K || dt == DType::Q8_0) && gemv_kq_supported(&m, 1, in)) {
         GemvInput gi;                 // F32 activations are quantised inside the kernel prologue: one launch, no state
         gi.x = x;
         gemv_kq(&m, 1, in, gi, ep, s);
