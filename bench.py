@@ -40,6 +40,9 @@ WORKLOADS = {
     "llama3-70b-q6_k-decode": ("70b", "Q6_K", 16, 4096),
     "llama3-8b-q4_k_m-decode": ("8b", "Q4_K_M", 16, 4096),
     "tiny-q4_k_m-decode": ("tiny", "Q4_K_M", 8, 128),
+    # BASELINE.json configs[4]: the step is one whole 4096-token prompt (metric prefill_tok_s); see run_prefill
+    "llama3-8b-f16-prefill-4096": ("8b", "F16", 4096, 4096),
+    "tiny-f16-prefill-96": ("tiny", "F16", 96, 128),
 }
 DTYPE_NOTE = "k-quant codes x block-scaled int8x3 activations via dp4a (s32 exact) + f32 scales/accumulate; KV f16"
 
@@ -119,6 +122,122 @@ def measured_peak_hbm():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_peak_tensor():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.load(open(p))["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, cuBLAS 8192^3 burst)"
+        except Exception:
+            pass
+    return 1750.0, "fallback (B200_PROFILING.md dense bf16)"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_prefill(args, rank, world):
+    """BASELINE.json configs[4]: F16 prefill of a whole prompt through the batched tcgen05 path.  One step = one prompt;
+    value = prompt tokens / s with the prompt ids already on the host side of the C-ABI call but no logits read-back,
+    e2e = the same through nt_model_forward (token ids H2D + logits D2H inside the timed region)."""
+    import torch
+    from ntransformer_b200 import kernels as K
+    from ntransformer_b200.engine import Model
+
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "prefill_tok_s", "unavailable": "the batched prefill path is single-GPU in this round"}))
+        return
+    shape, mix, prompt_len, max_seq = WORKLOADS[args.workload]
+    if args.prompt_tokens is not None:
+        prompt_len = args.prompt_tokens
+    cfg = shape_cfg(shape, max_seq)
+    torch.cuda.set_device(0)
+    model = Model.synthetic(cfg, mix, seed=1234)
+    stream = torch.cuda.ExternalStream(model.stream)
+    vocab = cfg.vocab_size
+    steps = min(args.steps, 16)                                  # a step is a whole prompt
+    prompts = [[token_at(i + 97 * j, vocab) for i in range(prompt_len)] for j in range(4)]
+    for i in range(args.warmup):
+        model.forward_async(prompts[i % 4], 0)
+    model.sync()
+    sampler = ClockSampler(0)
+    launches0 = K.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0.record(stream)
+    for i in range(steps):
+        model.forward_async(prompts[i % 4], 0)
+    ev1.record(stream)
+    model.sync()
+    ms = ev0.elapsed_time(ev1)
+    launches = K.launch_count() - launches0
+    clocks = sampler.stop()
+    tok_s = steps * prompt_len / (ms / 1e3)
+    # end to end
+    t0 = time.perf_counter()
+    for i in range(steps):
+        logits = model.forward(prompts[i % 4], 0)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    assert np.isfinite(logits).all(), "non-finite logits"
+    # per-token replay of the decode step (what the reference's forward loop does, on our kernels) for comparison
+    model.set_prefill_min_tokens(0)
+    n_cmp = min(prompt_len, 64)
+    model.forward_async(prompts[0][:n_cmp], 0)
+    model.sync()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    model.forward_async(prompts[1][:n_cmp], 0)
+    b.record(stream)
+    model.sync()
+    per_token_tok_s = n_cmp / (a.elapsed_time(b) / 1e3)
+    model.set_prefill_min_tokens(16)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM, ffn gate shape), measured live ----
+    peak, peak_src = measured_peak_tensor()
+    T, N, Kd = prompt_len, cfg.intermediate_size, cfg.hidden_size
+    A = torch.randn(T, Kd, device="cuda")
+    W = model._keep["blk.0.ffn_gate.weight"][0]
+    Cm = torch.empty(T, N, device="cuda")
+    ws = torch.empty(K.gemm_f16_tc_workspace_bytes(T, Kd), dtype=torch.uint8, device="cuda")
+    evs = []
+    for r in range(6):
+        K.split_activations(ws, A, T, Kd)
+        x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x.record()
+        K.gemm_f16_tc_ws(Cm, ws, W, T, N, Kd)
+        y.record()
+        if r > 0:
+            evs.append((x, y))
+    torch.cuda.synchronize()
+    dur_ms = float(np.mean([x.elapsed_time(y) for x, y in evs]))
+    flops = 2.0 * T * N * Kd
+    ach = flops / (dur_ms / 1e3) / 1e12
+    n_mat = sum(model._keep[f"blk.0.{n}.weight"][0].numel() // 2 for n in          # uint8 view of F16 -> weights
+                ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down")) * cfg.n_layers
+    step_flops = 2.0 * prompt_len * n_mat + 4.0 * cfg.n_layers * cfg.n_heads * cfg.head_dim * prompt_len * (prompt_len + 1) / 2
+    step_tf = step_flops / (ms / steps / 1e3) / 1e12
+    roof = {"bound": "tensor", "kernel": "gemm_f16_tc_kernel (ffn gate, M=%d N=%d K=%d)" % (T, N, Kd), "achieved": round(ach, 1),
+            "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
+            "flops_per_launch": flops, "avg_launch_us": round(dur_ms * 1e3, 1), "launches_timed": len(evs), "peak_source": peak_src,
+            "note": "algorithmic flops 2MNK; the kernel issues 2x that (F32 activations split into F16 hi+lo to keep parity <= 1e-3)",
+            "step_achieved": round(step_tf, 1), "step_frac": round(step_tf / peak, 4)}
+    line = {
+        "metric": "prefill_tok_s", "value": round(tok_s, 1), "unit": "tok/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16 weights x f32 activations as f16 hi+lo on tcgen05 (f32 accumulate in TMEM); KV f16; attention f32",
+        "data": "synthetic (seeded random F16 weights generated on the GPU)",
+        "config": {"workload": args.workload, "quant_mix": mix, "batch": 1, "prompt_tokens": prompt_len, "max_seq": max_seq,
+                   "parallelism": "single", "l2_policy": "16 GB of weights per prompt exceed the 126 MB L2; no flush needed"},
+        "clocks": clocks,
+        "e2e": {"value": round(steps * prompt_len / (e2e_ms / 1e3), 1), "unit": "tok/s", "h2d_bytes_per_step": 4 * prompt_len,
+                "d2h_bytes_per_step": vocab * 4, "ms_per_step": round(e2e_ms / steps, 3)},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "per_token_replay_tok_s": round(per_token_tok_s, 1),
+    }
+    print(json.dumps(line), flush=True)
+    model.close()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -436,6 +555,8 @@ def main():
         sys.exit("bench.py --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif "prefill" in args.workload:
+        run_prefill(args, rank, world)
     else:
         run_ours(args, rank, world)
 

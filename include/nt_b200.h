@@ -84,6 +84,18 @@ int    nt_b200_gemv_fused(int n_mat, float* const* y, const void* const* W, cons
                           const int* dtypes, int in_features, const void* xq, int epilogue, void* stream);
 void   nt_b200_embed_rows(float* out, const void* table, int dtype, const int* tokens_dev,
                           int n_tokens, int hidden, void* stream);
+/* Prefill GEMM on the tcgen05 tensor cores: C[M,N] (F32, row-major) = A[M,K] (F32) . W[N,K]^T (F16 weights, GGUF F16
+ * row-major).  The reference has no live counterpart (its forward loops launch_gemv per token: src/model/attention.cpp:144-162;
+ * launch_gemm_f32, src/cuda/kernels.h:72-74, is unused).  N % 128 == 0 and K % 64 == 0; workspace holds the F16 hi/lo split
+ * of A.  Returns 0, or -1 for unsupported shapes (nothing launched). */
+size_t nt_b200_gemm_f16_tc_workspace_bytes(int M, int K);
+int    nt_b200_gemm_f16_tc(float* C, const float* A, const void* W_f16, int M, int N, int K,
+                           void* workspace, void* stream);
+/* the two halves of nt_b200_gemm_f16_tc, for callers that reuse one split of A across several weight matrices
+ * (q/k/v, gate/up); add != 0 accumulates into C (residual epilogue) */
+void   nt_b200_split_activations(void* workspace, const float* A, int M, int K, void* stream);
+int    nt_b200_gemm_f16_tc_ws(float* C, const void* workspace, const void* W_f16, int M, int N, int K,
+                              int add, void* stream);
 unsigned long long nt_b200_launch_count(void);   /* kernels launched by this library so far */
 int    nt_b200_stream_sync(void* stream);        /* cudaStreamSynchronize; returns cudaError_t */
 const char* nt_b200_version(void);

@@ -43,6 +43,9 @@ void*  nt_model_stream(nt_model_t m);
 int  nt_model_argmax(nt_model_t m);                 /* greedy token of the last logits, computed on the GPU */
 void nt_model_clear_kv(nt_model_t m);
 void nt_model_use_graph(nt_model_t m, int on);
+/* prompts of >= n tokens use the batched tcgen05 prefill when every layer matrix is F16 and tile-aligned
+ * (default 16; 0 = always replay the per-token decode step like the reference's forward loop) */
+void nt_model_set_prefill_min_tokens(nt_model_t m, int n);
 /* algorithmic bytes read per decoded token by this rank at context length ctx */
 unsigned long long nt_model_bytes_per_token(nt_model_t m, int ctx);
 

@@ -35,6 +35,7 @@ ENGINE_SIGNATURES = {
     "nt_model_argmax": (_i, [_vp]),
     "nt_model_clear_kv": (None, [_vp]),
     "nt_model_use_graph": (None, [_vp, _i]),
+    "nt_model_set_prefill_min_tokens": (None, [_vp, _i]),
     "nt_model_bytes_per_token": (C.c_ulonglong, [_vp, _i]),
     "nt_gguf_describe": (_i, [C.c_char_p, _vp, _sz]),
     "nt_tokenize": (_i, [C.c_char_p, C.c_char_p, _i, _vp, _i]),

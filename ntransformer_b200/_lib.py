@@ -43,6 +43,10 @@ SIGNATURES = {
     "nt_b200_quantize_x": (None, [_vp, _vp, _i, _vp]),
     "nt_b200_gemv_fused": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _i, _vp]),
     "nt_b200_embed_rows": (None, [_vp, _vp, _i, _vp, _i, _i, _vp]),
+    "nt_b200_gemm_f16_tc_workspace_bytes": (_sz, [_i, _i]),
+    "nt_b200_gemm_f16_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "nt_b200_split_activations": (None, [_vp, _vp, _i, _i, _vp]),
+    "nt_b200_gemm_f16_tc_ws": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nt_b200_launch_count": (C.c_ulonglong, []),
     "nt_b200_stream_sync": (_i, [_vp]),
     "nt_b200_version": (C.c_char_p, []),

@@ -353,7 +353,6 @@ void launch_prefill(float* out, const float* Q, const __half* kc, const __half* 
 
 void attention_decode(float* out, const float* q, const void* kc, const void* vc, int seq_len, int n_heads, int n_kv,
                       int hd, int max_seq, float scale, cudaStream_t s) {
-    (void)max_seq;
     if (seq_len <= 0 || n_heads <= 0) return;
     const __half* k = static_cast<const __half*>(kc);
     const __half* v = static_cast<const __half*>(vc);
@@ -382,8 +381,11 @@ void attention_decode_dyn(float* out, const float* q, const void* kc, const void
 
 void attention_prefill(float* out, const float* Q, const void* kc, const void* vc, int seq_len, int start_pos, int n_heads,
                        int n_kv, int hd, int max_seq, float scale, cudaStream_t s) {
-    (void)max_seq;
     if (seq_len <= 0 || n_heads <= 0) return;
+    if (attention_prefill_mma_supported(seq_len, n_heads, n_kv, hd)) {       // prompt-sized chunks: tiled tensor-core kernel
+        attention_prefill_mma(out, Q, kc, vc, seq_len, start_pos, n_heads, n_kv, hd, max_seq, scale, s);
+        return;
+    }
     const __half* k = static_cast<const __half*>(kc);
     const __half* v = static_cast<const __half*>(vc);
     NT_DISPATCH_ATTN(launch_prefill, out, Q, k, v, seq_len, start_pos, n_heads, n_kv, scale, s);

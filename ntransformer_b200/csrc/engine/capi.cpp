@@ -82,6 +82,7 @@ float* nt_model_logits_device(nt_model_t m) { return m ? H(m)->model.logits_devi
 void* nt_model_stream(nt_model_t m) { return m ? (void*)H(m)->model.stream() : nullptr; }
 int nt_model_argmax(nt_model_t m) { return m ? H(m)->model.argmax_last() : -1; }
 void nt_model_clear_kv(nt_model_t m) { if (m) H(m)->model.clear_kv(); }
+void nt_model_set_prefill_min_tokens(nt_model_t m, int n) { if (m) H(m)->model.set_prefill_min_tokens(n); }
 void nt_model_use_graph(nt_model_t m, int on) { if (m) H(m)->model.set_use_graph(on != 0); }
 unsigned long long nt_model_bytes_per_token(nt_model_t m, int ctx) { return m ? H(m)->model.bytes_per_token(ctx) : 0; }
 

@@ -13,6 +13,11 @@ namespace nt { namespace b200 {
 namespace {
 
 __global__ void set_step_kernel(int* step, int token, int pos) { step[0] = token; step[1] = pos; }
+__global__ void iota_kernel(int* out, int first, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = first + i;
+}
+constexpr int PREFILL_CHUNK = 2048;      // tokens per batched pass (bounds the activation buffers; weights re-read per chunk)
 
 // argmax over n floats, lowest index wins ties (reference Sampler::argmax, sampler.cpp:18-28)
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ x, int n, int* __restrict__ out) {
@@ -58,6 +63,9 @@ Model::~Model() {
     for (void* p : {(void*)hidden_, (void*)xnorm_, (void*)q_, (void*)k_, (void*)v_, (void*)attn_, (void*)act_, (void*)up_, (void*)part_,
                     (void*)logits_, (void*)logits_l_, (void*)attn_scratch_, xq_h_, xq_a_, xq_i_, kc_, vc_, (void*)step_dev_,
                     (void*)argmax_dev_})
+        if (p) cudaFree(p);
+    for (void* p : {(void*)pf_.x, (void*)pf_.xn, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, (void*)pf_.g, (void*)pf_.u,
+                    pf_.ws, (void*)pf_.tok, (void*)pf_.pos})
         if (p) cudaFree(p);
     if (argmax_host_) cudaFreeHost(argmax_host_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -374,10 +382,82 @@ void Model::run_step(bool with_head) {
     count_launch(n_kernels);                           // a replay re-runs every captured kernel
 }
 
+bool Model::batched_prefill_ok(int seq_len, int start_pos) const {
+    if (tp_size_ != 1 || prefill_min_tokens_ <= 0 || seq_len < prefill_min_tokens_ || getenv("NT_B200_NO_BATCHED_PREFILL")) return false;
+    if (!attention_prefill_mma_supported(seq_len, nh_l_, nkv_l_, cfg_.head_dim)) return false;
+    for (const LayerWeights& L : layers_)
+        for (const Weight* w : {&L.wq, &L.wk, &L.wv, &L.wo, &L.gate, &L.up, &L.down})
+            if (w->dtype != DType::F16 || !gemm_f16_tc_supported(w->ptr, w->rows, w->cols, w->pitch)) return false;
+    return true;
+}
+
+void Model::ensure_prefill_buffers(int tokens) {
+    if (tokens <= pf_.cap) return;
+    NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (void* p : {(void*)pf_.x, (void*)pf_.xn, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, (void*)pf_.g, (void*)pf_.u,
+                    pf_.ws, (void*)pf_.tok, (void*)pf_.pos})
+        if (p) cudaFree(p);
+    const size_t T = (size_t)((tokens + 127) / 128 * 128);
+    const size_t hidden = (size_t)cfg_.hidden_size, qdim = (size_t)nh_l_ * cfg_.head_dim, kvdim = (size_t)nkv_l_ * cfg_.head_dim;
+    const size_t inter = (size_t)inter_l_, kmax = std::max(std::max(hidden, qdim), inter);
+    pf_.x = dmalloc<float>(T * hidden);  pf_.xn = dmalloc<float>(T * hidden);
+    pf_.q = dmalloc<float>(T * qdim);    pf_.k = dmalloc<float>(T * kvdim);   pf_.v = dmalloc<float>(T * kvdim);
+    pf_.attn = dmalloc<float>(T * qdim); pf_.g = dmalloc<float>(T * inter);   pf_.u = dmalloc<float>(T * inter);
+    pf_.ws = dmalloc<uint8_t>(gemm_f16_tc_workspace_bytes((int)T, (int)kmax));
+    pf_.tok = dmalloc<int>(T);           pf_.pos = dmalloc<int>(T);
+    pf_.cap = (int)T;
+}
+
+void Model::prefill_batched(const int* tokens, int seq_len, int start_pos) {
+    cudaStream_t s = stream_;
+    const int hidden = cfg_.hidden_size, hd = cfg_.head_dim, max_seq = cfg_.max_seq_len, inter = inter_l_;
+    const int qdim = nh_l_ * hd, kvdim = nkv_l_ * hd;
+    const float scale = 1.0f / sqrtf((float)hd);
+    const size_t kv_stride = (size_t)max_seq * nkv_l_ * hd;
+    ensure_prefill_buffers(std::min(seq_len, PREFILL_CHUNK));
+    int last_rows = 0;
+    for (int c0 = 0; c0 < seq_len; c0 += PREFILL_CHUNK) {
+        const int T = std::min(PREFILL_CHUNK, seq_len - c0), p0 = start_pos + c0;
+        last_rows = T;
+        NT_CUDA_CHECK(cudaMemcpyAsync(pf_.tok, tokens + c0, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, s));
+        iota_kernel<<<(T + 255) / 256, 256, 0, s>>>(pf_.pos, p0, T);
+        count_launch();
+        embed_rows(pf_.x, embd_.ptr, embd_.dtype, pf_.tok, T, hidden, s);
+        for (int i = 0; i < cfg_.n_layers; i++) {
+            const LayerWeights& L = layers_[(size_t)i];
+            uint16_t* kc = static_cast<uint16_t*>(kc_) + (size_t)i * kv_stride;
+            uint16_t* vc = static_cast<uint16_t*>(vc_) + (size_t)i * kv_stride;
+            // --- attention sub-block (attention.cpp:120-211 for all T tokens at once) ---
+            rmsnorm(pf_.xn, pf_.x, L.attn_norm, T, hidden, cfg_.norm_eps, s);
+            split_activations(pf_.ws, pf_.xn, T, hidden, s);
+            NT_CHECK(gemm_f16_tc_ws(pf_.q, pf_.ws, L.wq.ptr, T, qdim, hidden, false, s), "prefill GEMM (q) rejected");
+            NT_CHECK(gemm_f16_tc_ws(pf_.k, pf_.ws, L.wk.ptr, T, kvdim, hidden, false, s), "prefill GEMM (k) rejected");
+            NT_CHECK(gemm_f16_tc_ws(pf_.v, pf_.ws, L.wv.ptr, T, kvdim, hidden, false, s), "prefill GEMM (v) rejected");
+            rope(pf_.q, pf_.k, pf_.pos, T, nh_l_, nkv_l_, hd, cfg_.rope_theta, cfg_.rope_freq_scale, false, s);
+            copy_to_kv_cache(kc, vc, pf_.k, pf_.v, T, nkv_l_, hd, p0, max_seq, s);
+            attention_prefill(pf_.attn, pf_.q, kc, vc, T, p0, nh_l_, nkv_l_, hd, max_seq, scale, s);
+            split_activations(pf_.ws, pf_.attn, T, qdim, s);
+            NT_CHECK(gemm_f16_tc_ws(pf_.x, pf_.ws, L.wo.ptr, T, hidden, qdim, true, s), "prefill GEMM (o) rejected");
+            // --- FFN sub-block (ffn.cpp:85-134) ---
+            rmsnorm(pf_.xn, pf_.x, L.ffn_norm, T, hidden, cfg_.norm_eps, s);
+            split_activations(pf_.ws, pf_.xn, T, hidden, s);
+            NT_CHECK(gemm_f16_tc_ws(pf_.g, pf_.ws, L.gate.ptr, T, inter, hidden, false, s), "prefill GEMM (gate) rejected");
+            NT_CHECK(gemm_f16_tc_ws(pf_.u, pf_.ws, L.up.ptr, T, inter, hidden, false, s), "prefill GEMM (up) rejected");
+            silu_mul(pf_.g, pf_.g, pf_.u, T * inter, s);
+            split_activations(pf_.ws, pf_.g, T, inter, s);
+            NT_CHECK(gemm_f16_tc_ws(pf_.x, pf_.ws, L.down.ptr, T, hidden, inter, true, s), "prefill GEMM (down) rejected");
+        }
+    }
+    copy(hidden_, pf_.x + (size_t)(last_rows - 1) * hidden, hidden, s);       // last token's residual stream -> LM head
+    step_head(s);
+}
+
 void Model::forward_async(const int* tokens, int seq_len, int start_pos) {
     NT_CHECK(finalized_, "Model::forward before finalize/load");
     NT_CHECK(seq_len >= 1, "forward: empty token list");
     NT_CHECK(start_pos >= 0 && start_pos + seq_len <= cfg_.max_seq_len, "forward: position beyond the KV cache (max_seq_len)");
+    for (int t = 0; t < seq_len; t++) NT_CHECK(tokens[t] >= 0 && tokens[t] < cfg_.vocab_size, "token id out of range");
+    if (batched_prefill_ok(seq_len, start_pos)) { prefill_batched(tokens, seq_len, start_pos); return; }
     for (int t = 0; t < seq_len; t++) {
         int tok = tokens[t];
         NT_CHECK(tok >= 0 && tok < cfg_.vocab_size, "token id out of range");

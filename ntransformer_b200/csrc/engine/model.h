@@ -68,6 +68,9 @@ public:
     size_t weight_bytes() const;
     void set_use_graph(bool on) { use_graph_ = on; }
     void set_use_pdl(bool on) { use_pdl_ = on; }
+    // Prompts of at least n tokens go through the batched tensor-core prefill when the weights allow it (0 = never).
+    void set_prefill_min_tokens(int n) { prefill_min_tokens_ = n; }
+    bool batched_prefill_ok(int seq_len, int start_pos) const;
     void clear_kv();
 
 private:
@@ -77,6 +80,10 @@ private:
     void matvec(const Weight* const* ws, float* const* ys, int n, const float* x, const float* norm_w, GemvEpilogue ep,
                 cudaStream_t s);
     void reduce_residual(float* partial, cudaStream_t s);
+    // All prompt tokens at once: tcgen05 GEMMs (csrc/prefill_gemm.cu) + batched norm/rope/KV-write/causal attention,
+    // instead of the reference's per-token loop (transformer.cpp:604-669 runs every layer's GEMVs once per token).
+    void prefill_batched(const int* tokens, int seq_len, int start_pos);
+    void ensure_prefill_buffers(int tokens);
     bool o_xq_fusable(const Weight& wo) const;
     const void* upload(const GGUFFile& f, const std::string& name, Weight* w, int split /*0 none,1 rows,2 cols*/);
     void release_graphs();
@@ -102,6 +109,14 @@ private:
     int* step_dev_ = nullptr;            // [0] token, [1] position
     int* argmax_dev_ = nullptr;
     int* argmax_host_ = nullptr;
+
+    struct PrefillBuffers {
+        int cap = 0;                     // tokens per chunk the buffers hold
+        float *x = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *attn = nullptr, *g = nullptr, *u = nullptr;
+        void* ws = nullptr;              // F16 hi/lo split of the current GEMM input
+        int *tok = nullptr, *pos = nullptr;
+    } pf_;
+    int prefill_min_tokens_ = 16;
 
     bool use_graph_ = true;
     bool use_pdl_ = true;

@@ -73,6 +73,10 @@ void attention_decode(float* out, const float* q, const void* kc, const void* vc
                       int n_kv, int hd, int max_seq, float scale, cudaStream_t s);
 void attention_prefill(float* out, const float* Q, const void* kc, const void* vc, int seq_len, int start_pos,
                        int n_heads, int n_kv, int hd, int max_seq, float scale, cudaStream_t s);
+// attention_prefill_mma.cu: 64-query x 64-key tiles on mma.sync (used by attention_prefill for seq_len >= 16, hd 64/128)
+bool attention_prefill_mma_supported(int seq_len, int n_heads, int n_kv, int hd);
+void attention_prefill_mma(float* out, const float* Q, const void* kc, const void* vc, int seq_len, int start_pos, int n_heads,
+                           int n_kv, int hd, int max_seq, float scale, cudaStream_t s);
 // CUDA-graph friendly decode attention: context length = *pos_dev + 1 is read on the device.
 int attention_decode_dyn_splits(int max_seq, int n_heads, int n_kv);
 size_t attention_decode_dyn_scratch_floats(int max_seq, int n_heads, int n_kv, int hd);
@@ -101,6 +105,13 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     cfg.attrs = at; cfg.numAttrs = 1;
     NT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
+
+// prefill_gemm.cu: tcgen05/TMEM GEMM, C[M,N] = A[M,K] (F32, split hi+lo F16) . W[N,K]^T (F16)
+size_t gemm_f16_tc_workspace_bytes(int M, int K);
+bool gemm_f16_tc(float* C, const float* A, const void* W_f16, int M, int N, int K, void* workspace, cudaStream_t s);
+bool gemm_f16_tc_supported(const void* W_f16, int N, int K, size_t row_pitch);
+void split_activations(void* workspace, const float* A, int M, int K, cudaStream_t s);
+bool gemm_f16_tc_ws(float* C, const void* workspace, const void* W_f16, int M, int N, int K, bool add, cudaStream_t s);
 
 // Number of kernels launched by this library since load (bench.py's gpu_launches claim).
 unsigned long long launch_count();

@@ -128,6 +128,16 @@ int nt_b200_gemv_fused(int n_mat, float* const* y, const void* const* W, const i
 void nt_b200_embed_rows(float* out, const void* table, int dt, const int* tokens_dev, int n, int hidden, void* s) {
     nt::b200::embed_rows(out, table, (DType)dt, tokens_dev, n, hidden, static_cast<cudaStream_t>(s));
 }
+size_t nt_b200_gemm_f16_tc_workspace_bytes(int M, int K) { return nt::b200::gemm_f16_tc_workspace_bytes(M, K); }
+int nt_b200_gemm_f16_tc(float* Cm, const float* A, const void* W, int M, int N, int K, void* ws, void* s) {
+    return nt::b200::gemm_f16_tc(Cm, A, W, M, N, K, ws, static_cast<cudaStream_t>(s)) ? 0 : -1;
+}
+void nt_b200_split_activations(void* ws, const float* A, int M, int K, void* s) {
+    nt::b200::split_activations(ws, A, M, K, static_cast<cudaStream_t>(s));
+}
+int nt_b200_gemm_f16_tc_ws(float* Cm, const void* ws, const void* W, int M, int N, int K, int add, void* s) {
+    return nt::b200::gemm_f16_tc_ws(Cm, ws, W, M, N, K, add != 0, static_cast<cudaStream_t>(s)) ? 0 : -1;
+}
 unsigned long long nt_b200_launch_count(void) { return nt::b200::launch_count(); }
 int nt_b200_stream_sync(void* s) { return (int)cudaStreamSynchronize(static_cast<cudaStream_t>(s)); }
 const char* nt_b200_version(void) { return "ntransformer_b200 0.1 (sm_100a)"; }

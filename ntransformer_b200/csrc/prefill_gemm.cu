@@ -1,0 +1,253 @@
+// prefill_gemm.cu — tensor-core GEMM for prefill: C[M,N] (F32) = A[M,K] (F32) . W[N,K]^T (F16 weights), sm_100a.
+//
+// The reference has no batched matmul on its forward path: prefill is a host loop of per-token GEMVs that re-reads
+// every weight matrix once per prompt token (src/model/attention.cpp:144-162, src/model/ffn.cpp:96-133; its
+// launch_gemm_f32, src/cuda/gemm.cu:677-694, is dead code).  This is the dense contraction BASELINE.json config 5
+// names, written for Blackwell's 5th-generation tensor cores:
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a 4-stage shared-memory ring,
+//   * tcgen05.mma.cta_group::1.kind::f16 issued by one elected thread, 128x128 F32 accumulator in TMEM,
+//   * tcgen05.commit -> mbarrier hand-offs (smem slot free / accumulator ready), epilogue via tcgen05.ld.
+// F32 activations keep (almost) their precision on F16 tensor cores by splitting a = hi + lo (two F16 values,
+// ~22 mantissa bits) and accumulating both products into the same TMEM tile; weights are F16 exactly.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include "kernels_internal.h"
+#include "ring.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <mutex>
+
+namespace nt { namespace b200 {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;           // CTA tile; BK halfs = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int TILE_A = BM * BK * 2;                  // 16 KB
+constexpr int TILE_B = BN * BK * 2;                  // 16 KB
+constexpr int STAGE_BYTES = 2 * TILE_A + TILE_B;     // A_hi, A_lo, B
+constexpr int TMEM_COLS = 128;
+
+// a = hi + lo with hi = f16(a), lo = f16(a - hi): 4 floats per thread
+__global__ void split_f32_kernel(__half2* __restrict__ hi, __half2* __restrict__ lo, const float4* __restrict__ a, size_t n4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        const float4 v = a[i];
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        hi[2 * i] = h0; hi[2 * i + 1] = h1;
+        lo[2 * i] = __floats2half2_rn(v.x - f0.x, v.y - f0.y);
+        lo[2 * i + 1] = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    }
+}
+
+// bounded mbarrier wait: a mis-programmed pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 24); spin++) {
+        asm volatile(
+            "{\n .reg .pred p;\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
+// [0,14), leading byte offset [16,30) (unused for swizzled K-major, canonical value 1), stride byte offset [32,46) =
+// 8 rows x 128 B = 1024 B, version 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64).
+__device__ __forceinline__ uint64_t make_desc(const void* smem_ptr) {
+    const uint64_t addr = (uint64_t)(smem_u32(smem_ptr) & 0x3FFFFu) >> 4;
+    return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = F16 (0), both K-major, N >> 3 at
+// [17,23), M >> 4 at [24,29)
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+template <bool ADD>
+__global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                             const __grid_constant__ CUtensorMap map_b,
+                                                             float* __restrict__ C, int M, int Mp, int N, int K) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int num_kb = K / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {                                   // whole warp: allocate the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {                               // ---- TMA producer ----
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % STAGES;
+                wait_or_trap(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+                uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                tma_load_2d(st, &map_a, kb * BK, m0, &full_bar[s]);                 // A_hi rows [m0, m0+128)
+                tma_load_2d(st + TILE_A, &map_a, kb * BK, Mp + m0, &full_bar[s]);   // A_lo lives below A_hi
+                tma_load_2d(st + 2 * TILE_A, &map_b, kb * BK, n0, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                               // ---- MMA issuer ----
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % STAGES;
+                wait_or_trap(&full_bar[s], (kb / STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+                const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + TILE_A), db = make_desc(st + 2 * TILE_A);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; k++)   // advance 32 bytes (>> 4 = 2) inside the 128-byte swizzle row
+                    umma_f16(tmem_base, da_hi + 2 * k, db + 2 * k, IDESC, (kb | k) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; k++)
+                    umma_f16(tmem_base, da_lo + 2 * k, db + 2 * k, IDESC, 1u);
+                umma_commit(&empty_bar[s]);            // smem slot reusable once these MMAs retire
+            }
+            umma_commit(&tmem_full_bar);               // accumulator complete
+        }
+    } else {
+        // ---- epilogue: TMEM -> registers -> C (warp w may only touch TMEM lanes [32 * (w % 4), +32)) ----
+        wait_or_trap(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3;
+        const int row = m0 + quarter * 32 + lane;
+        float* crow = C + (size_t)row * N + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c++) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4* dst = reinterpret_cast<float4*>(crow + c * 32 + j);
+                    float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    if (ADD) { const float4 r = *dst; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }   // residual accumulate
+                    *dst = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    __syncwarp();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+// 2-D F16 tensor [rows][cols] (cols contiguous), box = 64 cols x 128 rows, 128-byte swizzle
+bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {BK, BM};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+size_t gemm_f16_tc_workspace_bytes(int M, int K) {
+    const size_t Mp = ((size_t)M + BM - 1) / BM * BM;
+    return 2 * Mp * (size_t)K * sizeof(__half);
+}
+
+bool gemm_f16_tc_supported(const void* W_f16, int N, int K, size_t row_pitch) {
+    return N > 0 && K > 0 && N % BN == 0 && K % BK == 0 && (row_pitch == 0 || row_pitch == (size_t)K * 2) &&
+           (reinterpret_cast<uintptr_t>(W_f16) & 15) == 0 && encode_fn() != nullptr;
+}
+
+// workspace <- F16 hi/lo split of A[M,K] (rows padded with zeros to a multiple of 128)
+void split_activations(void* workspace, const float* A, int M, int K, cudaStream_t s) {
+    const size_t Mp = ((size_t)M + BM - 1) / BM * BM;
+    __half* hi = static_cast<__half*>(workspace);
+    __half* lo = hi + Mp * (size_t)K;
+    if (Mp != (size_t)M) NT_CUDA_CHECK(cudaMemsetAsync(workspace, 0, gemm_f16_tc_workspace_bytes(M, K), s));
+    const size_t n4 = (size_t)M * K / 4;
+    split_f32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<__half2*>(hi), reinterpret_cast<__half2*>(lo),
+                                                                  reinterpret_cast<const float4*>(A), n4);
+    count_launch();
+}
+
+// C[M,N] (+)= split(A)[M,K] . W[N,K]^T with A already split into `workspace`
+bool gemm_f16_tc_ws(float* C, const void* workspace, const void* W_f16, int M, int N, int K, bool add, cudaStream_t s) {
+    if (M <= 0 || !gemm_f16_tc_supported(W_f16, N, K, 0)) return false;
+    const size_t Mp = ((size_t)M + BM - 1) / BM * BM;
+    CUtensorMap map_a, map_b;
+    if (!make_map(&map_a, workspace, 2 * Mp, (uint64_t)K) || !make_map(&map_b, W_f16, (uint64_t)N, (uint64_t)K)) return false;
+    static bool configured = false;
+    const int smem = STAGES * STAGE_BYTES + 1024;
+    if (!configured) {
+        NT_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NT_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid(N / BN, (unsigned)(Mp / BM));
+    if (add) gemm_f16_tc_kernel<true><<<grid, 192, smem, s>>>(map_a, map_b, C, M, (int)Mp, N, K);
+    else gemm_f16_tc_kernel<false><<<grid, 192, smem, s>>>(map_a, map_b, C, M, (int)Mp, N, K);
+    count_launch();
+    return true;
+}
+
+// C[M,N] = A[M,K] . W[N,K]^T ; N % 128 == 0, K % 64 == 0; workspace >= gemm_f16_tc_workspace_bytes(M, K)
+bool gemm_f16_tc(float* C, const float* A, const void* W_f16, int M, int N, int K, void* workspace, cudaStream_t s) {
+    if (M <= 0 || !gemm_f16_tc_supported(W_f16, N, K, 0)) return false;
+    split_activations(workspace, A, M, K, s);
+    return gemm_f16_tc_ws(C, workspace, W_f16, M, N, K, false, s);
+}
+
+}}  // namespace nt::b200

@@ -124,6 +124,10 @@ class Model:
     def use_graph(self, on: bool):
         lib().nt_model_use_graph(self._h, int(on))
 
+    def set_prefill_min_tokens(self, n: int):
+        """Prompts of >= n tokens take the batched tensor-core prefill (F16 models); 0 = per-token replay only."""
+        lib().nt_model_set_prefill_min_tokens(self._h, int(n))
+
     @property
     def stream(self) -> int:
         return lib().nt_model_stream(self._h)

@@ -130,5 +130,27 @@ def embed_rows(out, table, dtype, tokens_dev, n_tokens, hidden, stream=None):
     lib().nt_b200_embed_rows(_p(out), _p(table), int(dtype), _p(tokens_dev), n_tokens, hidden, _s(stream))
 
 
+def gemm_f16_tc_workspace_bytes(M: int, K: int) -> int:
+    return lib().nt_b200_gemm_f16_tc_workspace_bytes(M, K)
+
+
+def gemm_f16_tc(Cm, A, W_f16, M, N, K, workspace, stream=None):
+    """Prefill GEMM on tcgen05 tensor cores: Cm[M,N] (F32) = A[M,K] (F32) . W_f16[N,K]^T."""
+    rc = lib().nt_b200_gemm_f16_tc(_p(Cm), _p(A), _p(W_f16), M, N, K, _p(workspace), _s(stream))
+    if rc != 0:
+        raise ValueError(f"nt_b200_gemm_f16_tc rejected the shape M={M} N={N} K={K}")
+
+
+def split_activations(workspace, A, M, K, stream=None):
+    lib().nt_b200_split_activations(_p(workspace), _p(A), M, K, _s(stream))
+
+
+def gemm_f16_tc_ws(Cm, workspace, W_f16, M, N, K, add=False, stream=None):
+    """GEMM over an already split activation workspace; add=True accumulates into Cm (residual epilogue)."""
+    rc = lib().nt_b200_gemm_f16_tc_ws(_p(Cm), _p(workspace), _p(W_f16), M, N, K, int(add), _s(stream))
+    if rc != 0:
+        raise ValueError(f"nt_b200_gemm_f16_tc_ws rejected the shape M={M} N={N} K={K}")
+
+
 def launch_count() -> int:
     return int(lib().nt_b200_launch_count())

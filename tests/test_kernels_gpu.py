@@ -314,11 +314,13 @@ def test_attention_decode_vs_reference_cuda(ref_lib, cfg, ctx):
 
 
 @pytest.mark.parametrize("cfg", [(32, 8, 128), (4, 2, 64)])
-@pytest.mark.parametrize("seq,start", [(1, 0), (7, 0), (5, 11), (33, 100)])
+@pytest.mark.parametrize("seq,start", [(1, 0), (7, 0), (5, 11), (33, 100), (16, 0), (64, 0), (100, 37), (200, 50), (65, 63)])
 def test_attention_prefill_vs_oracle(cfg, seq, start):
+    """seq < 16 runs the per-query kernel, seq >= 16 the tiled mma.sync kernel (attention_prefill_mma.cu); the cache is
+    random beyond the visible range too (250 rows: the last key tile runs past max_seq), so masking is exercised."""
     nh, nkv, hd = cfg
     rng = np.random.default_rng(seq * 31 + start)
-    max_seq = 256
+    max_seq = 250
     kc, vc = make_cache(rng, max_seq, nkv, hd)
     Q = rng.standard_normal((seq, nh, hd)).astype(np.float32)
     scale = 1.0 / np.sqrt(hd)

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 import torch
 
+from ntransformer_b200 import kernels as K
 from ntransformer_b200.engine import Engine, Model
 from ntransformer_b200.gguf_write import synthetic_tensors_np, write_gguf
 from ntransformer_b200.model_spec import TINY, LlamaConfig
@@ -67,6 +68,40 @@ def test_graph_replay_equals_eager_launches(gguf_case):
     la, lb = a.forward(toks, 0).copy(), b.forward(toks, 0).copy()
     np.testing.assert_array_equal(la, lb)
     np.testing.assert_array_equal(a.forward([9], 5), b.forward([9], 5))
+    a.close(), b.close()
+
+
+@pytest.mark.parametrize("n_prompt,start", [(16, 0), (97, 0), (128, 0), (40, 23), (200, 0)])
+def test_batched_tensor_core_prefill_vs_oracle_and_per_token(tmp_path, n_prompt, start):
+    """F16 model: the tcgen05 batched prefill (csrc/prefill_gemm.cu) against the oracle's forward and against the
+    per-token replay path; the KV cache it leaves must continue into identical greedy decode."""
+    from dataclasses import replace
+    cfg = replace(TINY, max_seq_len=256)
+    tensors = synthetic_tensors_np(cfg, "F16", seed=5)
+    path = tmp_path / "f16.gguf"
+    write_gguf(path, cfg, tensors)
+    host = {n: (np.ascontiguousarray(a), int(dt)) for n, (a, dt, r, c) in tensors.items()}
+    rng = np.random.default_rng(n_prompt)
+    warm = [int(t) for t in rng.integers(3, cfg.vocab_size, size=start)]
+    prompt = [int(t) for t in rng.integers(3, cfg.vocab_size, size=n_prompt)]
+    a, b, om = Model.load(path, cfg.max_seq_len), Model.load(path, cfg.max_seq_len), O.Model(cfg.dict(), host)
+    b.set_prefill_min_tokens(0)                      # per-token replay
+    a.set_prefill_min_tokens(8)
+    if start:
+        a.set_prefill_min_tokens(0), a.forward(warm, 0), a.set_prefill_min_tokens(8)
+        b.forward(warm, 0), om.forward(warm, 0)
+    n0 = K.launch_count()
+    la = a.forward(prompt, start).copy()
+    batched_launches = K.launch_count() - n0
+    lb, lo = b.forward(prompt, start).copy(), om.forward(prompt, start)
+    assert batched_launches < 25 * cfg.n_layers          # one pass over the layers, not n_prompt of them
+    assert rel(la, lo) <= 1e-3 and rel(la, lb) <= 1e-3
+    pos, ta, tb = start + n_prompt, int(np.argmax(la)), int(np.argmax(lo))
+    for _ in range(12):
+        assert ta == tb
+        la, lo = a.forward([ta], pos), om.forward([tb], pos)
+        assert rel(la, lo) <= 1e-3
+        ta, tb, pos = int(np.argmax(la)), int(np.argmax(lo)), pos + 1
     a.close(), b.close()
 
 
