@@ -197,27 +197,27 @@ def run_prefill(args, rank, world):
     peak, peak_src = measured_peak_tensor()
     T, N, Kd = prompt_len, cfg.intermediate_size, cfg.hidden_size
     A = torch.randn(T, Kd, device="cuda")
-    W = model._keep["blk.0.ffn_gate.weight"][0]
-    Cm = torch.empty(T, N, device="cuda")
+    Wg, Wu = model._keep["blk.0.ffn_gate.weight"][0], model._keep["blk.0.ffn_up.weight"][0]
     ws = torch.empty(K.gemm_f16_tc_workspace_bytes(T, Kd), dtype=torch.uint8, device="cuda")
+    ws2 = torch.empty(K.gemm_f16_tc_workspace_bytes(T, N), dtype=torch.uint8, device="cuda")
+    K.split_activations(ws, A, T, Kd)
     evs = []
     for r in range(6):
-        K.split_activations(ws, A, T, Kd)
         x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         x.record()
-        K.gemm_f16_tc_ws(Cm, ws, W, T, N, Kd)
+        K.gemm_f16_tc_swiglu_ws(ws2, ws, Wg, Wu, T, N, Kd)
         y.record()
         if r > 0:
             evs.append((x, y))
     torch.cuda.synchronize()
     dur_ms = float(np.mean([x.elapsed_time(y) for x, y in evs]))
-    flops = 2.0 * T * N * Kd
+    flops = 2.0 * T * (2 * N) * Kd
     ach = flops / (dur_ms / 1e3) / 1e12
     n_mat = sum(model._keep[f"blk.0.{n}.weight"][0].numel() // 2 for n in          # uint8 view of F16 -> weights
                 ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down")) * cfg.n_layers
     step_flops = 2.0 * prompt_len * n_mat + 4.0 * cfg.n_layers * cfg.n_heads * cfg.head_dim * prompt_len * (prompt_len + 1) / 2
     step_tf = step_flops / (ms / steps / 1e3) / 1e12
-    roof = {"bound": "tensor", "kernel": "gemm_f16_tc_kernel (ffn gate, M=%d N=%d K=%d)" % (T, N, Kd), "achieved": round(ach, 1),
+    roof = {"bound": "tensor", "kernel": "gemm_f16_tc_kernel<256, SWIGLU> (ffn gate+up, M=%d N=2x%d K=%d)" % (T, N, Kd), "achieved": round(ach, 1),
             "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
             "flops_per_launch": flops, "avg_launch_us": round(dur_ms * 1e3, 1), "launches_timed": len(evs), "peak_source": peak_src,
             "note": "algorithmic flops 2MNK; the kernel issues 2x that (F32 activations split into F16 hi+lo to keep parity <= 1e-3)",

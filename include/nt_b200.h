@@ -96,6 +96,13 @@ int    nt_b200_gemm_f16_tc(float* C, const float* A, const void* W_f16, int M, i
 void   nt_b200_split_activations(void* workspace, const float* A, int M, int K, void* stream);
 int    nt_b200_gemm_f16_tc_ws(float* C, const void* workspace, const void* W_f16, int M, int N, int K,
                               int add, void* stream);
+/* FFN front half for prefill: workspace_out = split(silu(A.Wgate^T) * (A.Wup^T)) with A pre-split in workspace_in
+ * (reference: ffn.cpp:96-133, three launches per token); N = rows of Wgate/Wup (% 128), feeds nt_b200_gemm_f16_tc_ws */
+int    nt_b200_gemm_f16_tc_swiglu_ws(void* workspace_out, const void* workspace_in, const void* Wgate_f16,
+                                     const void* Wup_f16, int M, int N, int K, void* stream);
+/* RMSNorm (launch_rmsnorm math) written straight into the split workspace */
+void   nt_b200_rmsnorm_split(void* workspace, const float* x, const float* w, int rows, int hidden, float eps,
+                             void* stream);
 unsigned long long nt_b200_launch_count(void);   /* kernels launched by this library so far */
 int    nt_b200_stream_sync(void* stream);        /* cudaStreamSynchronize; returns cudaError_t */
 const char* nt_b200_version(void);

@@ -17,7 +17,7 @@ __global__ void iota_kernel(int* out, int first, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = first + i;
 }
-constexpr int PREFILL_CHUNK = 2048;      // tokens per batched pass (bounds the activation buffers; weights re-read per chunk)
+constexpr int PREFILL_CHUNK = 4096;      // tokens per batched pass (bounds the activation buffers; weights re-read per chunk)
 
 // argmax over n floats, lowest index wins ties (reference Sampler::argmax, sampler.cpp:18-28)
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ x, int n, int* __restrict__ out) {
@@ -64,8 +64,7 @@ Model::~Model() {
                     (void*)logits_, (void*)logits_l_, (void*)attn_scratch_, xq_h_, xq_a_, xq_i_, kc_, vc_, (void*)step_dev_,
                     (void*)argmax_dev_})
         if (p) cudaFree(p);
-    for (void* p : {(void*)pf_.x, (void*)pf_.xn, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, (void*)pf_.g, (void*)pf_.u,
-                    pf_.ws, (void*)pf_.tok, (void*)pf_.pos})
+    for (void* p : {(void*)pf_.x, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, pf_.ws, pf_.ws2, (void*)pf_.tok, (void*)pf_.pos})
         if (p) cudaFree(p);
     if (argmax_host_) cudaFreeHost(argmax_host_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -394,16 +393,15 @@ bool Model::batched_prefill_ok(int seq_len, int start_pos) const {
 void Model::ensure_prefill_buffers(int tokens) {
     if (tokens <= pf_.cap) return;
     NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
-    for (void* p : {(void*)pf_.x, (void*)pf_.xn, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, (void*)pf_.g, (void*)pf_.u,
-                    pf_.ws, (void*)pf_.tok, (void*)pf_.pos})
+    for (void* p : {(void*)pf_.x, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, pf_.ws, pf_.ws2, (void*)pf_.tok, (void*)pf_.pos})
         if (p) cudaFree(p);
     const size_t T = (size_t)((tokens + 127) / 128 * 128);
     const size_t hidden = (size_t)cfg_.hidden_size, qdim = (size_t)nh_l_ * cfg_.head_dim, kvdim = (size_t)nkv_l_ * cfg_.head_dim;
-    const size_t inter = (size_t)inter_l_, kmax = std::max(std::max(hidden, qdim), inter);
-    pf_.x = dmalloc<float>(T * hidden);  pf_.xn = dmalloc<float>(T * hidden);
+    pf_.x = dmalloc<float>(T * hidden);
     pf_.q = dmalloc<float>(T * qdim);    pf_.k = dmalloc<float>(T * kvdim);   pf_.v = dmalloc<float>(T * kvdim);
-    pf_.attn = dmalloc<float>(T * qdim); pf_.g = dmalloc<float>(T * inter);   pf_.u = dmalloc<float>(T * inter);
-    pf_.ws = dmalloc<uint8_t>(gemm_f16_tc_workspace_bytes((int)T, (int)kmax));
+    pf_.attn = dmalloc<float>(T * qdim);
+    pf_.ws = dmalloc<uint8_t>(gemm_f16_tc_workspace_bytes((int)T, (int)std::max(hidden, qdim)));
+    pf_.ws2 = dmalloc<uint8_t>(gemm_f16_tc_workspace_bytes((int)T, inter_l_));
     pf_.tok = dmalloc<int>(T);           pf_.pos = dmalloc<int>(T);
     pf_.cap = (int)T;
 }
@@ -428,8 +426,7 @@ void Model::prefill_batched(const int* tokens, int seq_len, int start_pos) {
             uint16_t* kc = static_cast<uint16_t*>(kc_) + (size_t)i * kv_stride;
             uint16_t* vc = static_cast<uint16_t*>(vc_) + (size_t)i * kv_stride;
             // --- attention sub-block (attention.cpp:120-211 for all T tokens at once) ---
-            rmsnorm(pf_.xn, pf_.x, L.attn_norm, T, hidden, cfg_.norm_eps, s);
-            split_activations(pf_.ws, pf_.xn, T, hidden, s);
+            rmsnorm_split(pf_.ws, pf_.x, L.attn_norm, T, hidden, cfg_.norm_eps, s);
             NT_CHECK(gemm_f16_tc_ws(pf_.q, pf_.ws, L.wq.ptr, T, qdim, hidden, false, s), "prefill GEMM (q) rejected");
             NT_CHECK(gemm_f16_tc_ws(pf_.k, pf_.ws, L.wk.ptr, T, kvdim, hidden, false, s), "prefill GEMM (k) rejected");
             NT_CHECK(gemm_f16_tc_ws(pf_.v, pf_.ws, L.wv.ptr, T, kvdim, hidden, false, s), "prefill GEMM (v) rejected");
@@ -439,13 +436,9 @@ void Model::prefill_batched(const int* tokens, int seq_len, int start_pos) {
             split_activations(pf_.ws, pf_.attn, T, qdim, s);
             NT_CHECK(gemm_f16_tc_ws(pf_.x, pf_.ws, L.wo.ptr, T, hidden, qdim, true, s), "prefill GEMM (o) rejected");
             // --- FFN sub-block (ffn.cpp:85-134) ---
-            rmsnorm(pf_.xn, pf_.x, L.ffn_norm, T, hidden, cfg_.norm_eps, s);
-            split_activations(pf_.ws, pf_.xn, T, hidden, s);
-            NT_CHECK(gemm_f16_tc_ws(pf_.g, pf_.ws, L.gate.ptr, T, inter, hidden, false, s), "prefill GEMM (gate) rejected");
-            NT_CHECK(gemm_f16_tc_ws(pf_.u, pf_.ws, L.up.ptr, T, inter, hidden, false, s), "prefill GEMM (up) rejected");
-            silu_mul(pf_.g, pf_.g, pf_.u, T * inter, s);
-            split_activations(pf_.ws, pf_.g, T, inter, s);
-            NT_CHECK(gemm_f16_tc_ws(pf_.x, pf_.ws, L.down.ptr, T, hidden, inter, true, s), "prefill GEMM (down) rejected");
+            rmsnorm_split(pf_.ws, pf_.x, L.ffn_norm, T, hidden, cfg_.norm_eps, s);
+            NT_CHECK(gemm_f16_tc_swiglu_ws(pf_.ws2, pf_.ws, L.gate.ptr, L.up.ptr, T, inter, hidden, s), "prefill GEMM (gate/up) rejected");
+            NT_CHECK(gemm_f16_tc_ws(pf_.x, pf_.ws2, L.down.ptr, T, hidden, inter, true, s), "prefill GEMM (down) rejected");
         }
     }
     copy(hidden_, pf_.x + (size_t)(last_rows - 1) * hidden, hidden, s);       // last token's residual stream -> LM head

@@ -112,8 +112,8 @@ private:
 
     struct PrefillBuffers {
         int cap = 0;                     // tokens per chunk the buffers hold
-        float *x = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *attn = nullptr, *g = nullptr, *u = nullptr;
-        void* ws = nullptr;              // F16 hi/lo split of the current GEMM input
+        float *x = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *attn = nullptr;
+        void *ws = nullptr, *ws2 = nullptr;   // F16 hi/lo split of the current GEMM input (ws2: SwiGLU output -> down projection)
         int *tok = nullptr, *pos = nullptr;
     } pf_;
     int prefill_min_tokens_ = 16;

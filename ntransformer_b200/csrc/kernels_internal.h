@@ -112,6 +112,10 @@ bool gemm_f16_tc(float* C, const float* A, const void* W_f16, int M, int N, int 
 bool gemm_f16_tc_supported(const void* W_f16, int N, int K, size_t row_pitch);
 void split_activations(void* workspace, const float* A, int M, int K, cudaStream_t s);
 bool gemm_f16_tc_ws(float* C, const void* workspace, const void* W_f16, int M, int N, int K, bool add, cudaStream_t s);
+// workspace_out <- split(silu(A.Wgate^T) * (A.Wup^T)): the FFN's gate/up GEMMs with the SwiGLU + split fused in the epilogue
+bool gemm_f16_tc_swiglu_ws(void* workspace_out, const void* workspace_in, const void* Wgate_f16, const void* Wup_f16, int M, int N, int K,
+                           cudaStream_t s);
+void rmsnorm_split(void* workspace, const float* x, const float* w, int rows, int hidden, float eps, cudaStream_t s);
 
 // Number of kernels launched by this library since load (bench.py's gpu_launches claim).
 unsigned long long launch_count();

@@ -138,6 +138,12 @@ void nt_b200_split_activations(void* ws, const float* A, int M, int K, void* s) 
 int nt_b200_gemm_f16_tc_ws(float* Cm, const void* ws, const void* W, int M, int N, int K, int add, void* s) {
     return nt::b200::gemm_f16_tc_ws(Cm, ws, W, M, N, K, add != 0, static_cast<cudaStream_t>(s)) ? 0 : -1;
 }
+int nt_b200_gemm_f16_tc_swiglu_ws(void* wo, const void* wi, const void* Wg, const void* Wu, int M, int N, int K, void* s) {
+    return nt::b200::gemm_f16_tc_swiglu_ws(wo, wi, Wg, Wu, M, N, K, static_cast<cudaStream_t>(s)) ? 0 : -1;
+}
+void nt_b200_rmsnorm_split(void* ws, const float* x, const float* w, int rows, int hidden, float eps, void* s) {
+    nt::b200::rmsnorm_split(ws, x, w, rows, hidden, eps, static_cast<cudaStream_t>(s));
+}
 unsigned long long nt_b200_launch_count(void) { return nt::b200::launch_count(); }
 int nt_b200_stream_sync(void* s) { return (int)cudaStreamSynchronize(static_cast<cudaStream_t>(s)); }
 const char* nt_b200_version(void) { return "ntransformer_b200 0.1 (sm_100a)"; }

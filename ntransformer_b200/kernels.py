@@ -152,5 +152,16 @@ def gemm_f16_tc_ws(Cm, workspace, W_f16, M, N, K, add=False, stream=None):
         raise ValueError(f"nt_b200_gemm_f16_tc_ws rejected the shape M={M} N={N} K={K}")
 
 
+def gemm_f16_tc_swiglu_ws(workspace_out, workspace_in, Wgate_f16, Wup_f16, M, N, K, stream=None):
+    """workspace_out = split(silu(A.Wgate^T) * (A.Wup^T)) for A pre-split in workspace_in (SwiGLU fused in the epilogue)."""
+    rc = lib().nt_b200_gemm_f16_tc_swiglu_ws(_p(workspace_out), _p(workspace_in), _p(Wgate_f16), _p(Wup_f16), M, N, K, _s(stream))
+    if rc != 0:
+        raise ValueError(f"nt_b200_gemm_f16_tc_swiglu_ws rejected the shape M={M} N={N} K={K}")
+
+
+def rmsnorm_split(workspace, x, w, rows, hidden, eps, stream=None):
+    lib().nt_b200_rmsnorm_split(_p(workspace), _p(x), _p(w), rows, hidden, eps, _s(stream))
+
+
 def launch_count() -> int:
     return int(lib().nt_b200_launch_count())

@@ -35,3 +35,58 @@ def test_gemm_f16_tc_rejects_unaligned_shapes():
     ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
     with pytest.raises(ValueError):
         K.gemm_f16_tc(Cm, A, W, 4, 100, 96, ws)
+
+
+def _unsplit(ws, M, N):
+    """hi + lo (as F64) of a split workspace holding an [M, N] matrix (rows padded to 128)."""
+    Mp = (M + 127) // 128 * 128
+    h = ws.view(torch.float16)[: 2 * Mp * N].view(2, Mp, N)
+    return h[0, :M].double() + h[1, :M].double()
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (200, 1024, 512), (1000, 14336, 4096), (4096, 3584, 1024)])
+def test_gemm_add_epilogue_and_many_tiles_per_cta(shape):
+    """Residual epilogue (C += A.W^T); the larger shapes give each persistent CTA several tiles (both TMEM accumulators)."""
+    M, N, Kd = shape
+    g = torch.Generator(device="cuda").manual_seed(N + Kd)
+    A = torch.randn(M, Kd, device="cuda", generator=g)
+    W = (torch.randn(N, Kd, device="cuda", generator=g) * 0.05).half()
+    C0 = torch.randn(M, N, device="cuda", generator=g)
+    Cm = C0.clone()
+    ws = torch.empty(K.gemm_f16_tc_workspace_bytes(M, Kd), dtype=torch.uint8, device="cuda")
+    K.split_activations(ws, A, M, Kd)
+    K.gemm_f16_tc_ws(Cm, ws, W, M, N, Kd, add=True)
+    torch.cuda.synchronize()
+    ref = C0.double() + A.double() @ W.double().T
+    assert (Cm.double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (77, 1024, 512), (600, 14336, 4096)])
+def test_gemm_swiglu_epilogue_vs_torch_f64(shape):
+    M, N, Kd = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, Kd, device="cuda", generator=g)
+    Wg = (torch.randn(N, Kd, device="cuda", generator=g) * 0.03).half()
+    Wu = (torch.randn(N, Kd, device="cuda", generator=g) * 0.03).half()
+    ws_in = torch.empty(K.gemm_f16_tc_workspace_bytes(M, Kd), dtype=torch.uint8, device="cuda")
+    ws_out = torch.empty(K.gemm_f16_tc_workspace_bytes(M, N), dtype=torch.uint8, device="cuda")
+    K.split_activations(ws_in, A, M, Kd)
+    K.gemm_f16_tc_swiglu_ws(ws_out, ws_in, Wg, Wu, M, N, Kd)
+    torch.cuda.synchronize()
+    gate, up = A.double() @ Wg.double().T, A.double() @ Wu.double().T
+    ref = gate / (1.0 + torch.exp(-gate)) * up
+    got = _unsplit(ws_out, M, N)
+    assert (got - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+def test_rmsnorm_split_vs_torch():
+    rows, hidden = 300, 4096
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(rows, hidden, device="cuda", generator=g) * 3
+    w = 1 + 0.1 * torch.randn(hidden, device="cuda", generator=g)
+    ws = torch.empty(K.gemm_f16_tc_workspace_bytes(rows, hidden), dtype=torch.uint8, device="cuda")
+    K.rmsnorm_split(ws, x, w, rows, hidden, 1e-5)
+    torch.cuda.synchronize()
+    xd = x.double()
+    ref = xd * torch.rsqrt((xd * xd).mean(dim=1, keepdim=True) + 1e-5) * w.double()
+    assert (_unsplit(ws, rows, hidden) - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
