@@ -8,6 +8,7 @@
 #include "kernels_internal.h"
 #include "ring.cuh"
 #include <cuda_fp16.h>
+#include <algorithm>
 
 namespace nt { namespace b200 {
 
@@ -189,6 +190,66 @@ __global__ void __launch_bounds__(GW * 32) gemv_generic_kernel(float* __restrict
     }
 }
 
+// ---- F16 weights, 16-byte aligned rows (reference K6, gemm.cu:546-610): x staged once per CTA in shared memory, a warp
+// streams two rows at a time with four 16-byte loads per row in flight per lane (ld.global.nc, no L1 allocation). ----
+constexpr int F16_WARPS = 8;
+__device__ __forceinline__ uint4 ldg_stream16(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float dot8(const uint4& w, const float4& xa, const float4& xb, float acc) {
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w.z));
+    const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
+    acc = fmaf(f0.x, xa.x, acc); acc = fmaf(f0.y, xa.y, acc); acc = fmaf(f1.x, xa.z, acc); acc = fmaf(f1.y, xa.w, acc);
+    acc = fmaf(f2.x, xb.x, acc); acc = fmaf(f2.y, xb.y, acc); acc = fmaf(f3.x, xb.z, acc); acc = fmaf(f3.y, xb.w, acc);
+    return acc;
+}
+__global__ void __launch_bounds__(F16_WARPS * 32) gemv_f16_kernel(float* __restrict__ y, const uint8_t* __restrict__ W,
+                                                                  const float* __restrict__ x, int out, int in, size_t pitch, int ep) {
+    extern __shared__ __align__(16) float xs[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int i = threadIdx.x * 4; i < in; i += F16_WARPS * 32 * 4) *reinterpret_cast<float4*>(xs + i) = *reinterpret_cast<const float4*>(x + i);
+    __syncthreads();
+    const int n8 = in / 8;
+    const float4* x4 = reinterpret_cast<const float4*>(xs);
+    for (int pair = blockIdx.x * F16_WARPS + warp; 2 * pair < out; pair += gridDim.x * F16_WARPS) {
+        const int r0 = 2 * pair, r1 = min(r0 + 1, out - 1);
+        const uint4* w0 = reinterpret_cast<const uint4*>(W + (size_t)r0 * pitch);
+        const uint4* w1 = reinterpret_cast<const uint4*>(W + (size_t)r1 * pitch);
+        float a0 = 0.f, a1 = 0.f;
+        int v = lane;
+        for (; v + 96 < n8; v += 128) {
+            uint4 p[4], q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { p[u] = ldg_stream16(w0 + v + 32 * u); q[u] = ldg_stream16(w1 + v + 32 * u); }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float4 xa = x4[2 * (v + 32 * u)], xb = x4[2 * (v + 32 * u) + 1];
+                a0 = dot8(p[u], xa, xb, a0);
+                a1 = dot8(q[u], xa, xb, a1);
+            }
+        }
+        for (; v < n8; v += 32) {
+            const uint4 p = ldg_stream16(w0 + v), q = ldg_stream16(w1 + v);
+            const float4 xa = x4[2 * v], xb = x4[2 * v + 1];
+            a0 = dot8(p, xa, xb, a0);
+            a1 = dot8(q, xa, xb, a1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xFFFFFFFFu, a0, o); a1 += __shfl_xor_sync(0xFFFFFFFFu, a1, o); }
+        if (lane == 0) {
+            if (ep == GEMV_ADD) { y[r0] += a0; if (r0 + 1 < out) y[r0 + 1] += a1; }
+            else { y[r0] = a0; if (r0 + 1 < out) y[r0 + 1] = a1; }
+        }
+    }
+}
+constexpr int F16_MAX_SMEM = 200 * 1024;
+
 }  // namespace
 
 void gemv_generic(float* y, const void* W, const float* x, int out, int in, DType dt, size_t row_pitch,
@@ -196,6 +257,21 @@ void gemv_generic(float* y, const void* W, const float* x, int out, int in, DTyp
     if (out <= 0) return;
     size_t pitch = row_pitch ? row_pitch : dtype_row_size(dt, (size_t)in);
     const uint8_t* w = static_cast<const uint8_t*>(W);
+    if (dt == DType::F16 && in % 8 == 0 && pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (size_t)in * 4 <= (size_t)F16_MAX_SMEM && ep != GEMV_SWIGLU) {
+        static bool configured = false;
+        if (!configured) {
+            NT_CUDA_CHECK(cudaFuncSetAttribute(gemv_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_MAX_SMEM));
+            configured = true;
+        }
+        const int pairs = (out + 1) / 2;
+        int grid16 = (pairs + F16_WARPS - 1) / F16_WARPS;
+        const int resident = (int)std::min<size_t>(8, (size_t)(220 * 1024) / ((size_t)in * 4 + 1024)) * 148;   // CTAs the chip holds
+        if (grid16 > resident && resident > 0) grid16 = resident;
+        launch_k(gemv_f16_kernel, dim3(grid16), dim3(F16_WARPS * 32), (size_t)in * 4, s, y, w, x, out, in, pitch, (int)ep);
+        count_launch();
+        return;
+    }
     int grid = (out + GW * RPW - 1) / (GW * RPW);
 #define NT_LAUNCH(DTV) launch_k(gemv_generic_kernel<(int)DTV>, dim3(grid), dim3(GW * 32), 0, s, y, w, x, out, in, pitch, (int)ep)
     switch (dt) {

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
                                                              const __grid_constant__ CUtensorMap map_b,
                                                              const __grid_constant__ CUtensorMap map_b2,
                                                              float* __restrict__ C, __half* __restrict__ split_out,
-                                                             int M, int Mp, int N, int K, int tiles_n, int n_tiles) {
+                                                             int M, int Mp, int N, int K, int tiles_m, int tiles_n, int n_tiles, int n_outer) {
     constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TMEM_COLS = 2 * BN;
     constexpr int TN = MODE == MODE_SWIGLU ? 128 : BN;          // output columns per tile
     constexpr uint32_t IDESC = MODE == MODE_SWIGLU ? Cfg<128>::IDESC : Cfg<BN>::IDESC;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
         if (lane == 0) {                               // ---- TMA producer ----
             uint32_t it = 0;                           // k-block counter across all of this CTA's tiles
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * TN;
+                const int m0 = (n_outer ? tile % tiles_m : tile / tiles_n) * BM, n0 = (n_outer ? tile / tiles_m : tile % tiles_n) * TN;
                 for (int kb = 0; kb < num_kb; kb++, it++) {
                     const uint32_t s = it % STAGES;
                     wait_or_trap(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, lt++) {
             const uint32_t acc = lt & 1, acc_phase = (lt >> 1) & 1;
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * TN;
+            const int m0 = (n_outer ? tile % tiles_m : tile / tiles_n) * BM, n0 = (n_outer ? tile / tiles_m : tile % tiles_n) * TN;
             const int row = m0 + quarter * 32 + lane;
             wait_or_trap(&tmem_full_bar[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -354,9 +354,17 @@ bool launch_gemm(float* C, __half* split_out, const void* workspace, const void*
         NT_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
         configured = true;
     }
-    const int tiles_n = N / TN, n_tiles = tiles_n * (int)(Mp / BM);
+    const int tiles_m = (int)(Mp / BM), tiles_n = N / TN, n_tiles = tiles_n * tiles_m;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    gemm_f16_tc_kernel<BN, MODE><<<grid, 192, Cfg<BN>::SMEM, s>>>(map_a, map_b, map_b2, C, split_out, M, (int)Mp, N, K, tiles_n, n_tiles);
+    // Tile order: concurrently running CTAs share the operand that is walked in the inner loop, the other one should stay
+    // L2-resident (126 MB) across the whole launch.  Keep the smaller operand resident: n-outer when the split activations
+    // (2 * Mp * K halfs) are smaller than the weights, m-outer otherwise (ncu: 1.5 GB of DRAM reads for 184 MB of operands
+    // with the wrong order, profiles/r01_gemm_tc_ncu_summary.txt).
+    const size_t a_bytes = 4 * Mp * (size_t)K, w_bytes = (MODE == MODE_SWIGLU ? 4 : 2) * (size_t)N * K;
+    static const bool force_m_outer = getenv("NT_B200_GEMM_M_OUTER") != nullptr;
+    const int n_outer = (a_bytes < w_bytes && !force_m_outer) ? 1 : 0;
+    gemm_f16_tc_kernel<BN, MODE><<<grid, 192, Cfg<BN>::SMEM, s>>>(map_a, map_b, map_b2, C, split_out, M, (int)Mp, N, K, tiles_m, tiles_n,
+                                                                 n_tiles, n_outer);
     count_launch();
     return true;
 }
