@@ -40,6 +40,9 @@ def test_sass_is_sm100a_with_tma_and_dp4a():
     assert "UBLKCP" in sass, "TMA bulk copies missing from the GEMV"
     assert "IDP.4A" in sass
     assert "SYNCS.ARRIVE.TRANS64" in sass
+    # prefill: tcgen05 MMA fed by tensor-map TMA with TMEM loads in the epilogue; tiled attention on the warp-level MMA
+    for mnemonic in ("UTCHMMA", "UTMALDG.2D", "LDTM", "UTCBAR", "HMMA.16816.F32", "LDSM.16.MT88.4"):
+        assert mnemonic in sass, f"{mnemonic} missing"
 
 
 def test_product_never_touches_the_oracle():
