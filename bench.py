@@ -101,10 +101,10 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def ncu_traffic(workload: str, world: int):
+def ncu_traffic(workload: str, world: int, name: str = "r01_gemv_gateup_ncu.json"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-    capture of the same shape (profiles/r01_gemv_gateup_ncu.json); None when no capture exists for this workload."""
-    p = ROOT / "profiles" / "r01_gemv_gateup_ncu.json"
+    capture of the same shape (profiles/<name>); None when no capture exists for this workload."""
+    p = ROOT / "profiles" / name
     if world != 1 or not p.exists():
         return None
     try:
@@ -218,7 +218,7 @@ def run_prefill(args, rank, world):
     step_flops = 2.0 * prompt_len * n_mat + 4.0 * cfg.n_layers * cfg.n_heads * cfg.head_dim * prompt_len * (prompt_len + 1) / 2
     step_tf = step_flops / (ms / steps / 1e3) / 1e12
     roof = {"bound": "tensor", "kernel": "gemm_f16_tc_kernel<256, SWIGLU> (ffn gate+up, M=%d N=2x%d K=%d)" % (T, N, Kd), "achieved": round(ach, 1),
-            "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
+            "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": ncu_traffic(args.workload, 1, "r01_gemm_tc_ncu.json"),
             "flops_per_launch": flops, "avg_launch_us": round(dur_ms * 1e3, 1), "launches_timed": len(evs), "peak_source": peak_src,
             "note": "algorithmic flops 2MNK; the kernel issues 2x that (F32 activations split into F16 hi+lo to keep parity <= 1e-3)",
             "step_achieved": round(step_tf, 1), "step_frac": round(step_tf / peak, 4)}
