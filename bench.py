@@ -43,6 +43,9 @@ WORKLOADS = {
     # BASELINE.json configs[4]: the step is one whole 4096-token prompt (metric prefill_tok_s); see run_prefill
     "llama3-8b-f16-prefill-4096": ("8b", "F16", 4096, 4096),
     "tiny-f16-prefill-96": ("tiny", "F16", 96, 128),
+    # quantised weights on the tensor-core prefill path (dequantised to an F16 hi/lo pair per matrix, two GEMMs each)
+    "llama3-8b-q4_k_m-prefill-4096": ("8b", "Q4_K_M", 4096, 4096),
+    "llama3-70b-q4_k_m-prefill-4096": ("70b", "Q4_K_M", 4096, 4096),
 }
 DTYPE_NOTE = "k-quant codes x block-scaled int8x3 activations via dp4a (s32 exact) + f32 scales/accumulate; KV f16"
 
@@ -193,42 +196,54 @@ def run_prefill(args, rank, world):
     per_token_tok_s = n_cmp / (a.elapsed_time(b) / 1e3)
     model.set_prefill_min_tokens(16)
 
-    # ---- roofline of the dominant kernel (tcgen05 GEMM, ffn gate shape), measured live ----
+    # ---- roofline of the dominant kernel (tcgen05 GEMM, ffn gate+up shape), measured live (F16 weights) ----
     peak, peak_src = measured_peak_tensor()
-    T, N, Kd = prompt_len, cfg.intermediate_size, cfg.hidden_size
-    A = torch.randn(T, Kd, device="cuda")
-    Wg, Wu = model._keep["blk.0.ffn_gate.weight"][0], model._keep["blk.0.ffn_up.weight"][0]
-    ws = torch.empty(K.gemm_f16_tc_workspace_bytes(T, Kd), dtype=torch.uint8, device="cuda")
-    ws2 = torch.empty(K.gemm_f16_tc_workspace_bytes(T, N), dtype=torch.uint8, device="cuda")
-    K.split_activations(ws, A, T, Kd)
+    ach = flops = dur_ms = None
     evs = []
-    for r in range(6):
-        x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        x.record()
-        K.gemm_f16_tc_swiglu_ws(ws2, ws, Wg, Wu, T, N, Kd)
-        y.record()
-        if r > 0:
-            evs.append((x, y))
-    torch.cuda.synchronize()
-    dur_ms = float(np.mean([x.elapsed_time(y) for x, y in evs]))
-    flops = 2.0 * T * (2 * N) * Kd
-    ach = flops / (dur_ms / 1e3) / 1e12
-    n_mat = sum(model._keep[f"blk.0.{n}.weight"][0].numel() // 2 for n in          # uint8 view of F16 -> weights
-                ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down")) * cfg.n_layers
+    if mix == "F16":
+        T, N, Kd = prompt_len, cfg.intermediate_size, cfg.hidden_size
+        A = torch.randn(T, Kd, device="cuda")
+        Wg, Wu = model._keep["blk.0.ffn_gate.weight"][0], model._keep["blk.0.ffn_up.weight"][0]
+        ws = torch.empty(K.gemm_f16_tc_workspace_bytes(T, Kd), dtype=torch.uint8, device="cuda")
+        ws2 = torch.empty(K.gemm_f16_tc_workspace_bytes(T, N), dtype=torch.uint8, device="cuda")
+        K.split_activations(ws, A, T, Kd)
+        evs = []
+        for r in range(6):
+            x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x.record()
+            K.gemm_f16_tc_swiglu_ws(ws2, ws, Wg, Wu, T, N, Kd)
+            y.record()
+            if r > 0:
+                evs.append((x, y))
+        torch.cuda.synchronize()
+        dur_ms = float(np.mean([x.elapsed_time(y) for x, y in evs]))
+        flops = 2.0 * T * (2 * N) * Kd
+        ach = flops / (dur_ms / 1e3) / 1e12
+    n_mat = (cfg.n_heads * cfg.head_dim * cfg.hidden_size * 2 + cfg.n_kv_heads * cfg.head_dim * cfg.hidden_size * 2 +
+             3 * cfg.intermediate_size * cfg.hidden_size) * cfg.n_layers                   # projection weights (elements)
     step_flops = 2.0 * prompt_len * n_mat + 4.0 * cfg.n_layers * cfg.n_heads * cfg.head_dim * prompt_len * (prompt_len + 1) / 2
     step_tf = step_flops / (ms / steps / 1e3) / 1e12
-    roof = {"bound": "tensor", "kernel": "gemm_f16_tc_kernel<256, SWIGLU> (ffn gate+up, M=%d N=2x%d K=%d)" % (T, N, Kd), "achieved": round(ach, 1),
-            "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": ncu_traffic(args.workload, 1, "r01_gemm_tc_ncu.json"),
-            "flops_per_launch": flops, "avg_launch_us": round(dur_ms * 1e3, 1), "launches_timed": len(evs), "peak_source": peak_src,
-            "note": "algorithmic flops 2MNK; the kernel issues 2x that (F32 activations split into F16 hi+lo to keep parity <= 1e-3)",
-            "step_achieved": round(step_tf, 1), "step_frac": round(step_tf / peak, 4)}
+    if mix == "F16":
+        roof = {"bound": "tensor", "kernel": "gemm_f16_tc_kernel<256, SWIGLU> (ffn gate+up, M=%d N=2x%d K=%d)" % (T, N, Kd),
+                "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+                "traffic": ncu_traffic(args.workload, 1, "r01_gemm_tc_ncu.json"),
+                "flops_per_launch": flops, "avg_launch_us": round(dur_ms * 1e3, 1), "launches_timed": len(evs), "peak_source": peak_src,
+                "note": "algorithmic flops 2MNK; the kernel issues 2x that (F32 activations split into F16 hi+lo to keep parity <= 1e-3)",
+                "step_achieved": round(step_tf, 1), "step_frac": round(step_tf / peak, 4)}
+    else:
+        roof = {"bound": "tensor", "kernel": "whole prefill step (gemm_f16_tc_kernel over dequantised F16 hi/lo weights, 2 launches per matrix)",
+                "achieved": round(step_tf, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(step_tf / peak, 4), "traffic": None,
+                "peak_source": peak_src,
+                "note": "algorithmic flops; the path issues 4x that (activations and dequantised weights both as F16 hi+lo)",
+                "step_achieved": round(step_tf, 1), "step_frac": round(step_tf / peak, 4)}
     line = {
         "metric": "prefill_tok_s", "value": round(tok_s, 1), "unit": "tok/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup,
         "ms_per_step": round(ms / steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f16 weights x f32 activations as f16 hi+lo on tcgen05 (f32 accumulate in TMEM); KV f16; attention f32",
-        "data": "synthetic (seeded random F16 weights generated on the GPU)",
+        "dtype": ("f16 weights" if mix == "F16" else mix + " weights dequantised to f16 hi+lo") +
+                 " x f32 activations as f16 hi+lo on tcgen05 (f32 accumulate in TMEM); KV f16; attention f32",
+        "data": "synthetic (seeded random weights generated on the GPU)",
         "config": {"workload": args.workload, "quant_mix": mix, "batch": 1, "prompt_tokens": prompt_len, "max_seq": max_seq,
-                   "parallelism": "single", "l2_policy": "16 GB of weights per prompt exceed the 126 MB L2; no flush needed"},
+                   "parallelism": "single", "l2_policy": "the weights read per prompt (GBs) exceed the 126 MB L2; no flush needed"},
         "clocks": clocks,
         "e2e": {"value": round(steps * prompt_len / (e2e_ms / 1e3), 1), "unit": "tok/s", "h2d_bytes_per_step": 4 * prompt_len,
                 "d2h_bytes_per_step": vocab * 4, "ms_per_step": round(e2e_ms / steps, 3)},

@@ -103,6 +103,11 @@ int    nt_b200_gemm_f16_tc_swiglu_ws(void* workspace_out, const void* workspace_
 /* RMSNorm (launch_rmsnorm math) written straight into the split workspace */
 void   nt_b200_rmsnorm_split(void* workspace, const float* x, const float* w, int rows, int hidden, float eps,
                              void* stream);
+/* Any GGUF weight matrix (dtype = numeric nt::DType, row_pitch 0 = dense rows) -> dense F16 pair with W = w_hi + w_lo, the
+ * operands of two nt_b200_gemm_f16_tc_ws launches (second with add = 1): tensor-core prefill for quantised models.
+ * Reference dequant formulas: src/cuda/gemm.cu:32-470, src/model/transformer.cpp:394-599. */
+void   nt_b200_dequant_split(void* w_hi, void* w_lo, const void* W, int dtype, size_t row_pitch, int rows, int cols,
+                             void* stream);
 unsigned long long nt_b200_launch_count(void);   /* kernels launched by this library so far */
 int    nt_b200_stream_sync(void* stream);        /* cudaStreamSynchronize; returns cudaError_t */
 const char* nt_b200_version(void);

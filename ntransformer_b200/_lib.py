@@ -49,6 +49,7 @@ SIGNATURES = {
     "nt_b200_gemm_f16_tc_ws": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nt_b200_gemm_f16_tc_swiglu_ws": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "nt_b200_rmsnorm_split": (None, [_vp, _vp, _vp, _i, _i, C.c_float, _vp]),
+    "nt_b200_dequant_split": (None, [_vp, _vp, _vp, _i, _sz, _i, _i, _vp]),
     "nt_b200_launch_count": (C.c_ulonglong, []),
     "nt_b200_stream_sync": (_i, [_vp]),
     "nt_b200_version": (C.c_char_p, []),

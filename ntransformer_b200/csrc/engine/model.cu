@@ -64,7 +64,8 @@ Model::~Model() {
                     (void*)logits_, (void*)logits_l_, (void*)attn_scratch_, xq_h_, xq_a_, xq_i_, kc_, vc_, (void*)step_dev_,
                     (void*)argmax_dev_})
         if (p) cudaFree(p);
-    for (void* p : {(void*)pf_.x, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, pf_.ws, pf_.ws2, (void*)pf_.tok, (void*)pf_.pos})
+    for (void* p : {(void*)pf_.x, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, pf_.ws, pf_.ws2, (void*)pf_.tok, (void*)pf_.pos,
+                    (void*)pf_.g, (void*)pf_.u, pf_.whi, pf_.wlo})
         if (p) cudaFree(p);
     if (argmax_host_) cudaFreeHost(argmax_host_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -386,15 +387,32 @@ bool Model::batched_prefill_ok(int seq_len, int start_pos) const {
     if (!attention_prefill_mma_supported(seq_len, nh_l_, nkv_l_, cfg_.head_dim)) return false;
     for (const LayerWeights& L : layers_)
         for (const Weight* w : {&L.wq, &L.wk, &L.wv, &L.wo, &L.gate, &L.up, &L.down})
-            if (w->dtype != DType::F16 || !gemm_f16_tc_supported(w->ptr, w->rows, w->cols, w->pitch)) return false;
+            if (!dequant_split_supported(w->dtype) || w->rows % 128 != 0 || w->cols % 64 != 0) return false;
     return true;
+}
+
+bool Model::f16_direct(const Weight& w) const {
+    return w.dtype == DType::F16 && gemm_f16_tc_supported(w.ptr, w.rows, w.cols, w.pitch);
+}
+
+void Model::prefill_gemm(float* C, const void* ws, const Weight& w, int T, bool add, cudaStream_t s) {
+    if (f16_direct(w)) {
+        NT_CHECK(gemm_f16_tc_ws(C, ws, w.ptr, T, w.rows, w.cols, add, s), "prefill GEMM rejected");
+        return;
+    }
+    // quantised (or unaligned F16 / F32) weights: expand once per prompt chunk, then C (+)= A.W_hi^T ; C += A.W_lo^T
+    dequant_split(pf_.whi, pf_.wlo, w.ptr, w.dtype, w.pitch, w.rows, w.cols, s);
+    NT_CHECK(gemm_f16_tc_ws(C, ws, pf_.whi, T, w.rows, w.cols, add, s), "prefill GEMM (hi) rejected");
+    NT_CHECK(gemm_f16_tc_ws(C, ws, pf_.wlo, T, w.rows, w.cols, true, s), "prefill GEMM (lo) rejected");
 }
 
 void Model::ensure_prefill_buffers(int tokens) {
     if (tokens <= pf_.cap) return;
     NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
-    for (void* p : {(void*)pf_.x, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, pf_.ws, pf_.ws2, (void*)pf_.tok, (void*)pf_.pos})
+    for (void* p : {(void*)pf_.x, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, pf_.ws, pf_.ws2, (void*)pf_.tok, (void*)pf_.pos,
+                    (void*)pf_.g, (void*)pf_.u, pf_.whi, pf_.wlo})
         if (p) cudaFree(p);
+    pf_.g = pf_.u = nullptr; pf_.whi = pf_.wlo = nullptr;
     const size_t T = (size_t)((tokens + 127) / 128 * 128);
     const size_t hidden = (size_t)cfg_.hidden_size, qdim = (size_t)nh_l_ * cfg_.head_dim, kvdim = (size_t)nkv_l_ * cfg_.head_dim;
     pf_.x = dmalloc<float>(T * hidden);
@@ -403,6 +421,15 @@ void Model::ensure_prefill_buffers(int tokens) {
     pf_.ws = dmalloc<uint8_t>(gemm_f16_tc_workspace_bytes((int)T, (int)std::max(hidden, qdim)));
     pf_.ws2 = dmalloc<uint8_t>(gemm_f16_tc_workspace_bytes((int)T, inter_l_));
     pf_.tok = dmalloc<int>(T);           pf_.pos = dmalloc<int>(T);
+    size_t w_elems = 0;                  // largest matrix that needs the dequantised scratch pair
+    bool swiglu_unfused = false;
+    for (const LayerWeights& L : layers_) {
+        for (const Weight* w : {&L.wq, &L.wk, &L.wv, &L.wo, &L.gate, &L.up, &L.down})
+            if (!f16_direct(*w)) w_elems = std::max(w_elems, (size_t)w->rows * (size_t)w->cols);
+        swiglu_unfused = swiglu_unfused || !f16_direct(L.gate) || !f16_direct(L.up);
+    }
+    if (w_elems) { pf_.whi = dmalloc<uint16_t>(w_elems); pf_.wlo = dmalloc<uint16_t>(w_elems); }
+    if (swiglu_unfused) { pf_.g = dmalloc<float>(T * (size_t)inter_l_); pf_.u = dmalloc<float>(T * (size_t)inter_l_); }
     pf_.cap = (int)T;
 }
 
@@ -427,18 +454,25 @@ void Model::prefill_batched(const int* tokens, int seq_len, int start_pos) {
             uint16_t* vc = static_cast<uint16_t*>(vc_) + (size_t)i * kv_stride;
             // --- attention sub-block (attention.cpp:120-211 for all T tokens at once) ---
             rmsnorm_split(pf_.ws, pf_.x, L.attn_norm, T, hidden, cfg_.norm_eps, s);
-            NT_CHECK(gemm_f16_tc_ws(pf_.q, pf_.ws, L.wq.ptr, T, qdim, hidden, false, s), "prefill GEMM (q) rejected");
-            NT_CHECK(gemm_f16_tc_ws(pf_.k, pf_.ws, L.wk.ptr, T, kvdim, hidden, false, s), "prefill GEMM (k) rejected");
-            NT_CHECK(gemm_f16_tc_ws(pf_.v, pf_.ws, L.wv.ptr, T, kvdim, hidden, false, s), "prefill GEMM (v) rejected");
+            prefill_gemm(pf_.q, pf_.ws, L.wq, T, false, s);
+            prefill_gemm(pf_.k, pf_.ws, L.wk, T, false, s);
+            prefill_gemm(pf_.v, pf_.ws, L.wv, T, false, s);
             rope(pf_.q, pf_.k, pf_.pos, T, nh_l_, nkv_l_, hd, cfg_.rope_theta, cfg_.rope_freq_scale, false, s);
             copy_to_kv_cache(kc, vc, pf_.k, pf_.v, T, nkv_l_, hd, p0, max_seq, s);
             attention_prefill(pf_.attn, pf_.q, kc, vc, T, p0, nh_l_, nkv_l_, hd, max_seq, scale, s);
             split_activations(pf_.ws, pf_.attn, T, qdim, s);
-            NT_CHECK(gemm_f16_tc_ws(pf_.x, pf_.ws, L.wo.ptr, T, hidden, qdim, true, s), "prefill GEMM (o) rejected");
+            prefill_gemm(pf_.x, pf_.ws, L.wo, T, true, s);
             // --- FFN sub-block (ffn.cpp:85-134) ---
             rmsnorm_split(pf_.ws, pf_.x, L.ffn_norm, T, hidden, cfg_.norm_eps, s);
-            NT_CHECK(gemm_f16_tc_swiglu_ws(pf_.ws2, pf_.ws, L.gate.ptr, L.up.ptr, T, inter, hidden, s), "prefill GEMM (gate/up) rejected");
-            NT_CHECK(gemm_f16_tc_ws(pf_.x, pf_.ws2, L.down.ptr, T, hidden, inter, true, s), "prefill GEMM (down) rejected");
+            if (f16_direct(L.gate) && f16_direct(L.up)) {
+                NT_CHECK(gemm_f16_tc_swiglu_ws(pf_.ws2, pf_.ws, L.gate.ptr, L.up.ptr, T, inter, hidden, s), "prefill GEMM (gate/up) rejected");
+            } else {                                   // quantised gate/up: plain GEMMs, then SwiGLU and split as separate passes
+                prefill_gemm(pf_.g, pf_.ws, L.gate, T, false, s);
+                prefill_gemm(pf_.u, pf_.ws, L.up, T, false, s);
+                silu_mul(pf_.g, pf_.g, pf_.u, T * inter, s);
+                split_activations(pf_.ws2, pf_.g, T, inter, s);
+            }
+            prefill_gemm(pf_.x, pf_.ws2, L.down, T, true, s);
         }
     }
     copy(hidden_, pf_.x + (size_t)(last_rows - 1) * hidden, hidden, s);       // last token's residual stream -> LM head

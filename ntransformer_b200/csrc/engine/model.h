@@ -84,6 +84,9 @@ private:
     // instead of the reference's per-token loop (transformer.cpp:604-669 runs every layer's GEMVs once per token).
     void prefill_batched(const int* tokens, int seq_len, int start_pos);
     void ensure_prefill_buffers(int tokens);
+    bool f16_direct(const Weight& w) const;   // F16 rows usable by TMA in place
+    // C[T, w.rows] (+)= split(A)[T, w.cols] . W^T for a weight of any GGUF dtype (quantised: dequantise to hi/lo, two GEMMs)
+    void prefill_gemm(float* C, const void* ws, const Weight& w, int T, bool add, cudaStream_t s);
     bool o_xq_fusable(const Weight& wo) const;
     const void* upload(const GGUFFile& f, const std::string& name, Weight* w, int split /*0 none,1 rows,2 cols*/);
     void release_graphs();
@@ -114,6 +117,8 @@ private:
         int cap = 0;                     // tokens per chunk the buffers hold
         float *x = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *attn = nullptr;
         void *ws = nullptr, *ws2 = nullptr;   // F16 hi/lo split of the current GEMM input (ws2: SwiGLU output -> down projection)
+        float *g = nullptr, *u = nullptr;     // gate / up activations (only when those weights are not F16: unfused SwiGLU)
+        void *whi = nullptr, *wlo = nullptr;  // dequantised weight matrix as an F16 hi/lo pair (quantised models)
         int *tok = nullptr, *pos = nullptr;
     } pf_;
     int prefill_min_tokens_ = 16;

@@ -116,6 +116,9 @@ bool gemm_f16_tc_ws(float* C, const void* workspace, const void* W_f16, int M, i
 bool gemm_f16_tc_swiglu_ws(void* workspace_out, const void* workspace_in, const void* Wgate_f16, const void* Wup_f16, int M, int N, int K,
                            cudaStream_t s);
 void rmsnorm_split(void* workspace, const float* x, const float* w, int rows, int hidden, float eps, cudaStream_t s);
+// prefill_dequant.cu: any GGUF weight matrix -> dense F16 pair with W = w_hi + w_lo (operands of two tensor-core GEMMs)
+bool dequant_split_supported(DType dt);
+void dequant_split(void* w_hi, void* w_lo, const void* W, DType dt, size_t row_pitch, int rows, int cols, cudaStream_t s);
 
 // Number of kernels launched by this library since load (bench.py's gpu_launches claim).
 unsigned long long launch_count();

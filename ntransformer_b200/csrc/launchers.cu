@@ -144,6 +144,9 @@ int nt_b200_gemm_f16_tc_swiglu_ws(void* wo, const void* wi, const void* Wg, cons
 void nt_b200_rmsnorm_split(void* ws, const float* x, const float* w, int rows, int hidden, float eps, void* s) {
     nt::b200::rmsnorm_split(ws, x, w, rows, hidden, eps, static_cast<cudaStream_t>(s));
 }
+void nt_b200_dequant_split(void* hi, void* lo, const void* W, int dt, size_t pitch, int rows, int cols, void* s) {
+    nt::b200::dequant_split(hi, lo, W, (DType)dt, pitch, rows, cols, static_cast<cudaStream_t>(s));
+}
 unsigned long long nt_b200_launch_count(void) { return nt::b200::launch_count(); }
 int nt_b200_stream_sync(void* s) { return (int)cudaStreamSynchronize(static_cast<cudaStream_t>(s)); }
 const char* nt_b200_version(void) { return "ntransformer_b200 0.1 (sm_100a)"; }

@@ -163,5 +163,10 @@ def rmsnorm_split(workspace, x, w, rows, hidden, eps, stream=None):
     lib().nt_b200_rmsnorm_split(_p(workspace), _p(x), _p(w), rows, hidden, eps, _s(stream))
 
 
+def dequant_split(w_hi, w_lo, W, dtype, rows, cols, row_pitch=0, stream=None):
+    """GGUF blocks -> dense F16 pair with W = w_hi + w_lo (operands of the tensor-core prefill GEMM for quantised models)."""
+    lib().nt_b200_dequant_split(_p(w_hi), _p(w_lo), _p(W), int(dtype), row_pitch, rows, cols, _s(stream))
+
+
 def launch_count() -> int:
     return int(lib().nt_b200_launch_count())

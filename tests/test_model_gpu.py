@@ -71,14 +71,16 @@ def test_graph_replay_equals_eager_launches(gguf_case):
     a.close(), b.close()
 
 
-@pytest.mark.parametrize("n_prompt,start", [(16, 0), (97, 0), (128, 0), (40, 23), (200, 0)])
-def test_batched_tensor_core_prefill_vs_oracle_and_per_token(tmp_path, n_prompt, start):
-    """F16 model: the tcgen05 batched prefill (csrc/prefill_gemm.cu) against the oracle's forward and against the
-    per-token replay path; the KV cache it leaves must continue into identical greedy decode."""
+@pytest.mark.parametrize("mix,n_prompt,start", [("F16", 16, 0), ("F16", 97, 0), ("F16", 128, 0), ("F16", 40, 23), ("F16", 200, 0),
+                                                ("Q4_K_M", 48, 0), ("Q4_K_M", 130, 17), ("Q8_0", 64, 0), ("Q6_K", 33, 5)])
+def test_batched_tensor_core_prefill_vs_oracle_and_per_token(tmp_path, mix, n_prompt, start):
+    """The tcgen05 batched prefill (csrc/prefill_gemm.cu; quantised mixes go through csrc/prefill_dequant.cu's hi/lo
+    expansion) against the oracle's forward and against the per-token replay path; the KV cache it leaves must
+    continue into identical greedy decode."""
     from dataclasses import replace
-    cfg = replace(TINY, max_seq_len=256)
-    tensors = synthetic_tensors_np(cfg, "F16", seed=5)
-    path = tmp_path / "f16.gguf"
+    cfg = replace(TINY if mix != "Q6_K" else MID, max_seq_len=256)
+    tensors = synthetic_tensors_np(cfg, mix, seed=5)
+    path = tmp_path / "m.gguf"
     write_gguf(path, cfg, tensors)
     host = {n: (np.ascontiguousarray(a), int(dt)) for n, (a, dt, r, c) in tensors.items()}
     rng = np.random.default_rng(n_prompt)
@@ -94,7 +96,7 @@ def test_batched_tensor_core_prefill_vs_oracle_and_per_token(tmp_path, n_prompt,
     la = a.forward(prompt, start).copy()
     batched_launches = K.launch_count() - n0
     lb, lo = b.forward(prompt, start).copy(), om.forward(prompt, start)
-    assert batched_launches < 25 * cfg.n_layers          # one pass over the layers, not n_prompt of them
+    assert batched_launches < 40 * cfg.n_layers          # one pass over the layers, not n_prompt of them
     assert rel(la, lo) <= 1e-3 and rel(la, lb) <= 1e-3
     pos, ta, tb = start + n_prompt, int(np.argmax(la)), int(np.argmax(lo))
     for _ in range(12):

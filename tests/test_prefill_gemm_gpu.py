@@ -2,10 +2,14 @@
 
 The weights are F16 (exact in the reference too); activations are F32 split into two F16 terms, so the only error
 left is the F32 accumulation order: tolerance 1e-4 * max|C| against an F64 matmul (measured 4e-5 at K=14336) (north_star allows 1e-3)."""
+import numpy as np
 import pytest
 import torch
 
 from ntransformer_b200 import kernels as K
+from ntransformer_b200.dtypes import DType, dtype_row_size
+from ntransformer_b200.synth import random_blocks_np
+from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
@@ -90,3 +94,28 @@ def test_rmsnorm_split_vs_torch():
     xd = x.double()
     ref = xd * torch.rsqrt((xd * xd).mean(dim=1, keepdim=True) + 1e-5) * w.double()
     assert (_unsplit(ws, rows, hidden) - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dt", [DType.Q4_K_M, DType.Q5_K, DType.Q6_K, DType.Q8_0, DType.Q4_0, DType.F16, DType.F32])
+def test_dequant_split_vs_oracle_and_gemm_over_it(dt):
+    """GGUF blocks -> F16 hi/lo pair: hi + lo reproduces the oracle's dequantised row to F32 rounding, and the two-GEMM
+    product over the pair matches an F64 matmul with the oracle's weights (the quantised-model prefill path)."""
+    rows, cols, M = 256, 1024, 70
+    rng = np.random.default_rng(int(dt) + 40)
+    raw = random_blocks_np(dt, rows, cols, rng)
+    want = O.dequant_rows(int(dt), raw, rows, cols)
+    hi = torch.empty(rows, cols, dtype=torch.float16, device="cuda")
+    lo = torch.empty(rows, cols, dtype=torch.float16, device="cuda")
+    K.dequant_split(hi, lo, torch.from_numpy(raw).cuda(), dt, rows, cols)
+    torch.cuda.synchronize()
+    got = hi.double().cpu().numpy() + lo.double().cpu().numpy()
+    assert np.abs(got - want).max() <= 4e-7 * np.abs(want).max()
+    A = torch.randn(M, cols, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    Cm = torch.empty(M, rows, device="cuda")
+    ws = torch.empty(K.gemm_f16_tc_workspace_bytes(M, cols), dtype=torch.uint8, device="cuda")
+    K.split_activations(ws, A, M, cols)
+    K.gemm_f16_tc_ws(Cm, ws, hi, M, rows, cols)
+    K.gemm_f16_tc_ws(Cm, ws, lo, M, rows, cols, add=True)
+    torch.cuda.synchronize()
+    ref = A.double().cpu().numpy() @ want.astype(np.float64).T
+    assert np.abs(Cm.double().cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
