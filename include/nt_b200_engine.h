@@ -49,6 +49,27 @@ void nt_model_set_prefill_min_tokens(nt_model_t m, int n);
 /* algorithmic bytes read per decoded token by this rank at context length ctx */
 unsigned long long nt_model_bytes_per_token(nt_model_t m, int ctx);
 
+/* Opt-in: run each decoded token as ONE persistent kernel (all layers; grid barriers and, under tensor parallelism,
+ * NVLink peer-memory exchanges inside the kernel) instead of the CUDA graph of fused launches.  Same maths, same KV
+ * cache.  Models whose shapes/dtypes the kernel does not cover keep the graph path (a note goes to stderr).
+ * Also enabled by the environment variable NT_B200_MEGAKERNEL=1.  Call before the first forward. */
+void nt_model_use_megakernel(nt_model_t m, int on);
+int  nt_model_megakernel_active(nt_model_t m);      /* 1 once the persistent kernel has been built and is in use */
+/* phase kinds of the persistent kernel's per-token program (0 norm+quantise, 1 quantise, 2 GEMV, 3 attention,
+ * 4 combine); returns the number of phases (may exceed cap), 0 when the kernel is not active */
+int  nt_model_megakernel_plan(nt_model_t m, int* kinds, int cap);
+/* debug: copies one of the persistent kernel's working vectors ("hid0", "hid1", "q", "attn", "act", "slots") to the host;
+ * returns its length in floats, -1 when unknown / not active */
+long long nt_model_debug_read(nt_model_t m, const char* name, float* out_host, size_t cap);
+
+/* Host-only self-test of the persistent kernel's plan builder: builds the per-token program for one tensor-parallel rank
+ * of a model of shape *cfg (layer_dtypes: n_layers x 7 nt::DType values in the order q,k,v,o,gate,up,down) on a grid of
+ * `grid` CTAs and replays the schedule of every GEMV phase on the CPU.  info (8 ints, optional): phases, body phases, GEMV
+ * phases, min warps, min ring stages, exchanges, attention splits, keys per split.  Returns 0 ok, 1 shape not covered,
+ * 2 inconsistent plan (a bug), -1 bad arguments; msg receives the reason. */
+int  nt_mega_plan_selftest(const nt_model_config* cfg, int tp_rank, int tp_size, const int* layer_dtypes, int head_dtype,
+                           int grid, int split_fixed, int* info, char* msg, size_t cap);
+
 /* ---- host-only helpers (no GPU needed): GGUF header, tokenizer and sampler of the CLI path ---- */
 /* JSON description of a GGUF file as the engine parses it (config, vocab size, tensor table). Returns the
  * number of bytes written (excluding NUL) or -1. */

@@ -54,23 +54,6 @@ __device__ float block_max(float v, float* red) {
     return warp_max(t);
 }
 
-// Quantise the 32-element block held one element per lane into the global xq layout.
-__device__ __forceinline__ void quantize_block32(float v, int blk, int lane, int8_t* xq, int K) {
-    int q1, q2, q3;
-    float sc, s16;
-    quantize_lane32(v, q1, q2, q3, sc, s16);
-    // planes are stored in the GEMV's shared-memory order (16-byte columns XOR-swizzled inside each 128-byte line)
-    // so the consumer stages them with one TMA bulk copy
-    const int e = (int)xq_swizzle((uint32_t)(blk * 32 + lane));
-    xq[e] = (int8_t)q1;
-    xq[K + e] = (int8_t)q2;
-    xq[2 * K + e] = (int8_t)q3;
-    float* scale = reinterpret_cast<float*>(xq + 3 * (size_t)K);
-    float* sum16 = scale + K / 32;
-    if (lane == 0) scale[blk] = sc;
-    if ((lane & 15) == 0) sum16[blk * 2 + (lane >> 4)] = s16;
-}
-
 __global__ void quantize_x_kernel(const float* __restrict__ x, int8_t* __restrict__ xq, int K) {
     pdl_launch_dependents();
     pdl_wait();

@@ -4,7 +4,9 @@
 #include "engine.h"
 #include "tp_comm.h"
 #include <cstring>
+#include <algorithm>
 #include <memory>
+#include <string>
 
 using namespace nt::b200;
 
@@ -85,6 +87,87 @@ void nt_model_clear_kv(nt_model_t m) { if (m) H(m)->model.clear_kv(); }
 void nt_model_set_prefill_min_tokens(nt_model_t m, int n) { if (m) H(m)->model.set_prefill_min_tokens(n); }
 void nt_model_use_graph(nt_model_t m, int on) { if (m) H(m)->model.set_use_graph(on != 0); }
 unsigned long long nt_model_bytes_per_token(nt_model_t m, int ctx) { return m ? H(m)->model.bytes_per_token(ctx) : 0; }
+void nt_model_use_megakernel(nt_model_t m, int on) { if (m) H(m)->model.set_use_megakernel(on != 0); }
+int nt_model_megakernel_active(nt_model_t m) { return (m && H(m)->model.megakernel_active()) ? 1 : 0; }
+int nt_model_megakernel_plan(nt_model_t m, int* kinds, int cap) {
+    if (!m) return -1;
+    return H(m)->model.mega_plan_kinds(kinds, cap);
+}
+long long nt_model_debug_read(nt_model_t m, const char* name, float* out_host, size_t cap) {
+    if (!m || !name) return -1;
+    size_t n = 0;
+    const float* p = H(m)->model.mega_debug_buffer(name, &n);
+    if (!p) return -1;
+    NT_CUDA_CHECK(cudaStreamSynchronize(H(m)->model.stream()));
+    if (out_host) NT_CUDA_CHECK(cudaMemcpy(out_host, p, sizeof(float) * (n < cap ? n : cap), cudaMemcpyDeviceToHost));
+    return (long long)n;
+}
+
+// Host-only: builds the persistent kernel's per-token program for a model of the given (per-rank) shape with placeholder
+// addresses and replays its schedule on the CPU (decode_mega.h: mega_make_plan + mega_check_plan).  No CUDA call.
+int nt_mega_plan_selftest(const nt_model_config* c, int tp_rank, int tp_size, const int* layer_dtypes, int head_dtype, int grid,
+                          int split_fixed, int* info, char* msg, size_t cap) {
+    auto say = [&](const std::string& m) { if (msg && cap) { snprintf(msg, cap, "%s", m.c_str()); } };
+    if (!c || !layer_dtypes || tp_size < 1 || c->n_heads % tp_size || c->n_kv_heads % tp_size || c->intermediate_size % tp_size) {
+        say("bad arguments");
+        return -1;
+    }
+    MegaModelView mv;
+    mv.hidden = c->hidden_size; mv.nh = c->n_heads / tp_size; mv.nkv = c->n_kv_heads / tp_size; mv.hd = c->head_dim;
+    mv.inter = c->intermediate_size / tp_size; mv.max_seq = c->max_seq_len; mv.n_layers = c->n_layers;
+    mv.eps = c->norm_eps; mv.theta = c->rope_theta; mv.tp_rank = tp_rank; mv.tp_size = tp_size;
+    uintptr_t next = 0x10000000;                       // placeholder device addresses, 256-byte aligned
+    auto place = [&](size_t bytes) { void* p = reinterpret_cast<void*>(next); next += (bytes + 255) & ~(size_t)255; return p; };
+    auto weight = [&](int dt, int rows, int cols, bool col_shard) {
+        MegaWeight w;
+        w.dtype = (nt::DType)dt; w.rows = rows; w.cols = cols;
+        const size_t rb = nt::dtype_row_size(w.dtype, (size_t)cols);
+        w.pitch = col_shard ? ((rb + 15) & ~(size_t)15) : rb;      // Model::upload pads column shards to a 16-byte pitch
+        w.ptr = place(w.pitch * (size_t)std::max(rows, 1));
+        return w;
+    };
+    const int qdim = mv.nh * mv.hd, kvdim = mv.nkv * mv.hd;
+    for (int l = 0; l < mv.n_layers; l++) {
+        const int* d = layer_dtypes + 7 * l;
+        MegaLayerView L;
+        L.attn_norm = static_cast<const float*>(place((size_t)mv.hidden * 4));
+        L.ffn_norm = static_cast<const float*>(place((size_t)mv.hidden * 4));
+        L.wq = weight(d[0], qdim, mv.hidden, false); L.wk = weight(d[1], kvdim, mv.hidden, false); L.wv = weight(d[2], kvdim, mv.hidden, false);
+        L.wo = weight(d[3], mv.hidden, qdim, tp_size > 1);
+        L.gate = weight(d[4], mv.inter, mv.hidden, false); L.up = weight(d[5], mv.inter, mv.hidden, false);
+        L.down = weight(d[6], mv.hidden, mv.inter, tp_size > 1);
+        L.kc = place((size_t)mv.max_seq * kvdim * 2); L.vc = place((size_t)mv.max_seq * kvdim * 2);
+        mv.layers.push_back(L);
+    }
+    const int vl = (c->vocab_size + tp_size - 1) / tp_size;
+    const int vrows = tp_size == 1 ? c->vocab_size : std::max(0, std::min(vl, c->vocab_size - tp_rank * vl));
+    mv.head = weight(head_dtype, vrows, mv.hidden, false);
+    mv.out_norm = static_cast<const float*>(place((size_t)mv.hidden * 4));
+    mv.logits = static_cast<float*>(place((size_t)vl * 4));
+    mv.step = static_cast<const int*>(place(8));
+    MegaBuffers B;
+    B.hid[0] = static_cast<float*>(place((size_t)mv.hidden * 4)); B.hid[1] = static_cast<float*>(place((size_t)mv.hidden * 4));
+    B.q = static_cast<float*>(place((size_t)qdim * 4)); B.k = static_cast<float*>(place((size_t)kvdim * 4));
+    B.v = static_cast<float*>(place((size_t)kvdim * 4)); B.act = static_cast<float*>(place((size_t)mv.inter * 4));
+    B.xq_h = static_cast<int8_t*>(place(xq_bytes(mv.hidden))); B.xq_a = static_cast<int8_t*>(place(xq_bytes(qdim)));
+    B.xq_i = static_cast<int8_t*>(place(xq_bytes(mv.inter)));
+    MegaPlan pl;
+    std::string why;
+    if (!mega_make_plan(mv, B, grid, split_fixed, &pl, &why)) { say(why); return 1; }
+    if (info) {
+        int n_gemv = 0, min_warps = 99, min_stages = 99, n_exchange = 0;
+        for (const MegaPhase& ph : pl.phases) {
+            if (ph.kind == MPH_GEMV) { n_gemv++; min_warps = std::min(min_warps, ph.warps); min_stages = std::min(min_stages, ph.stages); }
+            if (ph.barrier == MBAR_EXCHANGE) n_exchange++;
+        }
+        info[0] = (int)pl.phases.size(); info[1] = pl.n_body; info[2] = n_gemv; info[3] = min_warps; info[4] = min_stages;
+        info[5] = n_exchange; info[6] = pl.n_splits_max; info[7] = pl.max_split;
+    }
+    const std::string bad = mega_check_plan(pl, grid, tp_size);
+    if (!bad.empty()) { say(bad); return 2; }
+    say("ok");
+    return 0;
+}
 
 int nt_gguf_describe(const char* path, char* out, size_t cap) {
     if (!path || !out || !cap) return -1;

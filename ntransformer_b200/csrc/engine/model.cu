@@ -355,7 +355,76 @@ void Model::step_head(cudaStream_t s) {
     }
 }
 
+// ---- opt-in: the decode step as one persistent kernel (engine/decode_mega.h) ----
+bool Model::ensure_mega() {
+    if (mega_) return true;
+    if (mega_tried_) return false;
+    mega_tried_ = true;
+    MegaModelView mv;
+    mv.hidden = cfg_.hidden_size; mv.nh = nh_l_; mv.nkv = nkv_l_; mv.hd = cfg_.head_dim; mv.inter = inter_l_;
+    mv.max_seq = cfg_.max_seq_len; mv.n_layers = cfg_.n_layers;
+    mv.eps = cfg_.norm_eps; mv.theta = cfg_.rope_theta; mv.freq_scale = cfg_.rope_freq_scale;
+    mv.tp_rank = tp_rank_; mv.tp_size = tp_size_;
+    auto W = [](const Weight& w) { return MegaWeight{w.ptr, w.dtype, w.rows, w.cols, w.pitch}; };
+    const size_t kv_stride = (size_t)cfg_.max_seq_len * nkv_l_ * cfg_.head_dim;
+    for (int i = 0; i < cfg_.n_layers; i++) {
+        const LayerWeights& L = layers_[(size_t)i];
+        MegaLayerView lv{L.attn_norm, L.ffn_norm, W(L.wq), W(L.wk), W(L.wv), W(L.wo), W(L.gate), W(L.up), W(L.down),
+                         static_cast<uint16_t*>(kc_) + (size_t)i * kv_stride, static_cast<uint16_t*>(vc_) + (size_t)i * kv_stride};
+        mv.layers.push_back(lv);
+    }
+    mv.head = W(head_);
+    mv.out_norm = out_norm_;
+    mv.logits = tp_size_ == 1 ? logits_ : logits_l_;
+    mv.step = step_dev_;
+    auto m = std::make_unique<DecodeMega>();
+    if (const char* sf = getenv("NT_B200_MEGA_SPLIT_COMPAT"))      // the graph path's split rule: bit-comparable attention
+        if (atoi(sf) != 0) m->set_split_fixed(attention_decode_dyn_splits(cfg_.max_seq_len, nh_l_, nkv_l_));
+    if (!m->build(mv)) {
+        fprintf(stderr, "Note: persistent decode kernel not used (%s); keeping the graph of fused launches\n", m->why().c_str());
+        return false;
+    }
+    if (tp_size_ > 1) {                                            // map every peer's slot/flag allocation (CUDA IPC over NVLink)
+        NT_CHECK(comm_ != nullptr, "tensor-parallel model without a communicator");
+        const size_t per = DecodeMega::kIpcBytes / sizeof(float);
+        float* buf = dmalloc<float>(per * (size_t)(tp_size_ + 1));
+        char mine[DecodeMega::kIpcBytes];
+        m->export_ipc(mine);
+        NT_CUDA_CHECK(cudaMemcpyAsync(buf, mine, sizeof(mine), cudaMemcpyHostToDevice, stream_));
+        comm_->all_gather(buf, buf + per, per, stream_);
+        std::vector<char> all((size_t)DecodeMega::kIpcBytes * tp_size_);
+        NT_CUDA_CHECK(cudaMemcpyAsync(all.data(), buf + per, all.size(), cudaMemcpyDeviceToHost, stream_));
+        NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        NT_CUDA_CHECK(cudaFree(buf));
+        m->import_peers(all.data());
+    }
+    mega_ = std::move(m);
+    return true;
+}
+
+bool Model::megakernel_active() { return mega_ != nullptr; }
+
+const float* Model::mega_debug_buffer(const char* name, size_t* count) {
+    if (!mega_) { if (count) *count = 0; return nullptr; }
+    return mega_->debug_buffer(name, count);
+}
+
+int Model::mega_plan_kinds(int* kinds, int cap) {
+    if (!mega_) return 0;
+    const auto& pl = mega_->plan();
+    for (int i = 0; i < (int)pl.size() && i < cap; i++) kinds[i] = pl[(size_t)i].kind;
+    return (int)pl.size();
+}
+
+// embedding gather -> persistent kernel (all layers [+ final norm and LM head]) [-> all-gather of the logits shards]
+void Model::run_step_mega(bool with_head) {
+    embed_rows(mega_->embed_out(), embd_.ptr, embd_.dtype, step_dev_, 1, cfg_.hidden_size, stream_);
+    mega_->launch(with_head, stream_);
+    if (with_head && tp_size_ > 1) comm_->all_gather(logits_l_, logits_, (size_t)vocab_l_, stream_);
+}
+
 void Model::run_step(bool with_head) {
+    if ((use_mega_ || getenv("NT_B200_MEGAKERNEL")) && ensure_mega()) { run_step_mega(with_head); return; }
     if (!use_graph_ || getenv("NT_B200_NO_GRAPH")) {
         step_body(stream_);
         if (with_head) step_head(stream_);
@@ -497,6 +566,7 @@ void Model::forward_async(const int* tokens, int seq_len, int start_pos) {
 float* Model::forward(const int* tokens, int seq_len, int start_pos) {
     forward_async(tokens, seq_len, start_pos);
     NT_CUDA_CHECK(cudaStreamSynchronize(stream_));                           // transformer.cpp:667
+    if (mega_) mega_->check_abort();
     return logits_;
 }
 
@@ -504,6 +574,7 @@ int Model::argmax_last() {
     argmax_kernel<<<1, 1024, 0, stream_>>>(logits_, cfg_.vocab_size, argmax_dev_);
     NT_CUDA_CHECK(cudaMemcpyAsync(argmax_host_, argmax_dev_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
     NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (mega_) mega_->check_abort();
     return *argmax_host_;
 }
 

@@ -11,8 +11,10 @@
 #include <cuda_runtime.h>
 #include <string>
 #include <vector>
+#include <memory>
 #include "../kernels_internal.h"
 #include "gguf.h"
+#include "decode_mega.h"
 
 namespace nt { namespace b200 {
 
@@ -72,8 +74,17 @@ public:
     void set_prefill_min_tokens(int n) { prefill_min_tokens_ = n; }
     bool batched_prefill_ok(int seq_len, int start_pos) const;
     void clear_kv();
+    // Opt-in (also NT_B200_MEGAKERNEL=1): run the decode step as one persistent kernel (engine/decode_mega.h) instead of
+    // the graph of fused launches.  Falls back to the graph path, with a note on stderr, when a shape is not covered.
+    void set_use_megakernel(bool on) { use_mega_ = on; }
+    bool megakernel_active();                 // true once the persistent kernel has been built for this model
+    // Debug read-back of the persistent kernel's working buffers ("hid0", "hid1", "q", "attn", "act", "slots"): device pointer.
+    const float* mega_debug_buffer(const char* name, size_t* count);
+    int mega_plan_kinds(int* kinds, int cap);  // phase kinds of the per-token program; returns their number (0 when inactive)
 
 private:
+    bool ensure_mega();
+    void run_step_mega(bool with_head);
     void step_body(cudaStream_t s);      // embedding + all layers for the token/position in step_dev_
     void step_head(cudaStream_t s);      // final norm + LM head (+ all-gather under TP)
     void run_step(bool with_head);
@@ -128,6 +139,10 @@ private:
     cudaGraphExec_t g_full_ = nullptr, g_body_ = nullptr;
     int n_full_ = 0, n_body_ = 0;        // kernels per graph replay
     bool finalized_ = false;
+
+    bool use_mega_ = false;
+    bool mega_tried_ = false;
+    std::unique_ptr<DecodeMega> mega_;
 };
 
 }}  // namespace nt::b200

@@ -128,6 +128,32 @@ class Model:
         """Prompts of >= n tokens take the batched tensor-core prefill (F16 models); 0 = per-token replay only."""
         lib().nt_model_set_prefill_min_tokens(self._h, int(n))
 
+    def use_megakernel(self, on: bool = True):
+        """Opt-in: decode each token as one persistent kernel (csrc/engine/decode_mega.h). Call before the first forward."""
+        lib().nt_model_use_megakernel(self._h, int(on))
+
+    @property
+    def megakernel_active(self) -> bool:
+        return bool(lib().nt_model_megakernel_active(self._h))
+
+    def megakernel_plan(self):
+        """Phase kinds of the persistent kernel's per-token program ([] when it is not active)."""
+        n = lib().nt_model_megakernel_plan(self._h, None, 0)
+        if n <= 0:
+            return []
+        buf = (C.c_int * n)()
+        lib().nt_model_megakernel_plan(self._h, buf, n)
+        return list(buf)
+
+    def debug_read(self, name: str):
+        """Host copy of one of the persistent kernel's working vectors (hid0, hid1, q, attn, act, slots)."""
+        n = lib().nt_model_debug_read(self._h, name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, dtype=np.float32)
+        lib().nt_model_debug_read(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), n)
+        return out
+
     @property
     def stream(self) -> int:
         return lib().nt_model_stream(self._h)
