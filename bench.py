@@ -394,7 +394,8 @@ def run_ours(args, rank, world):
                        "ctx_during_timing": [ctx_first, ctx_first + args.steps], "max_seq": max_seq,
                        "parallelism": f"tp{world}" if world > 1 else "single",
                        "l2_policy": "weights per step (%.1f GB/GPU) exceed the 126 MB L2; no flush needed" % (b_tok / 1e9),
-                       "cuda_graph": True},
+                       "cuda_graph": not model.megakernel_active,
+                       "decode_path": "persistent kernel (NT_B200_MEGAKERNEL)" if model.megakernel_active else "cuda graph of fused launches"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_tok_s, 2), "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": vocab * 4,
                     "ms_per_step": round(e2e_ms / args.steps, 4)},
