@@ -33,10 +33,11 @@ def gpt2_byte_tokens():
     return out
 
 
-def write_gguf(path, cfg: LlamaConfig, tensors: dict, vocab_tokens=None, name="synthetic"):
+def write_gguf(path, cfg: LlamaConfig, tensors: dict, vocab_tokens=None, name="synthetic", vocab_scores=None, vocab_types=None):
     """tensors: name -> (np.ndarray bytes/f32, DType, rows, cols) in GGUF block layout."""
     table = [(n, dt, r, c) for n, (a, dt, r, c) in tensors.items()]
-    write_gguf_streaming(path, cfg, ((n, a, dt, r, c) for n, (a, dt, r, c) in tensors.items()), table, vocab_tokens, name)
+    write_gguf_streaming(path, cfg, ((n, a, dt, r, c) for n, (a, dt, r, c) in tensors.items()), table, vocab_tokens, name,
+                         vocab_scores, vocab_types)
 
 
 def _tensor_nbytes(dt, rows, cols):
@@ -44,7 +45,8 @@ def _tensor_nbytes(dt, rows, cols):
     return rows * dtype_row_size(dt, cols)
 
 
-def write_gguf_streaming(path, cfg: LlamaConfig, gen, table=None, vocab_tokens=None, name="synthetic"):
+def write_gguf_streaming(path, cfg: LlamaConfig, gen, table=None, vocab_tokens=None, name="synthetic", vocab_scores=None,
+                         vocab_types=None):
     """Like write_gguf but `gen` yields (name, array, DType, rows, cols) one tensor at a time, in the order of
     `table` ([(name, DType, rows, cols)], default tensor_table(cfg-independent order of gen is NOT allowed))."""
     if table is None:
@@ -73,9 +75,12 @@ def write_gguf_streaming(path, cfg: LlamaConfig, gen, table=None, vocab_tokens=N
     kv_u32("tokenizer.ggml.bos_token_id", cfg.bos_token_id)
     kv_u32("tokenizer.ggml.eos_token_id", cfg.eos_token_id)
     kv.append(_s("tokenizer.ggml.tokens") + struct.pack("<IIQ", _T_ARR, _T_STR, len(vocab_tokens)) + b"".join(_s(t) for t in vocab_tokens))
-    scores = np.arange(len(vocab_tokens), 0, -1, dtype=np.float32)
+    scores = (np.arange(len(vocab_tokens), 0, -1, dtype=np.float32) if vocab_scores is None
+              else np.asarray(vocab_scores, dtype=np.float32))
+    assert len(scores) == len(vocab_tokens)
     kv.append(_s("tokenizer.ggml.scores") + struct.pack("<IIQ", _T_ARR, _T_F32, len(scores)) + scores.tobytes())
-    types = np.ones(len(vocab_tokens), dtype=np.int32)
+    types = np.ones(len(vocab_tokens), dtype=np.int32) if vocab_types is None else np.asarray(vocab_types, dtype=np.int32)
+    assert len(types) == len(vocab_tokens)
     kv.append(_s("tokenizer.ggml.token_type") + struct.pack("<IIQ", _T_ARR, _T_I32, len(types)) + types.tobytes())
 
     infos, offset, offsets = [], 0, {}
