@@ -22,12 +22,28 @@ namespace nt { namespace b200 {
 
 namespace {
 
+#ifdef NT_CUSIM
+#define NT_NOINLINE __attribute__((noinline))
+#else
+#define NT_NOINLINE __noinline__
+#endif
+
 constexpr int NTHREADS = MEGA_WARPS * 32;
 constexpr int AW = MEGA_ATTN_WARPS;
 constexpr size_t MEGA_STATIC_SMEM = 4096;                                   // upper bound of the kernel's static __shared__
 constexpr size_t MEGA_DYN_SMEM = 227 * 1024 - MEGA_STATIC_SMEM;             // TMA rings; aliased by the attention scratch
 
 // ---- memory-model helpers -----------------------------------------------------------------------------------------
+#ifdef NT_CUSIM   // CPU emulation (tests/cusim): C++ atomics; the acquire loads yield so that spinning threads let others run
+inline unsigned ld_acquire_gpu(const unsigned* p) { cusim::yield("spin (grid barrier word)"); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline unsigned ld_acquire_sys(const unsigned* p) { cusim::yield("spin (peer flag)"); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline unsigned ld_relaxed_gpu(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline void red_release_gpu_add(unsigned* p, unsigned v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
+inline void st_release_gpu(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline void st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned long long global_timer_ns() { return (unsigned long long)(cusim::now_s() * 1e9); }
+inline void fence_proxy_async_smem() {}
+#else
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -59,10 +75,12 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#endif
+
 // Spin until (int)(*p - target) >= 0.  SYS: the word is written by another GPU.  A time-out (or an abort raised elsewhere)
 // sets the abort word and returns: every later barrier then falls through and the host reports the failure.
 template <bool SYS>
-__device__ __noinline__ void spin_until(const unsigned* p, unsigned target, unsigned* abort_word, unsigned long long timeout_ns) {
+__device__ NT_NOINLINE void spin_until(const unsigned* p, unsigned target, unsigned* abort_word, unsigned long long timeout_ns) {
     if (ld_relaxed_gpu(abort_word)) return;
     const unsigned long long t0 = global_timer_ns();
     unsigned n = 0;
@@ -594,7 +612,11 @@ __device__ void combine_phase(const MegaParams& P) {
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_constant__ MegaParams P) {
+#ifdef NT_CUSIM
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(cusim::g_cta->dyn_smem.data()) + 127) & ~(uintptr_t)127);
+#else
     extern __shared__ __align__(128) uint8_t smem[];
+#endif
     __shared__ Shared S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -682,14 +704,6 @@ MegaGemvGeom mega_gemv_geom(const int* fmts, int n_mat, int K, size_t ring_bytes
     g.stages = (int)std::min<size_t>(MEGA_MAX_STAGES, ring_bytes / ((size_t)best * g.slot_bytes));
     g.ok = g.stages >= 1;
     return g;
-}
-
-DecodeMega::~DecodeMega() {
-    for (size_t r = 0; r < peer_maps_.size(); r++)
-        if (peer_maps_[r] && (int)r != tp_rank_) cudaIpcCloseMemHandle(peer_maps_[r]);
-    for (void* p : {(void*)phases_dev_, (void*)hid_[0], (void*)hid_[1], (void*)q_, (void*)k_, (void*)v_, (void*)attn_, (void*)act_,
-                    (void*)scratch_, (void*)xq_h_, (void*)xq_a_, (void*)xq_i_, (void*)sync_, xchg_})
-        if (p) cudaFree(p);
 }
 
 // Pure host function (no CUDA calls): the per-token program for `mv` with working buffers `B` on a grid of `grid` CTAs.
@@ -925,6 +939,16 @@ std::string mega_check_plan(const MegaPlan& pl, int grid, int tp_size) {
     return "";
 }
 
+#ifndef NT_CUSIM   // everything below talks to the CUDA runtime; the CPU emulation (tests/cusim) stops here
+
+DecodeMega::~DecodeMega() {
+    for (size_t r = 0; r < peer_maps_.size(); r++)
+        if (peer_maps_[r] && (int)r != tp_rank_) cudaIpcCloseMemHandle(peer_maps_[r]);
+    for (void* p : {(void*)phases_dev_, (void*)hid_[0], (void*)hid_[1], (void*)q_, (void*)k_, (void*)v_, (void*)attn_, (void*)act_,
+                    (void*)scratch_, (void*)xq_h_, (void*)xq_a_, (void*)xq_i_, (void*)sync_, xchg_})
+        if (p) cudaFree(p);
+}
+
 bool DecodeMega::build(const MegaModelView& mv) {
     auto fail = [&](const std::string& w) { why_ = w; return false; };
     hidden_ = mv.hidden; nh_ = mv.nh; hd_ = mv.hd; inter_ = mv.inter; tp_rank_ = mv.tp_rank; tp_size_ = mv.tp_size;
@@ -1040,5 +1064,7 @@ const float* DecodeMega::debug_buffer(const char* name, size_t* count) const {
     if (count) *count = 0;
     return nullptr;
 }
+
+#endif  // NT_CUSIM
 
 }}  // namespace nt::b200

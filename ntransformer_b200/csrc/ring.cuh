@@ -1,6 +1,9 @@
 // ring.cuh — mbarrier + 1-D TMA bulk-copy helpers (sm_100a inline PTX).
 // SASS: cp.async.bulk -> UBLKCP.S.G, expect_tx -> SYNCS.ARRIVE.TRANS64, try_wait -> SYNCS.PHASECHK.TRYWAIT.
 #pragma once
+#ifdef NT_CUSIM            // CPU emulation of this header for tests/cusim (test infrastructure; never defined in the product build)
+#include "cusim_ring.h"
+#else
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -50,3 +53,4 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 }}  // namespace nt::b200
+#endif  // NT_CUSIM
