@@ -141,3 +141,11 @@ def test_tensor_parallel_exchange(sim, tmp_path, tp, cfg, grid, delay):
     # tp emulated GPUs in one process: partial o-proj / down-proj rows pushed into every peer's slots, flag round trip
     # between the master CTAs, identical residual stream on every rank, LM-head shards gathered by the harness
     check_against_oracle(sim, tmp_path, cfg, "Q4_K", steps=4 if cfg is not SMALL128 else 1, tp=tp, grid=grid, copy_delay=delay, tol=5e-4)
+
+
+def test_ragged_rows_odd_grid_and_uneven_vocab_shards(sim, tmp_path):
+    # vocab 510: the LM head's last row-group is ragged (rows % 4 != 0); under TP-2 the shards are 255 rows each;
+    # grid 5: row-groups do not divide evenly over the CTAs, some CTAs idle in the last round
+    cfg = LlamaConfig(**{**TINY.dict(), "vocab_size": 510, "n_layers": 2})
+    check_against_oracle(sim, tmp_path, cfg, "Q4_K", steps=3, grid=5)
+    check_against_oracle(sim, tmp_path, cfg, "Q4_K", steps=2, tp=2, grid=3, copy_delay=3, tol=5e-4)
