@@ -106,7 +106,7 @@ long long nt_model_debug_read(nt_model_t m, const char* name, float* out_host, s
 // Host-only: builds the persistent kernel's per-token program for a model of the given (per-rank) shape with placeholder
 // addresses and replays its schedule on the CPU (decode_mega.h: mega_make_plan + mega_check_plan).  No CUDA call.
 int nt_mega_plan_selftest(const nt_model_config* c, int tp_rank, int tp_size, const int* layer_dtypes, int head_dtype, int grid,
-                          int split_fixed, int* info, char* msg, size_t cap) {
+                          int split_fixed, int fuse, int* info, char* msg, size_t cap) {
     auto say = [&](const std::string& m) { if (msg && cap) { snprintf(msg, cap, "%s", m.c_str()); } };
     if (!c || !layer_dtypes || tp_size < 1 || c->n_heads % tp_size || c->n_kv_heads % tp_size || c->intermediate_size % tp_size) {
         say("bad arguments");
@@ -151,9 +151,10 @@ int nt_mega_plan_selftest(const nt_model_config* c, int tp_rank, int tp_size, co
     B.v = static_cast<float*>(place((size_t)kvdim * 4)); B.act = static_cast<float*>(place((size_t)mv.inter * 4));
     B.xq_h = static_cast<int8_t*>(place(xq_bytes(mv.hidden))); B.xq_a = static_cast<int8_t*>(place(xq_bytes(qdim)));
     B.xq_i = static_cast<int8_t*>(place(xq_bytes(mv.inter)));
+    B.cnt_quant = static_cast<unsigned*>(place((size_t)mv.inter / 32 * 4 + 4)); B.cnt_attn = static_cast<unsigned*>(place((size_t)mv.nh * 4 + 4));
     MegaPlan pl;
     std::string why;
-    if (!mega_make_plan(mv, B, grid, split_fixed, &pl, &why)) { say(why); return 1; }
+    if (!mega_make_plan(mv, B, grid, split_fixed, fuse, &pl, &why)) { say(why); return 1; }
     if (info) {
         int n_gemv = 0, min_warps = 99, min_stages = 99, n_exchange = 0;
         for (const MegaPhase& ph : pl.phases) {

@@ -45,6 +45,7 @@ constexpr int MEGA_SYNC_WORDS = 4 * 32;     // counter, go, abort, exchange sequ
 enum MegaPhaseKind : int { MPH_NORM_XQ = 0, MPH_QUANT = 1, MPH_GEMV = 2, MPH_ATTN = 3, MPH_COMBINE = 4 };
 enum MegaBarrierKind : int { MBAR_NONE = 0, MBAR_GRID = 1, MBAR_EXCHANGE = 2 };
 enum MegaEpilogue : int { MEP_STORE = 0, MEP_SWIGLU = 2, MEP_SLOT = 3 };
+enum MegaFuse : int { MEGA_FUSE_QUANT = 1, MEGA_FUSE_COMBINE = 2 };
 
 struct MegaMat {
     const uint8_t* W;
@@ -80,6 +81,14 @@ struct MegaPhase {
     // ---- MPH_ATTN / MPH_COMBINE: this layer's KV cache ----
     void* kc;
     void* vc;
+    // ---- producer-side fusions (MEGA_FUSE_*): "last arriver" counters, zero between uses ----
+    //   MPH_GEMV + SwiGLU: the warp that completes the last row-group of a 32-row block quantises the block into xq_out
+    //                      (x = the activation vector, n = its length) => no MPH_QUANT phase, one barrier less;
+    //   MPH_ATTN:          the unit that completes the last split of a head group merges the splits and emits xq_a
+    //                      => no MPH_COMBINE phase, one barrier less.
+    unsigned* cnt;
+    int fuse;
+    int pad_;
 };
 static_assert(sizeof(MegaPhase) % 4 == 0 && sizeof(MegaPhase) <= 4 * MEGA_WARPS * 32, "MegaPhase is copied by one CTA-wide pass of 32-bit loads");
 
@@ -124,6 +133,8 @@ struct MegaBuffers {
     float* hid[2] = {nullptr, nullptr};
     float *q = nullptr, *k = nullptr, *v = nullptr, *act = nullptr;
     int8_t *xq_h = nullptr, *xq_a = nullptr, *xq_i = nullptr;
+    unsigned* cnt_quant = nullptr;      // inter / 32 counters (MEGA_FUSE_QUANT)
+    unsigned* cnt_attn = nullptr;       // one counter per attention head group (MEGA_FUSE_COMBINE)
 };
 struct MegaPlan {
     std::vector<MegaPhase> phases;
@@ -131,9 +142,10 @@ struct MegaPlan {
     int first_gemv = -1;
     int gc = 0;                     // query heads per attention unit
     int n_splits_max = 0, split_fixed = 0, min_split = 0, max_split = 0;
+    int fuse = 0;                   // MegaFuse bits in effect
 };
 // Pure host functions (no CUDA calls; unit-tested on the CPU through nt_b200_mega_selftest).
-bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int split_fixed, MegaPlan* out, std::string* why);
+bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int split_fixed, int fuse, MegaPlan* out, std::string* why);
 std::string mega_check_gemv_schedule(const MegaPhase& d, int grid, size_t ring_bytes);   // "" = the schedule is consistent
 std::string mega_check_plan(const MegaPlan& pl, int grid, int tp_size);                  // "" = structural invariants hold
 
@@ -171,6 +183,7 @@ public:
     int n_phases(bool with_head) const { return with_head ? (int)plan_.phases.size() : plan_.n_body; }
     const float* debug_buffer(const char* name, size_t* count) const;
     void set_split_fixed(int n) { split_fixed_ = n; }      // before build(): use the graph path's split rule (bit-identical attention)
+    void set_fuse(int bits) { fuse_ = bits; }              // before build(): MegaFuse bits (default 0: the plain 9-phase program)
 
 private:
     MegaPlan plan_;
@@ -183,7 +196,8 @@ private:
     void* xchg_ = nullptr;             // [slots 2 x tp x hidden floats][flags tp x 32 words], IPC-exportable
     std::vector<void*> peer_maps_;
     int hidden_ = 0, nh_ = 0, hd_ = 0, inter_ = 0, tp_rank_ = 0, tp_size_ = 1, grid_ = 0;
-    int split_fixed_ = 0;
+    int split_fixed_ = 0, fuse_ = 0;
+    unsigned *cnt_quant_ = nullptr, *cnt_attn_ = nullptr;
     bool peers_ready_ = false;
     std::string why_;
 };

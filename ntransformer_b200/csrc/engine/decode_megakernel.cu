@@ -150,6 +150,7 @@ struct Shared {
     float partial[2][MEGA_WARPS][2][RG];             // [buffer][warp][segment][row] chunk partial sums
     float red[32];
     float s_max[8], s_sum[8];
+    unsigned bcast;                                  // CTA-wide broadcast of a last-arriver ticket
 };
 static_assert(sizeof(Shared) <= MEGA_STATIC_SMEM, "static shared memory budget");
 
@@ -314,25 +315,46 @@ __device__ void gemv_phase(const MegaParams& P, Shared& S, uint8_t* smem, Produc
             S.partial[buf][warp][1][r] = res[1];
         }
         __syncthreads();
-        if (live && chunk == 0 && lane < RG) {
-            float v0 = 0.f, v1 = 0.f;
-            for (int c = 0; c < NC; c++) {
-                v0 += S.partial[buf][gsub * NC + c][0][lane];
-                if (n_seg == 2) v1 += S.partial[buf][gsub * NC + c][1][lane];
-            }
+        if (live && chunk == 0) {                            // warp-uniform
             int mi, gl;
             locate(d, g, 0, mi, gl);
             const MegaMat& m = d.mat[mi];
-            const int row = gl * RG + lane;
-            if (row < m.out) {
-                if (d.epilogue == MEP_SWIGLU) {
-                    m.y[row] = __fdividef(v0, 1.0f + __expf(-v0)) * v1;       // reference gemm.cu:713-725
-                } else if (d.epilogue == MEP_SLOT) {
-                    // partial result of this rank -> slot [parity][this rank] on every tensor-parallel peer (NVLink stores)
-                    const size_t off = ((size_t)d.slot_parity * P.tp_size + P.tp_rank) * (size_t)P.hidden + (size_t)row;
-                    for (int r = 0; r < P.tp_size; r++) P.slots[r][off] = v0;
-                } else {
-                    m.y[row] = v0;
+            if (lane < RG) {
+                float v0 = 0.f, v1 = 0.f;
+                for (int c = 0; c < NC; c++) {
+                    v0 += S.partial[buf][gsub * NC + c][0][lane];
+                    if (n_seg == 2) v1 += S.partial[buf][gsub * NC + c][1][lane];
+                }
+                const int row = gl * RG + lane;
+                if (row < m.out) {
+                    if (d.epilogue == MEP_SWIGLU) {
+                        m.y[row] = __fdividef(v0, 1.0f + __expf(-v0)) * v1;       // reference gemm.cu:713-725
+                    } else if (d.epilogue == MEP_SLOT) {
+                        // partial result of this rank -> slot [parity][this rank] on every tensor-parallel peer (NVLink stores)
+                        const size_t off = ((size_t)d.slot_parity * P.tp_size + P.tp_rank) * (size_t)P.hidden + (size_t)row;
+                        for (int r = 0; r < P.tp_size; r++) P.slots[r][off] = v0;
+                    } else {
+                        m.y[row] = v0;
+                    }
+                }
+            }
+            if (d.epilogue == MEP_SWIGLU && (d.fuse & MEGA_FUSE_QUANT)) {
+                // Last-arriver quantiser: the warp that completes the 8th row-group of a 32-row block turns the block into xq
+                // (same quantize_block32 as the stand-alone phase => same bytes), so the down projection needs no separate
+                // quantise phase and barrier.  Writers fence before the ticket, the last arriver fences before it reads back.
+                __threadfence();
+                __syncwarp();
+                const int block = gl >> 3;
+                const int groups_in_block = min(8, m.groups - block * 8);
+                unsigned prev = 0;
+                if (lane == 0) prev = atomicAdd(d.cnt + block, 1u);
+                prev = __shfl_sync(0xFFFFFFFFu, prev, 0);
+                if ((int)prev == groups_in_block - 1) {
+                    __threadfence();
+                    const int e = block * 32 + lane;
+                    const float v = (e < d.n) ? __ldcg(d.x + e) : 0.f;
+                    quantize_block32(v, block, lane, d.xq_out, d.n);
+                    if (lane == 0) d.cnt[block] = 0;         // ready for the next layer
                 }
             }
         }
@@ -427,13 +449,15 @@ __device__ __forceinline__ SplitRule split_rule(const MegaParams& P, int ctx, in
     return r;
 }
 
+__device__ __forceinline__ void combine_head(const MegaParams& P, int h, int used);
+
 // One unit: GC query heads that share KV head `kv_head`, keys [k_begin, k_end) of a context of pos + 1 tokens.
 // RoPE of the unit's queries and of the token's own key (reference rotary.cu:16-62 expression), the F16 rounding of the
 // cache write (attention.cu:316-342) and, in the unit that owns the last split, the cache write itself happen here, so
 // no grid barrier is needed between the q/k/v projection and attention.  Scores / softmax / P.V as attend_group.
 template <int DPL, int GC>
 __device__ void attend_unit(const MegaParams& P, Shared& S, const MegaPhase& d, float* smf, int head0, int kv_head, int split,
-                            int k_begin, int k_end, int pos, bool write_cache) {
+                            int k_begin, int k_end, int pos, bool write_cache, int grp, int used) {
     constexpr int HD = DPL * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_keys = k_end - k_begin;
@@ -565,6 +589,20 @@ __device__ void attend_unit(const MegaParams& P, Shared& S, const MegaPhase& d, 
             ml[((size_t)(head0 + g) * NS + split) * 2 + (threadIdx.x & 1)] = (threadIdx.x & 1) ? S.s_sum[g] : S.s_max[g];
         }
     }
+    if (d.fuse & MEGA_FUSE_COMBINE) {
+        // Last-arriver combine: the unit that completes the last split of this head group merges the group's splits and
+        // emits their xq (same arithmetic as the combine phase), so no separate combine phase and barrier.
+        __threadfence();                                     // this unit's partials are visible before its ticket
+        __syncthreads();
+        if (threadIdx.x == 0) S.bcast = atomicAdd(d.cnt + grp, 1u);
+        __syncthreads();
+        if ((int)S.bcast == used - 1) {                      // CTA-uniform
+            __threadfence();
+            if (threadIdx.x < 128)
+                for (int g = 0; g < GC; g++) combine_head(P, head0 + g, used);
+            if (threadIdx.x == 0) d.cnt[grp] = 0;            // ready for the next layer
+        }
+    }
     __syncthreads();                                         // shared memory is reused by the CTA's next unit
 }
 
@@ -581,33 +619,35 @@ __device__ void attn_phase(const MegaParams& P, Shared& S, uint8_t* smem) {
         const int k_begin = split * sr.split_len, k_end = min(ctx, k_begin + sr.split_len);
         // the unit that holds the token's own position writes the cache row; one writer per KV head
         const bool write_cache = (k_end == ctx) && (head0 % ratio == 0);
-        attend_unit<DPL, GC>(P, S, d, reinterpret_cast<float*>(smem), head0, kv_head, split, k_begin, k_end, pos, write_cache);
+        attend_unit<DPL, GC>(P, S, d, reinterpret_cast<float*>(smem), head0, kv_head, split, k_begin, k_end, pos, write_cache, grp, sr.used);
     }
 }
 
-// Merge the split partials of each head and emit the o-projection's xq (decode_combine_kernel with xq_out).
-__device__ void combine_phase(const MegaParams& P) {
+// Merge the split partials of head h and emit its slice of the o-projection's xq (decode_combine_kernel with xq_out).
+// Called by threads 0..127 of a CTA (hd % 32 == 0: whole warps stay together in the quantiser).
+__device__ __forceinline__ void combine_head(const MegaParams& P, int h, int used) {
     const int hd = P.hd, n_heads = P.nh, NS = P.n_splits_max;
-    const int ctx = P.step[1] + 1;
-    const SplitRule sr = split_rule(P, ctx, n_heads / P.gc);
-    const int used = sr.used;
-    if (threadIdx.x >= 128) return;
-    for (int h = blockIdx.x; h < n_heads; h += gridDim.x) {
-        const float* ml = P.attn_scratch + (size_t)n_heads * NS * hd + (size_t)h * NS * 2;
-        float m = -FLT_MAX;
-        for (int i = 0; i < used; i++) m = fmaxf(m, __ldcg(ml + 2 * i));
-        float l = 0.f;
-        for (int i = 0; i < used; i++) l += __ldcg(ml + 2 * i + 1) * expf(__ldcg(ml + 2 * i) - m);
-        const float inv = (l > 0.f) ? 1.0f / l : 0.f;
-        for (int dd = threadIdx.x; dd < hd; dd += 128) {       // hd % 32 == 0: whole warps stay together
-            float o = 0.f;
-            for (int i = 0; i < used; i++) o += __ldcg(P.attn_scratch + ((size_t)h * NS + i) * hd + dd) * expf(__ldcg(ml + 2 * i) - m);
-            const float v = o * inv;
-            P.attn_out[(size_t)h * hd + dd] = v;
-            const int K = n_heads * hd, e = h * hd + dd, lane = threadIdx.x & 31;
-            quantize_block32(v, e >> 5, lane, P.xq_a, K);
-        }
+    const float* ml = P.attn_scratch + (size_t)n_heads * NS * hd + (size_t)h * NS * 2;
+    float m = -FLT_MAX;
+    for (int i = 0; i < used; i++) m = fmaxf(m, __ldcg(ml + 2 * i));
+    float l = 0.f;
+    for (int i = 0; i < used; i++) l += __ldcg(ml + 2 * i + 1) * expf(__ldcg(ml + 2 * i) - m);
+    const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+    for (int dd = threadIdx.x; dd < hd; dd += 128) {
+        float o = 0.f;
+        for (int i = 0; i < used; i++) o += __ldcg(P.attn_scratch + ((size_t)h * NS + i) * hd + dd) * expf(__ldcg(ml + 2 * i) - m);
+        const float v = o * inv;
+        P.attn_out[(size_t)h * hd + dd] = v;
+        const int K = n_heads * hd, e = h * hd + dd, lane = threadIdx.x & 31;
+        quantize_block32(v, e >> 5, lane, P.xq_a, K);
     }
+}
+
+__device__ void combine_phase(const MegaParams& P) {
+    const int ctx = P.step[1] + 1;
+    const SplitRule sr = split_rule(P, ctx, P.nh / P.gc);
+    if (threadIdx.x >= 128) return;
+    for (int h = blockIdx.x; h < P.nh; h += gridDim.x) combine_head(P, h, sr.used);
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------------
@@ -707,7 +747,7 @@ MegaGemvGeom mega_gemv_geom(const int* fmts, int n_mat, int K, size_t ring_bytes
 }
 
 // Pure host function (no CUDA calls): the per-token program for `mv` with working buffers `B` on a grid of `grid` CTAs.
-bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int split_fixed, MegaPlan* out, std::string* why) {
+bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int split_fixed, int fuse, MegaPlan* out, std::string* why) {
     auto fail = [&](const std::string& w) { if (why) *why = w; return false; };
     MegaPlan& pl = *out;
     pl = MegaPlan{};
@@ -722,6 +762,9 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
     if (hidden % 256 != 0 || (mv.nh * mv.hd) % 256 != 0 || inter % 256 != 0) return fail("dimensions must be multiples of 256");
     if (grid < 1 || hidden / 256 > grid) return fail("hidden / 256 exceeds the grid");
     pl.gc = gc;
+    if ((fuse & MEGA_FUSE_QUANT) && !B.cnt_quant) fuse &= ~MEGA_FUSE_QUANT;
+    if ((fuse & MEGA_FUSE_COMBINE) && !B.cnt_attn) fuse &= ~MEGA_FUSE_COMBINE;
+    pl.fuse = fuse;
     const int qdim = mv.nh * mv.hd;
 
     // ---- attention split geometry ----
@@ -802,8 +845,10 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
           if (L.wq.rows != qdim || L.wk.rows != mv.nkv * mv.hd || L.wv.rows != mv.nkv * mv.hd || L.wq.cols != hidden) return fail("attn_q/k/v shape");
           if (!gemv_phase(l, ws, ys, 3, MEP_STORE, B.xq_h, 0, &ph)) return fail("q/k/v weights not on the K-quant TMA path");
           plan.push_back(ph); }
-        ph = base_phase(MPH_ATTN, l); ph.kc = L.kc; ph.vc = L.vc; plan.push_back(ph);
-        ph = base_phase(MPH_COMBINE, l); plan.push_back(ph);
+        ph = base_phase(MPH_ATTN, l); ph.kc = L.kc; ph.vc = L.vc;
+        if (fuse & MEGA_FUSE_COMBINE) { ph.fuse = MEGA_FUSE_COMBINE; ph.cnt = B.cnt_attn; }
+        plan.push_back(ph);
+        if (!(fuse & MEGA_FUSE_COMBINE)) { ph = base_phase(MPH_COMBINE, l); plan.push_back(ph); }
         { const MegaWeight* ws[1] = {&L.wo}; float* ys[1] = {nullptr};
           if (L.wo.rows != hidden || L.wo.cols != qdim) return fail("attn_output shape");
           if (!gemv_phase(l, ws, ys, 1, MEP_SLOT, B.xq_a, 0, &ph)) return fail("attn_output weight not on the K-quant TMA path");
@@ -812,8 +857,9 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
         { const MegaWeight* ws[2] = {&L.gate, &L.up}; float* ys[2] = {B.act, nullptr};
           if (L.gate.rows != inter || L.up.rows != inter || L.gate.cols != hidden) return fail("ffn_gate/up shape");
           if (!gemv_phase(l, ws, ys, 2, MEP_SWIGLU, B.xq_h, 0, &ph)) return fail("ffn_gate/up weights not on the K-quant TMA path");
+          if (fuse & MEGA_FUSE_QUANT) { ph.fuse = MEGA_FUSE_QUANT; ph.cnt = B.cnt_quant; ph.x = B.act; ph.n = inter; ph.xq_out = B.xq_i; }
           plan.push_back(ph); }
-        ph = base_phase(MPH_QUANT, l); ph.x = B.act; ph.n = inter; ph.xq_out = B.xq_i; plan.push_back(ph);
+        if (!(fuse & MEGA_FUSE_QUANT)) { ph = base_phase(MPH_QUANT, l); ph.x = B.act; ph.n = inter; ph.xq_out = B.xq_i; plan.push_back(ph); }
         { const MegaWeight* ws[1] = {&L.down}; float* ys[1] = {nullptr};
           if (L.down.rows != hidden || L.down.cols != inter) return fail("ffn_down shape");
           if (!gemv_phase(l, ws, ys, 1, MEP_SLOT, B.xq_i, 1, &ph)) return fail("ffn_down weight not on the K-quant TMA path");
@@ -945,7 +991,7 @@ DecodeMega::~DecodeMega() {
     for (size_t r = 0; r < peer_maps_.size(); r++)
         if (peer_maps_[r] && (int)r != tp_rank_) cudaIpcCloseMemHandle(peer_maps_[r]);
     for (void* p : {(void*)phases_dev_, (void*)hid_[0], (void*)hid_[1], (void*)q_, (void*)k_, (void*)v_, (void*)attn_, (void*)act_,
-                    (void*)scratch_, (void*)xq_h_, (void*)xq_a_, (void*)xq_i_, (void*)sync_, xchg_})
+                    (void*)scratch_, (void*)xq_h_, (void*)xq_a_, (void*)xq_i_, (void*)sync_, xchg_, (void*)cnt_quant_, (void*)cnt_attn_})
         if (p) cudaFree(p);
 }
 
@@ -975,9 +1021,13 @@ bool DecodeMega::build(const MegaModelView& mv) {
     NT_CUDA_CHECK(cudaMalloc(&xchg_, slot_floats * sizeof(float) + (size_t)tp_size_ * 32 * sizeof(unsigned)));
     NT_CUDA_CHECK(cudaMemset(xchg_, 0, slot_floats * sizeof(float) + (size_t)tp_size_ * 32 * sizeof(unsigned)));
 
+    cnt_quant_ = dalloc<unsigned>((size_t)inter_ / 32 + 1);
+    cnt_attn_ = dalloc<unsigned>((size_t)mv.nh + 1);
+    if (const char* f = getenv("NT_B200_MEGA_FUSE")) fuse_ = atoi(f);
     MegaBuffers B;
     B.hid[0] = hid_[0]; B.hid[1] = hid_[1]; B.q = q_; B.k = k_; B.v = v_; B.act = act_; B.xq_h = xq_h_; B.xq_a = xq_a_; B.xq_i = xq_i_;
-    if (!mega_make_plan(mv, B, grid_, split_fixed_, &plan_, &why_)) return false;
+    B.cnt_quant = cnt_quant_; B.cnt_attn = cnt_attn_;
+    if (!mega_make_plan(mv, B, grid_, split_fixed_, fuse_, &plan_, &why_)) return false;
     const std::string bad = mega_check_plan(plan_, grid_, tp_size_);
     if (!bad.empty()) return fail("plan check failed: " + bad);
     scratch_ = dalloc<float>((size_t)mv.nh * plan_.n_splits_max * (mv.hd + 2));

@@ -34,7 +34,7 @@ struct Rank {
     MegaBuffers B;
     MegaPlan plan;
     MegaParams P{};
-    HostBuf hid[2], q, k, v, attn, act, xq_h, xq_a, xq_i, scratch, sync, xchg, logits, step;
+    HostBuf hid[2], q, k, v, attn, act, xq_h, xq_a, xq_i, scratch, sync, xchg, logits, step, cnt_quant, cnt_attn;
     std::vector<HostBuf> kc, vc;
 
     void* keep(size_t bytes) {
@@ -85,7 +85,8 @@ MegaWeight shard(Sim& S, Rank& R, const std::string& name, int split, int rank) 
 
 extern "C" {
 
-void* mega_sim_create(const char* gguf_path, int max_seq, int tp_size, int grid, int split_fixed, int copy_delay, char* msg, size_t cap) {
+void* mega_sim_create(const char* gguf_path, int max_seq, int tp_size, int grid, int split_fixed, int fuse, int copy_delay, char* msg,
+                      size_t cap) {
     auto say = [&](const std::string& m) { if (msg && cap) snprintf(msg, cap, "%s", m.c_str()); };
     auto S = std::make_unique<Sim>();
     if (!S->file.open(gguf_path)) { say("cannot open gguf"); return nullptr; }
@@ -137,7 +138,9 @@ void* mega_sim_create(const char* gguf_path, int max_seq, int tp_size, int grid,
         B.v = R.v.as<float>(); B.act = R.act.as<float>(); B.xq_h = R.xq_h.as<int8_t>(); B.xq_a = R.xq_a.as<int8_t>();
         B.xq_i = R.xq_i.as<int8_t>();
         std::string why;
-        if (!mega_make_plan(mv, B, grid, split_fixed, &R.plan, &why)) { say("plan: " + why); return nullptr; }
+        R.cnt_quant.alloc((size_t)inter / 32 * 4 + 4); R.cnt_attn.alloc((size_t)nh * 4 + 4);
+        B.cnt_quant = R.cnt_quant.as<unsigned>(); B.cnt_attn = R.cnt_attn.as<unsigned>();
+        if (!mega_make_plan(mv, B, grid, split_fixed, fuse, &R.plan, &why)) { say("plan: " + why); return nullptr; }
         const std::string bad = mega_check_plan(R.plan, grid, tp_size);
         if (!bad.empty()) { say("plan check: " + bad); return nullptr; }
         R.scratch.alloc((size_t)nh * R.plan.n_splits_max * (hd + 2) * 4);

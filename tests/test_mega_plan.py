@@ -15,14 +15,14 @@ from ntransformer_b200.model_spec import LLAMA3_8B, LLAMA3_70B, TINY, LlamaConfi
 ORDER = ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down")
 
 
-def selftest(cfg: LlamaConfig, mix: str, tp_rank=0, tp_size=1, grid=148, split_fixed=0):
+def selftest(cfg: LlamaConfig, mix: str, tp_rank=0, tp_size=1, grid=148, split_fixed=0, fuse=0):
     big = cfg.n_layers >= 64
     dts = np.array([[int(tensor_dtype(mix, n, l, cfg.n_layers, big)) for n in ORDER] for l in range(cfg.n_layers)], dtype=np.int32)
     head = int(tensor_dtype(mix, "output", 0, cfg.n_layers, big))
     c = ModelConfigC(**cfg.dict())
     info = (C.c_int * 8)()
     msg = C.create_string_buffer(512)
-    rc = lib().nt_mega_plan_selftest(C.byref(c), tp_rank, tp_size, dts.ctypes.data_as(C.c_void_p), head, grid, split_fixed, info, msg, 512)
+    rc = lib().nt_mega_plan_selftest(C.byref(c), tp_rank, tp_size, dts.ctypes.data_as(C.c_void_p), head, grid, split_fixed, fuse, info, msg, 512)
     return rc, list(info), msg.value.decode()
 
 
@@ -77,3 +77,10 @@ def test_uncovered_shapes_are_rejected_not_mangled():
     assert rc == 1 and "attention" in msg
     rc, _, msg = selftest(LLAMA3_8B, "Q4_K_M", grid=8)                # hidden / 256 CTAs are needed by the norm phase
     assert rc == 1
+
+
+def test_fusion_flags_shorten_the_program():
+    for fuse, per_layer in ((0, 9), (1, 8), (2, 8), (3, 7)):
+        rc, info, msg = selftest(LLAMA3_70B, "Q4_K_M", 0, 8, fuse=fuse)
+        assert rc == 0, msg
+        assert info[1] == per_layer * LLAMA3_70B.n_layers and info[2] == 4 * LLAMA3_70B.n_layers + 1

@@ -31,7 +31,7 @@ def sim():
         pytest.fail("tests/cusim does not build:\n" + r.stderr[-3000:])
     lib = C.CDLL(str(SIM_DIR / "_sim" / "libmega_sim.so"))
     lib.mega_sim_create.restype = C.c_void_p
-    lib.mega_sim_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    lib.mega_sim_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
     lib.mega_sim_free.argtypes = [C.c_void_p]
     lib.mega_sim_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.mega_sim_read.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int]
@@ -43,10 +43,10 @@ def rel(a, b):
 
 
 class SimModel:
-    def __init__(self, lib, path, cfg, host, tp=1, grid=4, split_fixed=0, copy_delay=0):
+    def __init__(self, lib, path, cfg, host, tp=1, grid=4, split_fixed=0, copy_delay=0, fuse=0):
         self.lib, self.cfg = lib, cfg
         msg = C.create_string_buffer(512)
-        self.h = lib.mega_sim_create(str(path).encode(), cfg.max_seq_len, tp, grid, split_fixed, copy_delay, msg, 512)
+        self.h = lib.mega_sim_create(str(path).encode(), cfg.max_seq_len, tp, grid, split_fixed, fuse, copy_delay, msg, 512)
         assert self.h, msg.value.decode()
         emb, dt = host["token_embd.weight"]
         self.table = O.dequant_rows(dt, emb, cfg.vocab_size, cfg.hidden_size)
@@ -149,3 +149,27 @@ def test_ragged_rows_odd_grid_and_uneven_vocab_shards(sim, tmp_path):
     cfg = LlamaConfig(**{**TINY.dict(), "vocab_size": 510, "n_layers": 2})
     check_against_oracle(sim, tmp_path, cfg, "Q4_K", steps=3, grid=5)
     check_against_oracle(sim, tmp_path, cfg, "Q4_K", steps=2, tp=2, grid=3, copy_delay=3, tol=5e-4)
+
+
+@pytest.mark.parametrize("fuse", [1, 2, 3])
+def test_producer_side_fusions(sim, tmp_path, fuse):
+    """MEGA_FUSE_QUANT (1): the SwiGLU epilogue's last arriver quantises each 32-row block; MEGA_FUSE_COMBINE (2): the last
+    split unit of a head group merges the splits.  Same arithmetic, two barriers fewer per layer."""
+    check_against_oracle(sim, tmp_path, SMALL128, "Q4_K_M", steps=2, grid=8, copy_delay=4, fuse=fuse)
+    check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=4, tp=2, grid=3, fuse=fuse, tol=5e-4)
+
+
+def test_fused_combine_across_split_boundaries(sim, tmp_path):
+    cfg = LlamaConfig(**{**TINY.dict(), "n_layers": 1, "max_seq_len": 160})
+    path, host = make_case(tmp_path, cfg, "Q4_K")
+    om = O.Model(cfg.dict(), host)
+    m = SimModel(sim, path, cfg, host, grid=4, fuse=3)
+    rng = np.random.default_rng(1)
+    toks = [int(t) for t in rng.integers(3, cfg.vocab_size, size=132)]
+    for pos, t in enumerate(toks):
+        head = pos in (0, 63, 64, 65, 128, 131)
+        got = m.step(t, pos, with_head=head)
+        want = om.forward([t], pos)
+        if head:
+            assert rel(got, want) <= 2e-4, pos
+    m.close()
