@@ -144,8 +144,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- shared-memory state -------------------------------------------------------------------------------------------
 struct Shared {
-    MegaPhase cur;                                   // the phase being executed
-    MegaPhase nxt;                                   // the GEMV phase whose rings are being primed
+    MegaPhase ph[4];                                 // descriptor ring: phase i lives in ph[i & 3], prefetched two phases ahead
     uint64_t bars[MEGA_WARPS * MEGA_MAX_STAGES];     // one mbarrier per (warp, ring stage)
     float partial[2][MEGA_WARPS][2][RG];             // [buffer][warp][segment][row] chunk partial sums
     float red[32];
@@ -245,8 +244,8 @@ __device__ __forceinline__ void prime_rings(const MegaPhase& d, Producer& pr, ui
 }
 
 // ---- GEMV phase: consumer ------------------------------------------------------------------------------------------------
-__device__ void gemv_phase(const MegaParams& P, Shared& S, uint8_t* smem, Producer& pr, uint32_t& parity_bits, int warp, int lane) {
-    const MegaPhase& d = S.cur;
+__device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, uint8_t* smem, Producer& pr, uint32_t& parity_bits,
+                           int warp, int lane) {
     const int n_rounds = phase_rounds(d, (int)gridDim.x);
     if (warp >= d.warps) {                                   // idle warp of this phase: keep the CTA barriers balanced
         for (int round = 0; round < n_rounds; round++) __syncthreads();
@@ -374,8 +373,7 @@ __device__ __forceinline__ float residual_at(const MegaParams& P, const MegaPhas
     return v;
 }
 
-__device__ void norm_xq_phase(const MegaParams& P, Shared& S, int warp, int lane) {
-    const MegaPhase& d = S.cur;
+__device__ void norm_xq_phase(const MegaParams& P, Shared& S, const MegaPhase& d, int warp, int lane) {
     const int hidden = P.hidden;
     if ((int)blockIdx.x * 256 >= hidden) return;             // CTA-uniform
     float ss = 0.f;
@@ -607,8 +605,7 @@ __device__ void attend_unit(const MegaParams& P, Shared& S, const MegaPhase& d, 
 }
 
 template <int DPL, int GC>
-__device__ void attn_phase(const MegaParams& P, Shared& S, uint8_t* smem) {
-    const MegaPhase& d = S.cur;
+__device__ void attn_phase(const MegaParams& P, Shared& S, const MegaPhase& d, uint8_t* smem) {
     const int pos = P.step[1], ctx = pos + 1;
     const int n_groups = P.nh / GC, ratio = P.nh / P.nkv;
     const SplitRule sr = split_rule(P, ctx, n_groups);
@@ -671,37 +668,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_c
         for (int s = 0; s < MEGA_MAX_STAGES; s++) mbar_init(S.bars + warp * MEGA_MAX_STAGES + s, 1);
         mbar_fence_init();
     }
-    if (P.first_gemv >= 0 && P.first_gemv < P.n_phases) load_phase(&S.nxt, P.phases + P.first_gemv);
+    // Descriptor ring: phase i is read from S.ph[i & 3].  Descriptors 0 and 1 are loaded here, descriptor i + 2 at the start
+    // of phase i (its slot held phase i - 2, which every thread has left), so no phase waits for its own descriptor and the
+    // priming step at the end of phase i (target i + 1 or i + 2, host-checked) finds its descriptor in shared memory.
+    load_phase(&S.ph[0], P.phases);
+    if (P.n_phases > 1) load_phase(&S.ph[1], P.phases + 1);
     __syncthreads();
     // Weights do not depend on anything computed in this kernel: start streaming the first GEMV's rows right away.
-    if (P.first_gemv >= 0 && P.first_gemv < P.n_phases) prime_rings(S.nxt, pr, smem, S.bars, warp, lane);
+    if (P.first_gemv >= 0 && P.first_gemv < P.n_phases) prime_rings(S.ph[P.first_gemv & 3], pr, smem, S.bars, warp, lane);
 
     for (int i = 0; i < P.n_phases; i++) {
-        __syncthreads();                                     // previous phase is done with S.cur
-        load_phase(&S.cur, P.phases + i);
-        __syncthreads();
-        const int kind = S.cur.kind;
+        if (i + 2 < P.n_phases) load_phase(&S.ph[(i + 2) & 3], P.phases + i + 2);
+        const MegaPhase& d = S.ph[i & 3];
+        const int kind = d.kind;
         if (kind == MPH_GEMV) {
-            gemv_phase(P, S, smem, pr, parity_bits, warp, lane);
+            gemv_phase(P, S, d, smem, pr, parity_bits, warp, lane);
         } else if (kind == MPH_NORM_XQ) {
-            norm_xq_phase(P, S, warp, lane);
+            norm_xq_phase(P, S, d, warp, lane);
         } else if (kind == MPH_QUANT) {
-            quant_phase(S.cur, warp, lane);
+            quant_phase(d, warp, lane);
         } else if (kind == MPH_ATTN) {
-            if (P.hd == 128 && P.gc == 8) attn_phase<4, 8>(P, S, smem);
-            else if (P.hd == 128 && P.gc == 4) attn_phase<4, 4>(P, S, smem);
-            else attn_phase<2, 4>(P, S, smem);               // hd 64, 4 query heads per KV head (host-checked)
+            if (P.hd == 128 && P.gc == 8) attn_phase<4, 8>(P, S, d, smem);
+            else if (P.hd == 128 && P.gc == 4) attn_phase<4, 4>(P, S, d, smem);
+            else attn_phase<2, 4>(P, S, d, smem);            // hd 64, 4 query heads per KV head (host-checked)
         } else {
             combine_phase(P);
         }
-        const int prime = S.cur.prime, barrier = S.cur.barrier;
+        const int prime = d.prime;
         if (prime >= 0 && prime < P.n_phases) {
-            __syncthreads();                                 // every warp is done with the ring area and with S.nxt
-            load_phase(&S.nxt, P.phases + prime);
-            __syncthreads();
-            prime_rings(S.nxt, pr, smem, S.bars, warp, lane);
+            __syncthreads();                                 // every warp is done with the ring area; descriptor i + 2 is visible
+            prime_rings(S.ph[prime & 3], pr, smem, S.bars, warp, lane);
         }
-        mega_barrier(P, barrier, st);
+        mega_barrier(P, d.barrier, st);
     }
     if (P.tp_size > 1 && blockIdx.x == 0 && threadIdx.x == 0) P.sync[96] = st.xchg_base + st.xchg_idx;
 }
@@ -947,6 +945,7 @@ std::string mega_check_plan(const MegaPlan& pl, int grid, int tp_size) {
     const std::vector<MegaPhase>& ph = pl.phases;
     const int n = (int)ph.size();
     if (n == 0 || pl.n_body <= 0 || pl.n_body > n) return "empty plan";
+    if (pl.first_gemv > 1) return "first GEMV phase beyond the initially loaded descriptors (0, 1)";
     int primed = pl.first_gemv;                  // GEMV phase whose rings are currently primed, -1 none
     const float* stream = nullptr;               // buffer that holds the residual stream
     int pending = -1;                            // parity of the slots waiting to be added
@@ -975,6 +974,7 @@ std::string mega_check_plan(const MegaPlan& pl, int grid, int tp_size) {
         }
         if (d.prime >= 0) {
             if (d.prime <= i || d.prime >= n || ph[(size_t)d.prime].kind != MPH_GEMV) return "prime target is not a later GEMV phase";
+            if (d.prime > i + 2) return "prime target beyond the descriptor prefetch window (i + 2)";
             if (primed >= 0) return "rings primed twice";
             for (int j = i + 1; j < d.prime; j++) if (ph[(size_t)j].kind == MPH_ATTN || ph[(size_t)j].kind == MPH_GEMV) return "phases between a prime and its GEMV touch the rings";
             primed = d.prime;
