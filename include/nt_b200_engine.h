@@ -64,7 +64,7 @@ long long nt_model_debug_read(nt_model_t m, const char* name, float* out_host, s
 
 /* Host-only self-test of the persistent kernel's plan builder: builds the per-token program for one tensor-parallel rank
  * of a model of shape *cfg (layer_dtypes: n_layers x 7 nt::DType values in the order q,k,v,o,gate,up,down) on a grid of
- * `grid` CTAs (fuse: producer-side fusion bits, 1 = activation quantiser, 2 = split combine) and replays the schedule of every GEMV phase on the CPU.  info (8 ints, optional): phases, body phases, GEMV
+ * `grid` CTAs (fuse: producer-side fusion bits, 1 = activation quantiser, 2 = split combine, 4 = residual add + next norm, single rank only) and replays the schedule of every GEMV phase on the CPU.  info (8 ints, optional): phases, body phases, GEMV
  * phases, min warps, min ring stages, exchanges, attention splits, keys per split.  Returns 0 ok, 1 shape not covered,
  * 2 inconsistent plan (a bug), -1 bad arguments; msg receives the reason. */
 int  nt_mega_plan_selftest(const nt_model_config* cfg, int tp_rank, int tp_size, const int* layer_dtypes, int head_dtype,

@@ -152,6 +152,7 @@ int nt_mega_plan_selftest(const nt_model_config* c, int tp_rank, int tp_size, co
     B.xq_h = static_cast<int8_t*>(place(xq_bytes(mv.hidden))); B.xq_a = static_cast<int8_t*>(place(xq_bytes(qdim)));
     B.xq_i = static_cast<int8_t*>(place(xq_bytes(mv.inter)));
     B.cnt_quant = static_cast<unsigned*>(place((size_t)mv.inter / 32 * 4 + 4)); B.cnt_attn = static_cast<unsigned*>(place((size_t)mv.nh * 4 + 4));
+    B.cnt_norm = static_cast<unsigned*>(place((size_t)mv.hidden / 32 * 4 + 4)); B.ssq = static_cast<float*>(place((size_t)mv.hidden / 32 * 4 + 4));
     MegaPlan pl;
     std::string why;
     if (!mega_make_plan(mv, B, grid, split_fixed, fuse, &pl, &why)) { say(why); return 1; }

@@ -45,7 +45,7 @@ constexpr int MEGA_SYNC_WORDS = 4 * 32;     // counter, go, abort, exchange sequ
 enum MegaPhaseKind : int { MPH_NORM_XQ = 0, MPH_QUANT = 1, MPH_GEMV = 2, MPH_ATTN = 3, MPH_COMBINE = 4 };
 enum MegaBarrierKind : int { MBAR_NONE = 0, MBAR_GRID = 1, MBAR_EXCHANGE = 2 };
 enum MegaEpilogue : int { MEP_STORE = 0, MEP_SWIGLU = 2, MEP_SLOT = 3 };
-enum MegaFuse : int { MEGA_FUSE_QUANT = 1, MEGA_FUSE_COMBINE = 2 };
+enum MegaFuse : int { MEGA_FUSE_QUANT = 1, MEGA_FUSE_COMBINE = 2, MEGA_FUSE_NORM = 4 /* single rank only */ };
 
 struct MegaMat {
     const uint8_t* W;
@@ -86,7 +86,14 @@ struct MegaPhase {
     //                      (x = the activation vector, n = its length) => no MPH_QUANT phase, one barrier less;
     //   MPH_ATTN:          the unit that completes the last split of a head group merges the splits and emits xq_a
     //                      => no MPH_COMBINE phase, one barrier less.
+    //   MPH_GEMV + slots, one rank only (MEGA_FUSE_NORM): the warp that completes a 32-row block adds it to the residual
+    //                      stream (hid_in + slot -> hid_out), stores the block's sum of squares in ssq_out and quantises
+    //                      h * norm_w (the NEXT norm's weights, without the 1/rms factor) into xq_out; the consuming GEMV
+    //                      (ssq_in != null) multiplies its results by rsqrt(sum(ssq_in) / hidden + eps)
+    //                      => no MPH_NORM_XQ phase, two barriers less per layer.
     unsigned* cnt;
+    float* ssq_out;
+    const float* ssq_in;
     int fuse;
     int pad_;
 };
@@ -135,6 +142,8 @@ struct MegaBuffers {
     int8_t *xq_h = nullptr, *xq_a = nullptr, *xq_i = nullptr;
     unsigned* cnt_quant = nullptr;      // inter / 32 counters (MEGA_FUSE_QUANT)
     unsigned* cnt_attn = nullptr;       // one counter per attention head group (MEGA_FUSE_COMBINE)
+    unsigned* cnt_norm = nullptr;       // hidden / 32 counters (MEGA_FUSE_NORM)
+    float* ssq = nullptr;               // hidden / 32 per-block sums of squares of the residual stream (MEGA_FUSE_NORM)
 };
 struct MegaPlan {
     std::vector<MegaPhase> phases;
@@ -197,7 +206,8 @@ private:
     std::vector<void*> peer_maps_;
     int hidden_ = 0, nh_ = 0, hd_ = 0, inter_ = 0, tp_rank_ = 0, tp_size_ = 1, grid_ = 0;
     int split_fixed_ = 0, fuse_ = 0;
-    unsigned *cnt_quant_ = nullptr, *cnt_attn_ = nullptr;
+    unsigned *cnt_quant_ = nullptr, *cnt_attn_ = nullptr, *cnt_norm_ = nullptr;
+    float* ssq_ = nullptr;
     bool peers_ready_ = false;
     std::string why_;
 };

@@ -247,6 +247,19 @@ __device__ __forceinline__ void prime_rings(const MegaPhase& d, Producer& pr, ui
 __device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, uint8_t* smem, Producer& pr, uint32_t& parity_bits,
                            int warp, int lane) {
     const int n_rounds = phase_rounds(d, (int)gridDim.x);
+    float rms_inv = 1.0f;
+    if (d.ssq_in) {
+        // MEGA_FUSE_NORM consumer: the activations were quantised as h * norm_w; the missing 1/rms factor is a scalar of the
+        // whole vector and is applied to the results.  Every CTA adds the per-block sums of squares in the same order.
+        float part = 0.f;
+        for (int b = threadIdx.x; b < P.hidden / 32; b += NTHREADS) part += __ldcg(d.ssq_in + b);
+        part = warp_sum(part);
+        if (lane == 0) S.red[warp] = part;
+        __syncthreads();
+        float t = (lane < MEGA_WARPS) ? S.red[lane] : 0.f;
+        t = warp_sum(t);
+        rms_inv = rsqrtf(t / P.hidden + P.eps);
+    }
     if (warp >= d.warps) {                                   // idle warp of this phase: keep the CTA barriers balanced
         for (int round = 0; round < n_rounds; round++) __syncthreads();
         return;
@@ -324,6 +337,7 @@ __device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
                     v0 += S.partial[buf][gsub * NC + c][0][lane];
                     if (n_seg == 2) v1 += S.partial[buf][gsub * NC + c][1][lane];
                 }
+                v0 *= rms_inv; v1 *= rms_inv;                // 1.0 unless the input came from a fused norm
                 const int row = gl * RG + lane;
                 if (row < m.out) {
                     if (d.epilogue == MEP_SWIGLU) {
@@ -354,6 +368,28 @@ __device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
                     const float v = (e < d.n) ? __ldcg(d.x + e) : 0.f;
                     quantize_block32(v, block, lane, d.xq_out, d.n);
                     if (lane == 0) d.cnt[block] = 0;         // ready for the next layer
+                }
+            }
+            if (d.epilogue == MEP_SLOT && (d.fuse & MEGA_FUSE_NORM)) {
+                // Single rank: the slot rows ARE the full projection.  Last arriver of a 32-row block: residual add, the block's
+                // sum of squares, and the next norm's quantiser input h * w (1/rms is applied by the consumer).
+                __threadfence();
+                __syncwarp();
+                const int block = gl >> 3;
+                const int groups_in_block = min(8, m.groups - block * 8);
+                unsigned prev = 0;
+                if (lane == 0) prev = atomicAdd(d.cnt + block, 1u);
+                prev = __shfl_sync(0xFFFFFFFFu, prev, 0);
+                if ((int)prev == groups_in_block - 1) {
+                    __threadfence();
+                    const int e = block * 32 + lane;
+                    const float* sl = P.slots[P.tp_rank] + (size_t)d.slot_parity * P.tp_size * (size_t)P.hidden;
+                    const float hval = __ldcg(d.hid_in + e) + __ldcg(sl + e);
+                    d.hid_out[e] = hval;
+                    const float ss = warp_sum(hval * hval);
+                    if (lane == 0) d.ssq_out[block] = ss;
+                    quantize_block32(hval * d.norm_w[e], block, lane, d.xq_out, P.hidden);
+                    if (lane == 0) d.cnt[block] = 0;
                 }
             }
         }
@@ -762,6 +798,7 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
     pl.gc = gc;
     if ((fuse & MEGA_FUSE_QUANT) && !B.cnt_quant) fuse &= ~MEGA_FUSE_QUANT;
     if ((fuse & MEGA_FUSE_COMBINE) && !B.cnt_attn) fuse &= ~MEGA_FUSE_COMBINE;
+    if ((fuse & MEGA_FUSE_NORM) && (!B.cnt_norm || !B.ssq || mv.tp_size != 1 || hidden % 32 != 0)) fuse &= ~MEGA_FUSE_NORM;
     pl.fuse = fuse;
     const int qdim = mv.nh * mv.hd;
 
@@ -834,14 +871,26 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
         return ph;
     };
     std::vector<MegaPhase>& plan = pl.phases;
+    const bool fnorm = (fuse & MEGA_FUSE_NORM) != 0;
+    bool deferred = false;       // the current xq_h was produced by a fused norm: its consumers apply 1/rms themselves
+    // fold "residual add + next norm" into a slot-epilogue GEMV phase (MEGA_FUSE_NORM, single rank)
+    auto fold_norm = [&](MegaPhase& ph, const float* next_norm_w) {
+        ph.fuse |= MEGA_FUSE_NORM;
+        ph.norm_w = next_norm_w; ph.hid_in = B.hid[cur]; ph.hid_out = B.hid[cur ^ 1]; cur ^= 1;
+        ph.xq_out = B.xq_h; ph.cnt = B.cnt_norm; ph.ssq_out = B.ssq;
+        deferred = true;
+    };
     for (int l = 0; l < mv.n_layers; l++) {
         const MegaLayerView& L = mv.layers[(size_t)l];
         if (!L.attn_norm || !L.ffn_norm) return fail("missing norm weights");
-        plan.push_back(norm_phase(l, L.attn_norm));
+        const float* next_attn_norm = (l + 1 < mv.n_layers) ? mv.layers[(size_t)l + 1].attn_norm : mv.out_norm;
+        if (fnorm && !next_attn_norm) return fail("missing norm weights");
+        if (!fnorm || l == 0) plan.push_back(norm_phase(l, L.attn_norm));
         MegaPhase ph;
         { const MegaWeight* ws[3] = {&L.wq, &L.wk, &L.wv}; float* ys[3] = {B.q, B.k, B.v};
           if (L.wq.rows != qdim || L.wk.rows != mv.nkv * mv.hd || L.wv.rows != mv.nkv * mv.hd || L.wq.cols != hidden) return fail("attn_q/k/v shape");
           if (!gemv_phase(l, ws, ys, 3, MEP_STORE, B.xq_h, 0, &ph)) return fail("q/k/v weights not on the K-quant TMA path");
+          if (deferred) ph.ssq_in = B.ssq;
           plan.push_back(ph); }
         ph = base_phase(MPH_ATTN, l); ph.kc = L.kc; ph.vc = L.vc;
         if (fuse & MEGA_FUSE_COMBINE) { ph.fuse = MEGA_FUSE_COMBINE; ph.cnt = B.cnt_attn; }
@@ -850,27 +899,33 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
         { const MegaWeight* ws[1] = {&L.wo}; float* ys[1] = {nullptr};
           if (L.wo.rows != hidden || L.wo.cols != qdim) return fail("attn_output shape");
           if (!gemv_phase(l, ws, ys, 1, MEP_SLOT, B.xq_a, 0, &ph)) return fail("attn_output weight not on the K-quant TMA path");
-          ph.barrier = MBAR_EXCHANGE; plan.push_back(ph); pending = 0; }
-        plan.push_back(norm_phase(l, L.ffn_norm));
+          ph.barrier = MBAR_EXCHANGE;
+          if (fnorm) fold_norm(ph, L.ffn_norm); else pending = 0;
+          plan.push_back(ph); }
+        if (!fnorm) plan.push_back(norm_phase(l, L.ffn_norm));
         { const MegaWeight* ws[2] = {&L.gate, &L.up}; float* ys[2] = {B.act, nullptr};
           if (L.gate.rows != inter || L.up.rows != inter || L.gate.cols != hidden) return fail("ffn_gate/up shape");
           if (!gemv_phase(l, ws, ys, 2, MEP_SWIGLU, B.xq_h, 0, &ph)) return fail("ffn_gate/up weights not on the K-quant TMA path");
           if (fuse & MEGA_FUSE_QUANT) { ph.fuse = MEGA_FUSE_QUANT; ph.cnt = B.cnt_quant; ph.x = B.act; ph.n = inter; ph.xq_out = B.xq_i; }
+          if (deferred) ph.ssq_in = B.ssq;
           plan.push_back(ph); }
         if (!(fuse & MEGA_FUSE_QUANT)) { ph = base_phase(MPH_QUANT, l); ph.x = B.act; ph.n = inter; ph.xq_out = B.xq_i; plan.push_back(ph); }
         { const MegaWeight* ws[1] = {&L.down}; float* ys[1] = {nullptr};
           if (L.down.rows != hidden || L.down.cols != inter) return fail("ffn_down shape");
           if (!gemv_phase(l, ws, ys, 1, MEP_SLOT, B.xq_i, 1, &ph)) return fail("ffn_down weight not on the K-quant TMA path");
-          ph.barrier = MBAR_EXCHANGE; plan.push_back(ph); pending = 1; }
+          ph.barrier = MBAR_EXCHANGE;
+          if (fnorm) fold_norm(ph, next_attn_norm); else pending = 1;
+          plan.push_back(ph); }
     }
     pl.n_body = (int)plan.size();
     if (!mv.out_norm || !mv.logits) return fail("missing output norm / logits buffer");
-    plan.push_back(norm_phase(mv.n_layers, mv.out_norm));
+    if (!fnorm) plan.push_back(norm_phase(mv.n_layers, mv.out_norm));
     if (mv.head.rows > 0) {
         MegaPhase ph;
         const MegaWeight* ws[1] = {&mv.head}; float* ys[1] = {mv.logits};
         if (mv.head.cols != hidden) return fail("output.weight shape");
         if (!gemv_phase(mv.n_layers, ws, ys, 1, MEP_STORE, B.xq_h, 0, &ph)) return fail("output.weight not on the K-quant TMA path");
+        if (deferred) ph.ssq_in = B.ssq;
         ph.barrier = MBAR_NONE;
         plan.push_back(ph);
     } else {
@@ -949,19 +1004,33 @@ std::string mega_check_plan(const MegaPlan& pl, int grid, int tp_size) {
     int primed = pl.first_gemv;                  // GEMV phase whose rings are currently primed, -1 none
     const float* stream = nullptr;               // buffer that holds the residual stream
     int pending = -1;                            // parity of the slots waiting to be added
+    bool deferred = false;                       // the latest norm output lacks its 1/rms factor (fused norm)
+    const int8_t* xq_norm = nullptr;             // where the latest norm wrote its quantised output
     for (int i = 0; i < n; i++) {
         const MegaPhase& d = ph[(size_t)i];
         if (i + 1 < n && d.barrier == MBAR_NONE) { snprintf(msg, sizeof(msg), "phase %d: no barrier before phase %d", i, i + 1); return msg; }
         if (d.kind == MPH_GEMV) {
             if (primed != i) { snprintf(msg, sizeof(msg), "GEMV phase %d starts with rings primed for %d", i, primed); return msg; }
             primed = -1;
+            // the 1/rms factor of a norm is applied exactly once: by the norm phase itself, or by the consumers of a fused norm
+            if ((d.ssq_in != nullptr) != (d.xq == xq_norm && deferred)) { snprintf(msg, sizeof(msg), "GEMV phase %d: 1/rms factor applied twice or never", i); return msg; }
             const std::string e = mega_check_gemv_schedule(d, grid, MEGA_DYN_SMEM);
             if (!e.empty()) { snprintf(msg, sizeof(msg), "GEMV phase %d: %s", i, e.c_str()); return msg; }
             if (d.epilogue == MEP_SLOT) {
                 if (d.barrier != MBAR_EXCHANGE) return "slot epilogue without an exchange barrier";
                 if (pending >= 0) return "two exchanges without a norm phase in between";
-                pending = d.slot_parity;
+                if (d.fuse & MEGA_FUSE_NORM) {                 // the epilogue adds the slots to the residual stream itself
+                    if (tp_size != 1) return "fused norm under tensor parallelism";
+                    if (stream && d.hid_in != stream) return "fused norm does not read the current residual stream";
+                    if (!d.hid_out || d.hid_out == d.hid_in || !d.ssq_out || !d.cnt || !d.norm_w || !d.xq_out) return "fused norm fields";
+                    stream = d.hid_out;
+                    xq_norm = d.xq_out;
+                    deferred = true;
+                } else {
+                    pending = d.slot_parity;
+                }
             } else if (d.barrier == MBAR_EXCHANGE) return "exchange barrier after a non-slot phase";
+
         } else if (d.kind == MPH_ATTN) {
             if (primed >= 0) { snprintf(msg, sizeof(msg), "attention phase %d would overwrite rings primed for %d", i, primed); return msg; }
         } else if (d.kind == MPH_NORM_XQ) {
@@ -971,6 +1040,8 @@ std::string mega_check_plan(const MegaPlan& pl, int grid, int tp_size) {
             if (d.hid_out == d.hid_in) return "residual stream updated in place";
             stream = d.hid_out ? d.hid_out : d.hid_in;
             pending = -1;
+            xq_norm = d.xq_out;
+            deferred = false;
         }
         if (d.prime >= 0) {
             if (d.prime <= i || d.prime >= n || ph[(size_t)d.prime].kind != MPH_GEMV) return "prime target is not a later GEMV phase";
@@ -991,7 +1062,7 @@ DecodeMega::~DecodeMega() {
     for (size_t r = 0; r < peer_maps_.size(); r++)
         if (peer_maps_[r] && (int)r != tp_rank_) cudaIpcCloseMemHandle(peer_maps_[r]);
     for (void* p : {(void*)phases_dev_, (void*)hid_[0], (void*)hid_[1], (void*)q_, (void*)k_, (void*)v_, (void*)attn_, (void*)act_,
-                    (void*)scratch_, (void*)xq_h_, (void*)xq_a_, (void*)xq_i_, (void*)sync_, xchg_, (void*)cnt_quant_, (void*)cnt_attn_})
+                    (void*)scratch_, (void*)xq_h_, (void*)xq_a_, (void*)xq_i_, (void*)sync_, xchg_, (void*)cnt_quant_, (void*)cnt_attn_, (void*)cnt_norm_, (void*)ssq_})
         if (p) cudaFree(p);
 }
 
@@ -1023,10 +1094,12 @@ bool DecodeMega::build(const MegaModelView& mv) {
 
     cnt_quant_ = dalloc<unsigned>((size_t)inter_ / 32 + 1);
     cnt_attn_ = dalloc<unsigned>((size_t)mv.nh + 1);
+    cnt_norm_ = dalloc<unsigned>((size_t)hidden_ / 32 + 1);
+    ssq_ = dalloc<float>((size_t)hidden_ / 32 + 1);
     if (const char* f = getenv("NT_B200_MEGA_FUSE")) fuse_ = atoi(f);
     MegaBuffers B;
     B.hid[0] = hid_[0]; B.hid[1] = hid_[1]; B.q = q_; B.k = k_; B.v = v_; B.act = act_; B.xq_h = xq_h_; B.xq_a = xq_a_; B.xq_i = xq_i_;
-    B.cnt_quant = cnt_quant_; B.cnt_attn = cnt_attn_;
+    B.cnt_quant = cnt_quant_; B.cnt_attn = cnt_attn_; B.cnt_norm = cnt_norm_; B.ssq = ssq_;
     if (!mega_make_plan(mv, B, grid_, split_fixed_, fuse_, &plan_, &why_)) return false;
     const std::string bad = mega_check_plan(plan_, grid_, tp_size_);
     if (!bad.empty()) return fail("plan check failed: " + bad);

@@ -34,7 +34,7 @@ struct Rank {
     MegaBuffers B;
     MegaPlan plan;
     MegaParams P{};
-    HostBuf hid[2], q, k, v, attn, act, xq_h, xq_a, xq_i, scratch, sync, xchg, logits, step, cnt_quant, cnt_attn;
+    HostBuf hid[2], q, k, v, attn, act, xq_h, xq_a, xq_i, scratch, sync, xchg, logits, step, cnt_quant, cnt_attn, cnt_norm, ssq;
     std::vector<HostBuf> kc, vc;
 
     void* keep(size_t bytes) {
@@ -140,6 +140,8 @@ void* mega_sim_create(const char* gguf_path, int max_seq, int tp_size, int grid,
         std::string why;
         R.cnt_quant.alloc((size_t)inter / 32 * 4 + 4); R.cnt_attn.alloc((size_t)nh * 4 + 4);
         B.cnt_quant = R.cnt_quant.as<unsigned>(); B.cnt_attn = R.cnt_attn.as<unsigned>();
+        R.cnt_norm.alloc((size_t)c.hidden_size / 32 * 4 + 4); R.ssq.alloc((size_t)c.hidden_size / 32 * 4 + 4);
+        B.cnt_norm = R.cnt_norm.as<unsigned>(); B.ssq = R.ssq.as<float>();
         if (!mega_make_plan(mv, B, grid, split_fixed, fuse, &R.plan, &why)) { say("plan: " + why); return nullptr; }
         const std::string bad = mega_check_plan(R.plan, grid, tp_size);
         if (!bad.empty()) { say("plan check: " + bad); return nullptr; }

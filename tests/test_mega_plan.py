@@ -80,7 +80,13 @@ def test_uncovered_shapes_are_rejected_not_mangled():
 
 
 def test_fusion_flags_shorten_the_program():
-    for fuse, per_layer in ((0, 9), (1, 8), (2, 8), (3, 7)):
+    for fuse, per_layer in ((0, 9), (1, 8), (2, 8), (3, 7), (7, 7)):          # bit 4 is ignored under tensor parallelism
         rc, info, msg = selftest(LLAMA3_70B, "Q4_K_M", 0, 8, fuse=fuse)
         assert rc == 0, msg
         assert info[1] == per_layer * LLAMA3_70B.n_layers and info[2] == 4 * LLAMA3_70B.n_layers + 1
+    L = LLAMA3_70B.n_layers
+    rc, info, msg = selftest(LLAMA3_70B, "Q4_K_M", fuse=7)                    # single rank: 5 phases per layer + the first norm
+    assert rc == 0, msg
+    assert info[1] == 5 * L + 1 and info[0] == info[1] + 1 and info[2] == 4 * L + 1
+    rc, info, msg = selftest(LLAMA3_8B, "Q4_K_M", fuse=4)
+    assert rc == 0 and info[1] == 7 * LLAMA3_8B.n_layers + 1, msg

@@ -173,3 +173,14 @@ def test_fused_combine_across_split_boundaries(sim, tmp_path):
         if head:
             assert rel(got, want) <= 2e-4, pos
     m.close()
+
+
+@pytest.mark.parametrize("fuse", [4, 7])
+def test_fused_residual_and_norm_single_rank(sim, tmp_path, fuse):
+    """MEGA_FUSE_NORM (4): at one rank the o-proj / down-proj epilogue's last arriver adds the block to the residual stream,
+    stores its sum of squares and quantises h * w for the next norm; the consuming GEMV applies 1/rms to its results.
+    5 phases per layer with all three fusions.  Mathematically equal, not bit-equal, to the separate norm phase."""
+    check_against_oracle(sim, tmp_path, SMALL128, "Q4_K_M", steps=3, grid=8, copy_delay=4, fuse=fuse)
+    check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=8, grid=3, fuse=fuse)
+    # under tensor parallelism the flag is ignored (the norm needs every rank's partial rows): still correct
+    check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=2, tp=2, grid=3, fuse=fuse, tol=5e-4)
