@@ -116,6 +116,27 @@ def test_adaptive_split_vs_oracle_and_graph_ids(case):
         assert rel(got[i + 1], lo) <= 1e-3
 
 
+@pytest.mark.parametrize("fuse", [3, 7])
+def test_producer_side_fusions_keep_the_greedy_ids(case, monkeypatch, fuse):
+    """NT_B200_MEGA_FUSE: 1 activation quantiser, 2 split combine (same arithmetic as the separate phases), 4 residual add +
+    next norm at one rank (1/rms applied by the consumer: equal up to round-off, not bit-equal)."""
+    cfg, mix, path, _ = case
+    prompt = [cfg.bos_token_id, 33, 8, 120]
+    g = Model.load(path, cfg.max_seq_len)
+    want, ids_g = run(g, prompt, 70)
+    g.close()
+    monkeypatch.setenv("NT_B200_MEGA_FUSE", str(fuse))
+    m = Model.load(path, cfg.max_seq_len)
+    m.use_megakernel(True)
+    got, ids_m = run(m, prompt, 70)
+    assert m.megakernel_active
+    per_layer = {3: 7, 7: 5}[fuse]
+    assert len(m.megakernel_plan()) == per_layer * cfg.n_layers + 2      # + first/final norm and the LM head
+    m.close()
+    assert max(rel(a, b) for a, b in zip(got, want)) <= 1e-3
+    assert ids_m == ids_g
+
+
 def test_uncovered_model_keeps_the_graph_path(tmp_path):
     tensors = synthetic_tensors_np(TINY, "F16", seed=3)
     path = tmp_path / "f16.gguf"
