@@ -49,6 +49,15 @@ void nt_model_set_prefill_min_tokens(nt_model_t m, int n);
 /* algorithmic bytes read per decoded token by this rank at context length ctx */
 unsigned long long nt_model_bytes_per_token(nt_model_t m, int ctx);
 
+/* Samples the next token from the last logits ON THE GPU: repeat penalty over recent_window (host ids, oldest first; applied in
+ * place to the device logits), temperature, top-k, top-p and the inverse-CDF draw with the uniform variate r — the steps of the
+ * reference's Sampler::apply_repeat_penalty + Sampler::sample (src/inference/sampler.cpp:30-117) in the same order.  Returns the
+ * token id, or -1 when the settings are not covered (temperature <= 0, top_k <= 0, top_k > 1024, top_k >= vocab): sample on the
+ * host then (nt_sample_token).  nt_sampler_uniform(seed, i) is the (i+1)-th variate of the reference's mt19937 stream. */
+int   nt_model_sample(nt_model_t m, float temperature, int top_k, float top_p, float repeat_penalty, const int* recent_window,
+                      int n_window, float r);
+float nt_sampler_uniform(uint64_t seed, int n_draws_before);
+
 /* Opt-in: run each decoded token as ONE persistent kernel (all layers; grid barriers and, under tensor parallelism,
  * NVLink peer-memory exchanges inside the kernel) instead of the CUDA graph of fused launches.  Same maths, same KV
  * cache.  Models whose shapes/dtypes the kernel does not cover keep the graph path (a note goes to stderr).

@@ -37,6 +37,8 @@ ENGINE_SIGNATURES = {
     "nt_model_use_graph": (None, [_vp, _i]),
     "nt_model_set_prefill_min_tokens": (None, [_vp, _i]),
     "nt_model_bytes_per_token": (C.c_ulonglong, [_vp, _i]),
+    "nt_model_sample": (_i, [_vp, _f, _i, _f, _f, _vp, _i, _f]),
+    "nt_sampler_uniform": (_f, [C.c_uint64, _i]),
     "nt_model_use_megakernel": (None, [_vp, _i]),
     "nt_model_megakernel_active": (_i, [_vp]),
     "nt_model_megakernel_plan": (_i, [_vp, _vp, _i]),

@@ -87,6 +87,18 @@ void nt_model_clear_kv(nt_model_t m) { if (m) H(m)->model.clear_kv(); }
 void nt_model_set_prefill_min_tokens(nt_model_t m, int n) { if (m) H(m)->model.set_prefill_min_tokens(n); }
 void nt_model_use_graph(nt_model_t m, int on) { if (m) H(m)->model.set_use_graph(on != 0); }
 unsigned long long nt_model_bytes_per_token(nt_model_t m, int ctx) { return m ? H(m)->model.bytes_per_token(ctx) : 0; }
+int nt_model_sample(nt_model_t m, float temperature, int top_k, float top_p, float repeat_penalty, const int* recent_window, int n_window,
+                    float r) {
+    return m ? H(m)->model.sample_last(temperature, top_k, top_p, repeat_penalty, recent_window, n_window, r) : -1;
+}
+float nt_sampler_uniform(uint64_t seed, int n_draws_before) {
+    SamplerConfig sc;
+    sc.seed = seed;
+    Sampler s;
+    s.init(sc);
+    for (int i = 0; i < n_draws_before; i++) s.draw();
+    return s.draw();
+}
 void nt_model_use_megakernel(nt_model_t m, int on) { if (m) H(m)->model.set_use_megakernel(on != 0); }
 int nt_model_megakernel_active(nt_model_t m) { return (m && H(m)->model.megakernel_active()) ? 1 : 0; }
 int nt_model_megakernel_plan(nt_model_t m, int* kinds, int cap) {

@@ -1,5 +1,7 @@
 #include "engine.h"
+#include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <iostream>
 
 namespace nt { namespace b200 {
@@ -27,8 +29,16 @@ std::string Engine::generate(const std::string& prompt, const GenerateConfig& cf
     std::vector<float> logits((size_t)vocab);
     // Greedy without a repeat penalty needs no logits on the host: argmax runs on the GPU (4 B D2H instead of 513 KB).
     const bool gpu_greedy = cfg.temperature <= 0.0f && cfg.repeat_penalty <= 1.0f;
+    // Opt-in: penalty + top-k/top-p sampling on the GPU with the host's mt19937 stream (4 B D2H per token, csrc/sample.cu).
+    const bool gpu_sample = (cfg.gpu_sampler || getenv("NT_B200_GPU_SAMPLER")) && sample_topk_supported(vocab, cfg.temperature, cfg.top_k);
     auto next_from = [&](float* dev_logits) {
         if (gpu_greedy) return model_.argmax_last();
+        if (gpu_sample) {
+            const int window = cfg.repeat_penalty > 1.0f ? std::min((int)tokens.size(), cfg.repeat_window) : 0;
+            const int id = model_.sample_last(cfg.temperature, cfg.top_k, cfg.top_p, cfg.repeat_penalty,
+                                              tokens.data() + (tokens.size() - (size_t)window), window, sampler.draw());
+            if (id >= 0) return id;
+        }
         NT_CUDA_CHECK(cudaMemcpy(logits.data(), dev_logits, sizeof(float) * (size_t)vocab, cudaMemcpyDeviceToHost));
         sampler.apply_repeat_penalty(logits.data(), vocab, tokens);
         return sampler.sample(logits.data(), vocab);

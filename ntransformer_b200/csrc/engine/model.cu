@@ -62,7 +62,7 @@ Model::~Model() {
     for (void* p : owned_) cudaFree(p);
     for (void* p : {(void*)hidden_, (void*)xnorm_, (void*)q_, (void*)k_, (void*)v_, (void*)attn_, (void*)act_, (void*)up_, (void*)part_,
                     (void*)logits_, (void*)logits_l_, (void*)attn_scratch_, xq_h_, xq_a_, xq_i_, kc_, vc_, (void*)step_dev_,
-                    (void*)argmax_dev_})
+                    (void*)argmax_dev_, (void*)recent_dev_})
         if (p) cudaFree(p);
     for (void* p : {(void*)pf_.x, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, pf_.ws, pf_.ws2, (void*)pf_.tok, (void*)pf_.pos,
                     (void*)pf_.g, (void*)pf_.u, pf_.whi, pf_.wlo})
@@ -572,6 +572,22 @@ float* Model::forward(const int* tokens, int seq_len, int start_pos) {
 
 int Model::argmax_last() {
     argmax_kernel<<<1, 1024, 0, stream_>>>(logits_, cfg_.vocab_size, argmax_dev_);
+    NT_CUDA_CHECK(cudaMemcpyAsync(argmax_host_, argmax_dev_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (mega_) mega_->check_abort();
+    return *argmax_host_;
+}
+
+int Model::sample_last(float temperature, int top_k, float top_p, float repeat_penalty, const int* recent_window, int n_window, float r) {
+    if (!sample_topk_supported(cfg_.vocab_size, temperature, top_k)) return -1;
+    if (n_window > recent_cap_) {
+        if (recent_dev_) { NT_CUDA_CHECK(cudaStreamSynchronize(stream_)); NT_CUDA_CHECK(cudaFree(recent_dev_)); }
+        recent_cap_ = std::max(256, n_window);
+        recent_dev_ = dmalloc<int>((size_t)recent_cap_);
+    }
+    if (n_window > 0) NT_CUDA_CHECK(cudaMemcpyAsync(recent_dev_, recent_window, sizeof(int) * (size_t)n_window, cudaMemcpyHostToDevice, stream_));
+    NT_CHECK(sample_topk(logits_, cfg_.vocab_size, temperature, top_k, top_p, repeat_penalty, recent_dev_, n_window, r, argmax_dev_, stream_),
+             "sample_topk rejected supported settings");
     NT_CUDA_CHECK(cudaMemcpyAsync(argmax_host_, argmax_dev_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
     NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
     if (mega_) mega_->check_abort();

@@ -58,6 +58,10 @@ public:
     void forward_async(const int* tokens, int seq_len, int start_pos);
     // Greedy next token computed on the GPU from the last logits (argmax, lowest index on ties like Sampler::argmax).
     int argmax_last();
+    // Samples the next token from the last logits on the GPU (csrc/sample.cu; penalty is applied in place to the device
+    // logits).  recent_window: the ids the repeat penalty looks at, oldest first.  Returns -1 when the settings are not
+    // covered (top_k <= 0, > 1024 or >= vocab, temperature <= 0): the caller samples on the host.
+    int sample_last(float temperature, int top_k, float top_p, float repeat_penalty, const int* recent_window, int n_window, float r);
 
     const ModelConfig& config() const { return cfg_; }
     const GGUFVocab& vocab() const { return vocab_; }
@@ -123,6 +127,8 @@ private:
     int* step_dev_ = nullptr;            // [0] token, [1] position
     int* argmax_dev_ = nullptr;
     int* argmax_host_ = nullptr;
+    int* recent_dev_ = nullptr;          // repeat-penalty window for the GPU sampler
+    int recent_cap_ = 0;
 
     struct PrefillBuffers {
         int cap = 0;                     // tokens per chunk the buffers hold

@@ -48,6 +48,9 @@ public:
     static int argmax(const float* logits, int n);
     void apply_repeat_penalty(float* logits, int n, const std::vector<int>& recent) const;
     int sample(const float* logits, int n);
+    // The uniform variate Sampler::sample would draw next (sampler.cpp:105-106): lets the GPU sampler consume the same stream.
+    float draw() { std::uniform_real_distribution<float> dist(0.0f, 1.0f); return dist(rng_); }
+    const SamplerConfig& config() const { return cfg_; }
 private:
     SamplerConfig cfg_;
     std::mt19937 rng_;

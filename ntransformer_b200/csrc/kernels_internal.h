@@ -89,6 +89,13 @@ void rope_kv_decode(float* q, float* k, const float* v, void* kc, void* vc, cons
 // Embedding-row gather + dequant on the GPU (reference does this on the CPU, transformer.cpp:419-599).
 void embed_rows(float* out, const void* table, DType dt, const int* tokens_dev, int n_tokens, int hidden, cudaStream_t s);
 
+// sample.cu: repeat penalty (in place on the logits) + temperature + top-k + top-p + inverse-CDF draw with the host-supplied
+// uniform variate r; the sampled token id goes to out_dev[0].  Returns false (nothing launched) unless 0 < top_k <= 1024 < n
+// and temperature > 0 — the caller then samples on the host like the reference (sampler.cpp:47-117).
+bool sample_topk_supported(int n, float temperature, int top_k);
+bool sample_topk(float* logits_dev, int n, float temperature, int top_k, float top_p, float repeat_penalty, const int* recent_dev,
+                 int n_recent, float r, int* out_dev, cudaStream_t s);
+
 // Programmatic dependent launch (PDL): when enabled, kernels are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization so that a kernel's prologue (barrier init, TMA weight
 // prefetch) overlaps the tail of its predecessor; every kernel executes griddepcontrol.wait before it touches
