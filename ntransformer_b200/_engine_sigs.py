@@ -42,6 +42,8 @@ ENGINE_SIGNATURES = {
     "nt_model_use_megakernel": (None, [_vp, _i]),
     "nt_model_megakernel_active": (_i, [_vp]),
     "nt_model_megakernel_plan": (_i, [_vp, _vp, _i]),
+    "nt_model_megakernel_trace": (None, [_vp, _i]),
+    "nt_model_megakernel_trace_read": (C.c_longlong, [_vp, _vp, _sz]),
     "nt_model_debug_read": (C.c_longlong, [_vp, C.c_char_p, _vp, _sz]),
     "nt_mega_plan_selftest": (_i, [C.POINTER(ModelConfigC), _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz]),
     "nt_gguf_describe": (_i, [C.c_char_p, _vp, _sz]),

@@ -105,6 +105,10 @@ int nt_model_megakernel_plan(nt_model_t m, int* kinds, int cap) {
     if (!m) return -1;
     return H(m)->model.mega_plan_kinds(kinds, cap);
 }
+void nt_model_megakernel_trace(nt_model_t m, int on) { if (m) H(m)->model.mega_trace(on != 0); }
+long long nt_model_megakernel_trace_read(nt_model_t m, unsigned long long* out_host, size_t cap) {
+    return m ? (long long)H(m)->model.mega_trace_read(out_host, cap) : -1;
+}
 long long nt_model_debug_read(nt_model_t m, const char* name, float* out_host, size_t cap) {
     if (!m || !name) return -1;
     size_t n = 0;

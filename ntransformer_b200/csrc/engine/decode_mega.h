@@ -41,6 +41,7 @@ constexpr int MEGA_MAX_STAGES = 4;          // TMA ring depth per warp
 constexpr int MEGA_MAX_TP = 8;
 constexpr int MEGA_ATTN_WARPS = 8;          // warps that work in the attention phase (attention.cu AW)
 constexpr int MEGA_SYNC_WORDS = 4 * 32;     // counter, go, abort, exchange sequence: one 128-byte line each
+constexpr int MEGA_TRACE_CTAS = 4;          // CTAs that record the phase timeline when tracing is on
 
 enum MegaPhaseKind : int { MPH_NORM_XQ = 0, MPH_QUANT = 1, MPH_GEMV = 2, MPH_ATTN = 3, MPH_COMBINE = 4 };
 enum MegaBarrierKind : int { MBAR_NONE = 0, MBAR_GRID = 1, MBAR_EXCHANGE = 2 };
@@ -113,6 +114,11 @@ struct MegaParams {
     unsigned* sync;             // MEGA_SYNC_WORDS words
     unsigned long long timeout_ns;
     int tp_rank, tp_size;
+    // Optional timeline (null = off): CTAs 0..MEGA_TRACE_CTAS-1 store %globaltimer at [cta][phase][0 start, 1 work done,
+    // 2 barrier passed], nanoseconds.  tools/mega_trace.py turns it into time per phase kind and time spent waiting in barriers.
+    unsigned long long* trace;
+    int trace_stride;               // values per CTA (3 x phases of the full program)
+    int pad2_;
     float* slots[MEGA_MAX_TP];      // rank r's slot buffer [2][tp_size][hidden] as mapped into this process
     unsigned* flags[MEGA_MAX_TP];   // rank r's flag words (one 128-byte line per source rank)
 };
@@ -193,6 +199,9 @@ public:
     const float* debug_buffer(const char* name, size_t* count) const;
     void set_split_fixed(int n) { split_fixed_ = n; }      // before build(): use the graph path's split rule (bit-identical attention)
     void set_fuse(int bits) { fuse_ = bits; }              // before build(): MegaFuse bits (default 0: the plain 9-phase program)
+    // Phase timeline of the most recent launch ([MEGA_TRACE_CTAS][n_phases][3] ns); enabling it costs three timer reads per phase.
+    void set_trace(bool on);
+    size_t read_trace(unsigned long long* out_host, size_t cap) const;     // returns the number of values available
 
 private:
     MegaPlan plan_;
@@ -207,6 +216,8 @@ private:
     int hidden_ = 0, nh_ = 0, hd_ = 0, inter_ = 0, tp_rank_ = 0, tp_size_ = 1, grid_ = 0;
     int split_fixed_ = 0, fuse_ = 0;
     unsigned *cnt_quant_ = nullptr, *cnt_attn_ = nullptr, *cnt_norm_ = nullptr;
+    unsigned long long* trace_ = nullptr;
+    bool trace_on_ = false;
     float* ssq_ = nullptr;
     bool peers_ready_ = false;
     std::string why_;

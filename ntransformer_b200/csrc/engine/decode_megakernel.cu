@@ -713,10 +713,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_c
     // Weights do not depend on anything computed in this kernel: start streaming the first GEMV's rows right away.
     if (P.first_gemv >= 0 && P.first_gemv < P.n_phases) prime_rings(S.ph[P.first_gemv & 3], pr, smem, S.bars, warp, lane);
 
+    const bool tracing = P.trace != nullptr && blockIdx.x < MEGA_TRACE_CTAS && threadIdx.x == 0;
+    unsigned long long* trace = tracing ? P.trace + (size_t)blockIdx.x * P.trace_stride : nullptr;
     for (int i = 0; i < P.n_phases; i++) {
         if (i + 2 < P.n_phases) load_phase(&S.ph[(i + 2) & 3], P.phases + i + 2);
         const MegaPhase& d = S.ph[i & 3];
         const int kind = d.kind;
+        if (tracing) trace[3 * i] = global_timer_ns();
         if (kind == MPH_GEMV) {
             gemv_phase(P, S, d, smem, pr, parity_bits, warp, lane);
         } else if (kind == MPH_NORM_XQ) {
@@ -735,7 +738,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_c
             __syncthreads();                                 // every warp is done with the ring area; descriptor i + 2 is visible
             prime_rings(S.ph[prime & 3], pr, smem, S.bars, warp, lane);
         }
+        if (tracing) trace[3 * i + 1] = global_timer_ns();
         mega_barrier(P, d.barrier, st);
+        if (tracing) trace[3 * i + 2] = global_timer_ns();
     }
     if (P.tp_size > 1 && blockIdx.x == 0 && threadIdx.x == 0) P.sync[96] = st.xchg_base + st.xchg_idx;
 }
@@ -1062,7 +1067,7 @@ DecodeMega::~DecodeMega() {
     for (size_t r = 0; r < peer_maps_.size(); r++)
         if (peer_maps_[r] && (int)r != tp_rank_) cudaIpcCloseMemHandle(peer_maps_[r]);
     for (void* p : {(void*)phases_dev_, (void*)hid_[0], (void*)hid_[1], (void*)q_, (void*)k_, (void*)v_, (void*)attn_, (void*)act_,
-                    (void*)scratch_, (void*)xq_h_, (void*)xq_a_, (void*)xq_i_, (void*)sync_, xchg_, (void*)cnt_quant_, (void*)cnt_attn_, (void*)cnt_norm_, (void*)ssq_})
+                    (void*)scratch_, (void*)xq_h_, (void*)xq_a_, (void*)xq_i_, (void*)sync_, xchg_, (void*)cnt_quant_, (void*)cnt_attn_, (void*)cnt_norm_, (void*)ssq_, (void*)trace_})
         if (p) cudaFree(p);
 }
 
@@ -1156,6 +1161,8 @@ void DecodeMega::launch(bool with_head, cudaStream_t s) {
     NT_CUDA_CHECK(cudaMemsetAsync(sync_, 0, 64 * sizeof(unsigned), s));
     MegaParams p = p_;
     p.n_phases = n_phases(with_head);
+    p.trace = trace_on_ ? trace_ : nullptr;     // laid out for the full program; a body-only launch fills a prefix per CTA
+    p.trace_stride = (int)plan_.phases.size() * 3;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid_); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = MEGA_DYN_SMEM; cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -1164,6 +1171,17 @@ void DecodeMega::launch(bool with_head, cudaStream_t s) {
     cfg.attrs = at; cfg.numAttrs = 1;
     NT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_step_kernel, p));
     count_launch();
+}
+
+void DecodeMega::set_trace(bool on) {
+    trace_on_ = on;
+    if (on && !trace_) trace_ = dalloc<unsigned long long>((size_t)MEGA_TRACE_CTAS * plan_.phases.size() * 3);
+}
+
+size_t DecodeMega::read_trace(unsigned long long* out_host, size_t cap) const {
+    const size_t n = trace_ ? (size_t)MEGA_TRACE_CTAS * plan_.phases.size() * 3 : 0;
+    if (out_host && n) NT_CUDA_CHECK(cudaMemcpy(out_host, trace_, sizeof(unsigned long long) * std::min(n, cap), cudaMemcpyDeviceToHost));
+    return n;
 }
 
 void DecodeMega::check_abort() {

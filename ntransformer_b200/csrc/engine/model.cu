@@ -409,6 +409,13 @@ const float* Model::mega_debug_buffer(const char* name, size_t* count) {
     return mega_->debug_buffer(name, count);
 }
 
+void Model::mega_trace(bool on) { if (mega_) mega_->set_trace(on); }
+size_t Model::mega_trace_read(unsigned long long* out_host, size_t cap) {
+    if (!mega_) return 0;
+    NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    return mega_->read_trace(out_host, cap);
+}
+
 int Model::mega_plan_kinds(int* kinds, int cap) {
     if (!mega_) return 0;
     const auto& pl = mega_->plan();

@@ -84,6 +84,8 @@ public:
     bool megakernel_active();                 // true once the persistent kernel has been built for this model
     // Debug read-back of the persistent kernel's working buffers ("hid0", "hid1", "q", "attn", "act", "slots"): device pointer.
     const float* mega_debug_buffer(const char* name, size_t* count);
+    void mega_trace(bool on);                  // record the persistent kernel's phase timeline (debug/tuning)
+    size_t mega_trace_read(unsigned long long* out_host, size_t cap);   // [4 CTAs][phases][start, work done, barrier passed] ns
     int mega_plan_kinds(int* kinds, int cap);  // phase kinds of the per-token program; returns their number (0 when inactive)
 
 private:

@@ -145,6 +145,19 @@ class Model:
         lib().nt_model_megakernel_plan(self._h, buf, n)
         return list(buf)
 
+    def megakernel_trace(self, on: bool = True):
+        """Record the persistent kernel's phase timeline (call after it is active, i.e. after one decoded token)."""
+        lib().nt_model_megakernel_trace(self._h, int(on))
+
+    def megakernel_trace_read(self):
+        """ns timestamps [4 CTAs, phases, (start, work done, barrier passed)] of the most recent launch."""
+        n = lib().nt_model_megakernel_trace_read(self._h, None, 0)
+        if n <= 0:
+            return np.zeros((0, 0, 3), dtype=np.uint64)
+        out = np.zeros(n, dtype=np.uint64)
+        lib().nt_model_megakernel_trace_read(self._h, out.ctypes.data_as(C.c_void_p), n)
+        return out.reshape(4, -1, 3)
+
     def debug_read(self, name: str):
         """Host copy of one of the persistent kernel's working vectors (hid0, hid1, q, attn, act, slots)."""
         n = lib().nt_model_debug_read(self._h, name.encode(), None, 0)
