@@ -8,6 +8,7 @@ thread_local Cta* g_cta = nullptr;
 std::atomic<bool> g_failed{false};
 double g_watchdog_s = 120.0;
 static std::mutex g_print_mu;
+static const size_t g_stack_bytes = []() { const char* e = getenv("CUSIM_STACK_KB"); return (size_t)(e ? atoi(e) : 128) * 1024; }();
 
 void complete_copy(const PendingCopy& c) {
     memcpy(c.dst, c.src, c.bytes);
@@ -99,7 +100,7 @@ bool launch(int grid, int threads, size_t dyn_smem, int copy_delay, const std::f
                 c.fibers[(size_t)t].warp = t / 32;
                 c.fibers[(size_t)t].lane = t % 32;
             }
-            if (!run_cta(c, 256 * 1024)) bad++;
+            if (!run_cta(c, g_stack_bytes)) bad++;
         });
     }
     for (auto& t : th) t.join();

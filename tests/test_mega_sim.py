@@ -102,7 +102,7 @@ def test_tiny_hd64_single_rank(sim, tmp_path):
 
 
 def test_hd128_q4_k_m_mix_with_async_copies(sim, tmp_path):
-    # Q4_K / Q6_K mix in one launch, two chunks per row, TMA copies completing out of order after random delays
+    # Q4_K / Q6_K mix in one launch (half-filled chunks: 8 super-blocks per row), TMA copies completing out of order
     check_against_oracle(sim, tmp_path, SMALL128, "Q4_K_M", steps=3, grid=8, copy_delay=7)
 
 
@@ -184,3 +184,20 @@ def test_fused_residual_and_norm_single_rank(sim, tmp_path, fuse):
     check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=8, grid=3, fuse=fuse)
     # under tensor parallelism the flag is ignored (the norm needs every rank's partial rows): still correct
     check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=2, tp=2, grid=3, fuse=fuse, tol=5e-4)
+
+
+def test_multi_chunk_rows_with_ragged_last_chunk(sim, tmp_path):
+    """The 70B-like row geometries: hidden 4608 = 18 super-blocks -> two chunks per row, the second only 2 super-blocks wide
+    (idle lanes); intermediate 12544 = 49 super-blocks -> four chunks for the down projection (8 of 12 warps busy, last chunk
+    1 super-block).  36 query heads / 9 KV heads, one layer, grid 18 (the norm phase needs hidden / 256 CTAs)."""
+    cfg = LlamaConfig(vocab_size=512, hidden_size=4608, intermediate_size=12544, n_layers=1, n_heads=36, n_kv_heads=9, head_dim=128,
+                      max_seq_len=64, bos_token_id=1, eos_token_id=2)
+    check_against_oracle(sim, tmp_path, cfg, "Q4_K", steps=1, grid=18, copy_delay=3, fuse=3)
+
+
+def test_eight_way_tensor_parallel(sim, tmp_path):
+    """The benchmark's widest configuration in miniature: 8 emulated ranks, one KV head and a 256-column o-proj / down-proj
+    shard each (one super-block per row: 2 of 32 lanes busy), every exchange an 8-way flag round trip."""
+    cfg = LlamaConfig(vocab_size=512, hidden_size=2048, intermediate_size=2048, n_layers=1, n_heads=32, n_kv_heads=8, head_dim=64,
+                      max_seq_len=64, bos_token_id=1, eos_token_id=2)
+    check_against_oracle(sim, tmp_path, cfg, "Q4_K", steps=1, tp=8, grid=8, fuse=3, tol=5e-4)
