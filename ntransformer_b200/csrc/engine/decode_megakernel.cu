@@ -36,11 +36,12 @@ constexpr size_t MEGA_DYN_SMEM = 227 * 1024 - MEGA_STATIC_SMEM;             // T
 // ---- memory-model helpers -----------------------------------------------------------------------------------------
 #ifdef NT_CUSIM   // CPU emulation (tests/cusim): C++ atomics; the acquire loads yield so that spinning threads let others run
 inline unsigned ld_acquire_gpu(const unsigned* p) { cusim::yield("spin (grid barrier word)"); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
-inline unsigned ld_acquire_sys(const unsigned* p) { cusim::yield("spin (peer flag)"); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline unsigned ld_relaxed_sys(const unsigned* p) { cusim::yield("spin (peer flag)"); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline unsigned ld_relaxed_gpu(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 inline void red_release_gpu_add(unsigned* p, unsigned v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
+inline void red_relaxed_gpu_add(unsigned* p, unsigned v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
 inline void st_release_gpu(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
-inline void st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline void st_relaxed_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline unsigned long long global_timer_ns() { return (unsigned long long)(cusim::now_s() * 1e9); }
 inline void fence_proxy_async_smem() {}
 #else
@@ -49,9 +50,9 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
@@ -65,8 +66,11 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
 __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_relaxed_gpu_add(unsigned* p, unsigned v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
@@ -77,15 +81,16 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 #endif
 
-// Spin until (int)(*p - target) >= 0.  SYS: the word is written by another GPU.  A time-out (or an abort raised elsewhere)
-// sets the abort word and returns: every later barrier then falls through and the host reports the failure.
+// Spin until (int)(*p - target) >= 0.  SYS: the word is written by another GPU and polled with relaxed system-scope loads (the
+// caller issues one system fence after all of its peers have arrived); otherwise acquire loads at GPU scope.  A time-out (or
+// an abort raised elsewhere) sets the abort word and returns: every later barrier then falls through and the host reports it.
 template <bool SYS>
 __device__ NT_NOINLINE void spin_until(const unsigned* p, unsigned target, unsigned* abort_word, unsigned long long timeout_ns) {
     if (ld_relaxed_gpu(abort_word)) return;
     const unsigned long long t0 = global_timer_ns();
     unsigned n = 0;
     for (;;) {
-        const unsigned v = SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p);
+        const unsigned v = SYS ? ld_relaxed_sys(p) : ld_acquire_gpu(p);
         if ((int)(v - target) >= 0) return;
         if ((++n & 255u) == 0) {
             if (ld_relaxed_gpu(abort_word)) return;
@@ -112,18 +117,20 @@ __device__ void mega_barrier(const MegaParams& P, int kind, SyncState& st) {
         unsigned* go = P.sync + 32;
         unsigned* abort_word = P.sync + 64;
         const unsigned target = st.bar_idx * gridDim.x;
-        if (xchg) __threadfence_system(); else __threadfence();
-        red_release_gpu_add(counter, 1u);
+        // One fence per hop.  Arrive: release at GPU scope, or — when this CTA has just pushed rows into peer memory — a
+        // system fence followed by a relaxed arrive (the system fence subsumes the GPU-scope release).
+        if (xchg) { __threadfence_system(); red_relaxed_gpu_add(counter, 1u); }
+        else red_release_gpu_add(counter, 1u);
         if (xchg) {
             const unsigned seq = st.xchg_base + st.xchg_idx;
             if (blockIdx.x == 0) {
                 spin_until<false>(counter, target, abort_word, P.timeout_ns);       // every local CTA has pushed its rows
-                __threadfence_system();
+                __threadfence_system();                                             // ... before the flags become visible
                 for (int r = 0; r < P.tp_size; r++)
-                    if (r != P.tp_rank) st_release_sys(P.flags[r] + 32 * P.tp_rank, seq);
+                    if (r != P.tp_rank) st_relaxed_sys(P.flags[r] + 32 * P.tp_rank, seq);      // posted NVLink writes
                 for (int r = 0; r < P.tp_size; r++)
-                    if (r != P.tp_rank) spin_until<true>(P.flags[P.tp_rank] + 32 * r, seq, abort_word, P.timeout_ns);
-                __threadfence_system();
+                    if (r != P.tp_rank) spin_until<true>(P.flags[P.tp_rank] + 32 * r, seq, abort_word, P.timeout_ns);   // local polls
+                __threadfence_system();                                             // acquire side: the peers' rows are visible
                 st_release_gpu(go, st.bar_idx);
             } else {
                 spin_until<false>(go, st.bar_idx, abort_word, P.timeout_ns);
@@ -131,7 +138,6 @@ __device__ void mega_barrier(const MegaParams& P, int kind, SyncState& st) {
         } else {
             spin_until<false>(counter, target, abort_word, P.timeout_ns);
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -394,7 +400,7 @@ __device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
             }
         }
     }
-    if (d.epilogue == MEP_SLOT && P.tp_size > 1) __threadfence_system();
+    if (d.epilogue == MEP_SLOT && P.tp_size > 1 && chunk == 0 && lane < RG) __threadfence_system();   // the lanes that stored to peer memory
 }
 
 // ---- norm + quantise (distributed over the first hidden/256 CTAs, as rmsnorm_xq_kernel) -----------------------------------
