@@ -43,10 +43,11 @@ constexpr int MEGA_ATTN_WARPS = 8;          // warps that work in the attention 
 constexpr int MEGA_SYNC_WORDS = 4 * 32;     // counter, go, abort, exchange sequence: one 128-byte line each
 constexpr int MEGA_TRACE_CTAS = 4;          // CTAs that record the phase timeline when tracing is on
 
-enum MegaPhaseKind : int { MPH_NORM_XQ = 0, MPH_QUANT = 1, MPH_GEMV = 2, MPH_ATTN = 3, MPH_COMBINE = 4 };
+enum MegaPhaseKind : int { MPH_NORM_XQ = 0, MPH_QUANT = 1, MPH_GEMV = 2, MPH_ATTN = 3, MPH_COMBINE = 4, MPH_REDUCE_XQ = 5 };
 enum MegaBarrierKind : int { MBAR_NONE = 0, MBAR_GRID = 1, MBAR_EXCHANGE = 2 };
 enum MegaEpilogue : int { MEP_STORE = 0, MEP_SWIGLU = 2, MEP_SLOT = 3 };
-enum MegaFuse : int { MEGA_FUSE_QUANT = 1, MEGA_FUSE_COMBINE = 2, MEGA_FUSE_NORM = 4 /* single rank only */ };
+enum MegaFuse : int { MEGA_FUSE_QUANT = 1, MEGA_FUSE_COMBINE = 2, MEGA_FUSE_NORM = 4 /* single rank only */,
+                      MEGA_DEFER_RMS = 8 /* always on under tensor parallelism */ };
 
 struct MegaMat {
     const uint8_t* W;
@@ -72,6 +73,8 @@ struct MegaPhase {
     const int8_t* xq;           // pre-quantised activations (kernels_internal.h "xq")
     // ---- MPH_NORM_XQ: h = hid_in (+ sum_r slot[pending_parity][r]);  hid_out <- h;  xq_out <- quantise(rmsnorm(h) * norm_w)
     //      MPH_QUANT:   xq_out <- quantise(x[0..n))
+    //      MPH_REDUCE_XQ (MEGA_DEFER_RMS): like MPH_NORM_XQ but one warp per 32-element block, no full-vector pass: hid_out <- h,
+    //                   ssq_out[block] <- sum(h^2), xq_out <- quantise(h * norm_w); the consuming GEMV applies 1/rms (ssq_in)
     const float* norm_w;
     const float* hid_in;
     float* hid_out;             // null when nothing is pending

@@ -407,12 +407,31 @@ __device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
 __device__ __forceinline__ float residual_at(const MegaParams& P, const MegaPhase& d, int i) {
     float v = __ldcg(d.hid_in + i);
     if (d.pending_parity >= 0) {
-        const float* sl = P.slots[P.tp_rank] + (size_t)d.pending_parity * P.tp_size * (size_t)P.hidden;
-        float t = __ldcg(sl + i);
-        for (int r = 1; r < P.tp_size; r++) t += __ldcg(sl + (size_t)r * P.hidden + i);
+        // sum of the ranks' partial rows in rank order; the loads are issued together (one L2 round trip, not tp_size)
+        const float* sl = P.slots[P.tp_rank] + (size_t)d.pending_parity * P.tp_size * (size_t)P.hidden + i;
+        float sv[MEGA_MAX_TP];
+#pragma unroll
+        for (int r = 0; r < MEGA_MAX_TP; r++) sv[r] = (r < P.tp_size) ? __ldcg(sl + (size_t)r * P.hidden) : 0.f;
+        float t = sv[0];
+#pragma unroll
+        for (int r = 1; r < MEGA_MAX_TP; r++) if (r < P.tp_size) t += sv[r];
         v += t;
     }
     return v;
+}
+
+// Distributed form of the norm phase (MEGA_DEFER_RMS): one warp per 32-element block anywhere in the grid, a single L2 round
+// trip, no CTA-wide reduction.  The 1/rms factor is left to the consumer (ssq_in), exactly as for MEGA_FUSE_NORM.
+__device__ void reduce_xq_phase(const MegaParams& P, const MegaPhase& d, int warp, int lane) {
+    const int nblk = P.hidden / 32;
+    for (int b = (int)blockIdx.x * MEGA_WARPS + warp; b < nblk; b += (int)gridDim.x * MEGA_WARPS) {
+        const int e = b * 32 + lane;
+        const float hval = residual_at(P, d, e);
+        if (d.hid_out) d.hid_out[e] = hval;
+        const float ss = warp_sum(hval * hval);
+        if (lane == 0) d.ssq_out[b] = ss;
+        quantize_block32(hval * d.norm_w[e], b, lane, d.xq_out, P.hidden);
+    }
 }
 
 __device__ void norm_xq_phase(const MegaParams& P, Shared& S, const MegaPhase& d, int warp, int lane) {
@@ -732,6 +751,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_c
             norm_xq_phase(P, S, d, warp, lane);
         } else if (kind == MPH_QUANT) {
             quant_phase(d, warp, lane);
+        } else if (kind == MPH_REDUCE_XQ) {
+            reduce_xq_phase(P, d, warp, lane);
         } else if (kind == MPH_ATTN) {
             if (P.hd == 128 && P.gc == 8) attn_phase<4, 8>(P, S, d, smem);
             else if (P.hd == 128 && P.gc == 4) attn_phase<4, 4>(P, S, d, smem);
@@ -805,12 +826,17 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
     if (!((mv.hd == 128 && (gc == 8 || gc == 4)) || (mv.hd == 64 && gc == 4)))
         return fail("attention shape not instantiated (head_dim 128 with 4/8 query heads per KV head, or 64 with 4)");
     if (hidden % 256 != 0 || (mv.nh * mv.hd) % 256 != 0 || inter % 256 != 0) return fail("dimensions must be multiples of 256");
-    if (grid < 1 || hidden / 256 > grid) return fail("hidden / 256 exceeds the grid");
+    if (grid < 1) return fail("empty grid");
     pl.gc = gc;
     if ((fuse & MEGA_FUSE_QUANT) && !B.cnt_quant) fuse &= ~MEGA_FUSE_QUANT;
     if ((fuse & MEGA_FUSE_COMBINE) && !B.cnt_attn) fuse &= ~MEGA_FUSE_COMBINE;
     if ((fuse & MEGA_FUSE_NORM) && (!B.cnt_norm || !B.ssq || mv.tp_size != 1 || hidden % 32 != 0)) fuse &= ~MEGA_FUSE_NORM;
+    // Under tensor parallelism the norm phase would read tp_size + 1 full vectors per participating CTA: always use the
+    // distributed reduce phase there.  At one rank it is optional (it gives up bit-comparability with the graph path).
+    if (mv.tp_size > 1 && B.ssq) fuse |= MEGA_DEFER_RMS;
+    if ((fuse & MEGA_DEFER_RMS) && !B.ssq) fuse &= ~MEGA_DEFER_RMS;
     pl.fuse = fuse;
+    if (!(fuse & MEGA_DEFER_RMS) && hidden / 256 > grid) return fail("hidden / 256 exceeds the grid");   // MPH_NORM_XQ needs them
     const int qdim = mv.nh * mv.hd;
 
     // ---- attention split geometry ----
@@ -875,15 +901,18 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
 
     int cur = 0;                 // B.hid[cur] holds the residual stream (before pending slots are added)
     int pending = -1;            // parity of the slots still to be added, -1 none
+    bool deferred = false;       // the current xq_h lacks its 1/rms factor: its consumers apply it themselves (ssq_in)
+    const bool defer = (fuse & MEGA_DEFER_RMS) != 0;
     auto norm_phase = [&](int layer, const float* w) {
-        MegaPhase ph = base_phase(MPH_NORM_XQ, layer);
+        MegaPhase ph = base_phase(defer ? MPH_REDUCE_XQ : MPH_NORM_XQ, layer);
         ph.norm_w = w; ph.hid_in = B.hid[cur]; ph.xq_out = B.xq_h; ph.pending_parity = pending;
         if (pending >= 0) { ph.hid_out = B.hid[cur ^ 1]; cur ^= 1; pending = -1; }
+        if (defer) ph.ssq_out = B.ssq;
+        deferred = defer;
         return ph;
     };
     std::vector<MegaPhase>& plan = pl.phases;
     const bool fnorm = (fuse & MEGA_FUSE_NORM) != 0;
-    bool deferred = false;       // the current xq_h was produced by a fused norm: its consumers apply 1/rms themselves
     // fold "residual add + next norm" into a slot-epilogue GEMV phase (MEGA_FUSE_NORM, single rank)
     auto fold_norm = [&](MegaPhase& ph, const float* next_norm_w) {
         ph.fuse |= MEGA_FUSE_NORM;
@@ -1044,7 +1073,7 @@ std::string mega_check_plan(const MegaPlan& pl, int grid, int tp_size) {
 
         } else if (d.kind == MPH_ATTN) {
             if (primed >= 0) { snprintf(msg, sizeof(msg), "attention phase %d would overwrite rings primed for %d", i, primed); return msg; }
-        } else if (d.kind == MPH_NORM_XQ) {
+        } else if (d.kind == MPH_NORM_XQ || d.kind == MPH_REDUCE_XQ) {
             if (stream && d.hid_in != stream) { snprintf(msg, sizeof(msg), "norm phase %d does not read the current residual stream", i); return msg; }
             if (d.pending_parity != pending) { snprintf(msg, sizeof(msg), "norm phase %d: pending parity %d, expected %d", i, d.pending_parity, pending); return msg; }
             if ((pending >= 0) != (d.hid_out != nullptr)) return "hid_out must be set exactly when slots are pending";
@@ -1052,7 +1081,8 @@ std::string mega_check_plan(const MegaPlan& pl, int grid, int tp_size) {
             stream = d.hid_out ? d.hid_out : d.hid_in;
             pending = -1;
             xq_norm = d.xq_out;
-            deferred = false;
+            deferred = (d.kind == MPH_REDUCE_XQ);
+            if (deferred && !d.ssq_out) return "reduce phase without a sum-of-squares buffer";
         }
         if (d.prime >= 0) {
             if (d.prime <= i || d.prime >= n || ph[(size_t)d.prime].kind != MPH_GEMV) return "prime target is not a later GEMV phase";

@@ -201,3 +201,11 @@ def test_eight_way_tensor_parallel(sim, tmp_path):
     cfg = LlamaConfig(vocab_size=512, hidden_size=2048, intermediate_size=2048, n_layers=1, n_heads=32, n_kv_heads=8, head_dim=64,
                       max_seq_len=64, bos_token_id=1, eos_token_id=2)
     check_against_oracle(sim, tmp_path, cfg, "Q4_K", steps=1, tp=8, grid=8, fuse=3, tol=5e-4)
+
+
+@pytest.mark.parametrize("fuse", [8, 11])
+def test_distributed_reduce_phase_single_rank(sim, tmp_path, fuse):
+    """MEGA_DEFER_RMS (8): the norm phases become one-warp-per-block reduce phases (always on under tensor parallelism, where
+    every test above with tp > 1 already runs them); here at one rank, alone and with the quantiser/combine fusions."""
+    check_against_oracle(sim, tmp_path, SMALL128, "Q4_K_M", steps=3, grid=5, copy_delay=4, fuse=fuse)
+    check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=6, grid=1, fuse=fuse)      # a single CTA is a valid grid now
