@@ -30,6 +30,7 @@ namespace {
 
 constexpr int NTHREADS = MEGA_WARPS * 32;
 constexpr int AW = MEGA_ATTN_WARPS;
+constexpr int KU = 4;                                                        // K / V rows in flight per warp in the attention phase
 constexpr size_t MEGA_STATIC_SMEM = 4096;                                   // upper bound of the kernel's static __shared__
 constexpr size_t MEGA_DYN_SMEM = 227 * 1024 - MEGA_STATIC_SMEM;             // TMA rings; aliased by the attention scratch
 
@@ -574,21 +575,33 @@ __device__ void attend_unit(const MegaParams& P, Shared& S, const MegaPhase& d, 
         for (int g = 0; g < GC; g++)
 #pragma unroll
             for (int i = 0; i < DPL; i++) qr[g][i] = q_s[g * HD + lane * DPL + i];
-        // ---- phase 1: scores ----
-        for (int p = warp; p < n_keys; p += AW) {
-            float kf[DPL];
-            if (k_begin + p == pos) load_row<DPL>(cur_k + lane * DPL, kf);
-            else load_row<DPL>(kbase + (size_t)(k_begin + p) * row_stride, kf);
-            float part[GC];
+        // ---- phase 1: scores.  KU key rows are fetched before any of them is used: one memory round trip per KU keys ----
+        for (int p0 = warp; p0 < n_keys; p0 += AW * KU) {
+            float kf[KU][DPL];
 #pragma unroll
-            for (int g = 0; g < GC; g++) {
-                float a = 0.f;
-#pragma unroll
-                for (int i = 0; i < DPL; i++) a = fmaf(qr[g][i], kf[i], a);
-                part[g] = a;
+            for (int u = 0; u < KU; u++) {
+                const int p = p0 + u * AW;
+                if (p < n_keys) {
+                    if (k_begin + p == pos) load_row<DPL>(cur_k + lane * DPL, kf[u]);
+                    else load_row<DPL>(kbase + (size_t)(k_begin + p) * row_stride, kf[u]);
+                }
             }
-            float tot = transpose_reduce<GC>(part, lane);
-            if ((lane & (32 / GC - 1)) == 0) sc[(size_t)(lane / (32 / GC)) * P.max_split + p] = tot * P.attn_scale;
+#pragma unroll
+            for (int u = 0; u < KU; u++) {
+                const int p = p0 + u * AW;
+                if (p < n_keys) {                            // warp-uniform
+                    float part[GC];
+#pragma unroll
+                    for (int g = 0; g < GC; g++) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int i = 0; i < DPL; i++) a = fmaf(qr[g][i], kf[u][i], a);
+                        part[g] = a;
+                    }
+                    float tot = transpose_reduce<GC>(part, lane);
+                    if ((lane & (32 / GC - 1)) == 0) sc[(size_t)(lane / (32 / GC)) * P.max_split + p] = tot * P.attn_scale;
+                }
+            }
         }
     }
     __syncthreads();
@@ -615,15 +628,27 @@ __device__ void attend_unit(const MegaParams& P, Shared& S, const MegaPhase& d, 
         for (int g = 0; g < GC; g++)
 #pragma unroll
             for (int i = 0; i < DPL; i++) acc[g][i] = 0.f;
-        for (int p = warp; p < n_keys; p += AW) {
-            float vf[DPL];
-            if (k_begin + p == pos) load_row<DPL>(cur_v + lane * DPL, vf);
-            else load_row<DPL>(vbase + (size_t)(k_begin + p) * row_stride, vf);
+        for (int p0 = warp; p0 < n_keys; p0 += AW * KU) {    // same key order per warp as the one-at-a-time loop
+            float vf[KU][DPL];
 #pragma unroll
-            for (int g = 0; g < GC; g++) {
-                float w = sc[(size_t)g * P.max_split + p];
+            for (int u = 0; u < KU; u++) {
+                const int p = p0 + u * AW;
+                if (p < n_keys) {
+                    if (k_begin + p == pos) load_row<DPL>(cur_v + lane * DPL, vf[u]);
+                    else load_row<DPL>(vbase + (size_t)(k_begin + p) * row_stride, vf[u]);
+                }
+            }
 #pragma unroll
-                for (int i = 0; i < DPL; i++) acc[g][i] = fmaf(w, vf[i], acc[g][i]);
+            for (int u = 0; u < KU; u++) {
+                const int p = p0 + u * AW;
+                if (p < n_keys) {
+#pragma unroll
+                    for (int g = 0; g < GC; g++) {
+                        float w = sc[(size_t)g * P.max_split + p];
+#pragma unroll
+                        for (int i = 0; i < DPL; i++) acc[g][i] = fmaf(w, vf[u][i], acc[g][i]);
+                    }
+                }
             }
         }
 #pragma unroll
@@ -632,6 +657,25 @@ __device__ void attend_unit(const MegaParams& P, Shared& S, const MegaPhase& d, 
             for (int i = 0; i < DPL; i++) red[((size_t)warp * GC + g) * HD + lane * DPL + i] = acc[g][i];
     }
     __syncthreads();
+    if ((d.fuse & MEGA_FUSE_COMBINE) && used == 1) {
+        // The only split of its head group: nothing to merge.  Normalise and quantise straight from shared memory — the values
+        // the combine would produce (o = t * e^0, l = sum * e^0), without the round trip through the scratch buffer.
+        if (threadIdx.x < AW * 32) {
+            for (int idx = threadIdx.x; idx < GC * HD; idx += AW * 32) {      // 32 consecutive idx = one warp, one head
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < AW; w++) t += red[(size_t)w * GC * HD + idx];
+                const int g = idx / HD, dd = idx - g * HD;
+                const float l = S.s_sum[g];
+                const float v = t * ((l > 0.f) ? 1.0f / l : 0.f);
+                const int e = (head0 + g) * HD + dd;
+                P.attn_out[e] = v;
+                quantize_block32(v, e >> 5, lane, P.xq_a, P.nh * HD);
+            }
+        }
+        __syncthreads();                                     // shared memory is reused by the CTA's next unit
+        return;
+    }
     // ---- unnormalised partials of this split -> scratch [head][split][HD], [head][split][2] ----
     const int NS = P.n_splits_max;
     float* ml = P.attn_scratch + (size_t)P.nh * NS * HD;
@@ -684,16 +728,41 @@ __device__ void attn_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
 // Merge the split partials of head h and emit its slice of the o-projection's xq (decode_combine_kernel with xq_out).
 // Called by threads 0..127 of a CTA (hd % 32 == 0: whole warps stay together in the quantiser).
 __device__ __forceinline__ void combine_head(const MegaParams& P, int h, int used) {
+    constexpr int CU = 8;                                    // splits whose partials are in flight together
     const int hd = P.hd, n_heads = P.nh, NS = P.n_splits_max;
     const float* ml = P.attn_scratch + (size_t)n_heads * NS * hd + (size_t)h * NS * 2;
     float m = -FLT_MAX;
-    for (int i = 0; i < used; i++) m = fmaxf(m, __ldcg(ml + 2 * i));
+    for (int i0 = 0; i0 < used; i0 += CU) {
+        float a[CU];
+#pragma unroll
+        for (int j = 0; j < CU; j++) a[j] = (i0 + j < used) ? __ldcg(ml + 2 * (i0 + j)) : -FLT_MAX;
+#pragma unroll
+        for (int j = 0; j < CU; j++) m = fmaxf(m, a[j]);
+    }
     float l = 0.f;
-    for (int i = 0; i < used; i++) l += __ldcg(ml + 2 * i + 1) * expf(__ldcg(ml + 2 * i) - m);
+    for (int i0 = 0; i0 < used; i0 += CU) {
+        float a[CU], b[CU];
+#pragma unroll
+        for (int j = 0; j < CU; j++) {
+            a[j] = (i0 + j < used) ? __ldcg(ml + 2 * (i0 + j)) : 0.f;
+            b[j] = (i0 + j < used) ? __ldcg(ml + 2 * (i0 + j) + 1) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < CU; j++) if (i0 + j < used) l += b[j] * expf(a[j] - m);
+    }
     const float inv = (l > 0.f) ? 1.0f / l : 0.f;
     for (int dd = threadIdx.x; dd < hd; dd += 128) {
         float o = 0.f;
-        for (int i = 0; i < used; i++) o += __ldcg(P.attn_scratch + ((size_t)h * NS + i) * hd + dd) * expf(__ldcg(ml + 2 * i) - m);
+        for (int i0 = 0; i0 < used; i0 += CU) {
+            float a[CU], b[CU];
+#pragma unroll
+            for (int j = 0; j < CU; j++) {
+                a[j] = (i0 + j < used) ? __ldcg(ml + 2 * (i0 + j)) : 0.f;
+                b[j] = (i0 + j < used) ? __ldcg(P.attn_scratch + ((size_t)h * NS + i0 + j) * hd + dd) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < CU; j++) if (i0 + j < used) o += b[j] * expf(a[j] - m);
+        }
         const float v = o * inv;
         P.attn_out[(size_t)h * hd + dd] = v;
         const int K = n_heads * hd, e = h * hd + dd, lane = threadIdx.x & 31;
