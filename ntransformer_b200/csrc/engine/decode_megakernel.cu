@@ -176,7 +176,7 @@ struct Producer {
 __host__ __device__ __forceinline__ int phase_rounds(const MegaPhase& d, int grid) {
     return (d.total_groups + grid * d.gpc - 1) / (grid * d.gpc);
 }
-__host__ __device__ __forceinline__ int blk_bytes(int fmt) { return fmt == 0 ? 144 : fmt == 1 ? 176 : fmt == 2 ? 210 : 272; }
+__host__ __device__ __forceinline__ int blk_bytes(int fmt) { return fmt == 1 ? 176 : fmt == 2 ? 210 : fmt == 3 ? 272 : 144; }   // 0 Q4_K, 4 Q4_0: 144
 
 __host__ __device__ __forceinline__ void locate(const MegaPhase& d, int g, int seg, int& mi, int& gl) {
     if (d.n_seg == 2) { mi = seg; gl = g; return; }
@@ -318,7 +318,8 @@ __device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
                 if (fmt == 0) process_stage<0>(slot_base, blk, h, X, acc);
                 else if (fmt == 1) process_stage<1>(slot_base, blk, h, X, acc);
                 else if (fmt == 2) process_stage<2>(slot_base, blk, h, X, acc);
-                else process_stage<3>(slot_base, blk, h, X, acc);
+                else if (fmt == 3) process_stage<3>(slot_base, blk, h, X, acc);
+                else process_stage<4>(slot_base, blk, h, X, acc);
             }
             __syncwarp();
             if (pr.issued < n_stages_total) issue_next(d, pr, ring, bars, slot, chunk, nbc, lane);
@@ -841,7 +842,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_c
     if (P.tp_size > 1 && blockIdx.x == 0 && threadIdx.x == 0) P.sync[96] = st.xchg_base + st.xchg_idx;
 }
 
-int fmt_of(DType dt) { return dt == DType::Q4_K_M ? 0 : dt == DType::Q5_K ? 1 : dt == DType::Q6_K ? 2 : dt == DType::Q8_0 ? 3 : -1; }
+int fmt_of(DType dt) {
+    return dt == DType::Q4_K_M ? 0 : dt == DType::Q5_K ? 1 : dt == DType::Q6_K ? 2 : dt == DType::Q8_0 ? 3 : dt == DType::Q4_0 ? 4 : -1;
+}
 
 template <typename T> T* dalloc(size_t n) {
     T* p = nullptr;
@@ -865,7 +868,7 @@ MegaGemvGeom mega_gemv_geom(const int* fmts, int n_mat, int K, size_t ring_bytes
     if (g.NC > MEGA_WARPS) return g;
     g.mask = 0;
     for (int i = 0; i < n_mat; i++) {
-        if (fmts[i] < 0 || fmts[i] > 3) return g;
+        if (fmts[i] < 0 || fmts[i] > 4) return g;
         g.mask |= 1 << fmts[i];
     }
     g.slot_bytes = RG * BS * max_blk(g.mask);
@@ -945,7 +948,16 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
             mats[i].W = ws[i]->ptr; mats[i].y = ys[i]; mats[i].out = ws[i]->rows; mats[i].dtype = ws[i]->dtype; mats[i].row_pitch = ws[i]->pitch;
             fmts[i] = fmt_of(ws[i]->dtype);
         }
-        if (!gemv_kq_supported(mats, n, K)) return false;
+        // same alignment rules as gemv_kq_supported (gemv_kquant.cu), with Q4_0 admitted unconditionally on this opt-in path
+        if (K <= 0 || K % 256 != 0 || (K / 256 + BS - 1) / BS > MEGA_WARPS) return false;
+        for (int i = 0; i < n; i++) {
+            if (fmts[i] < 0 || mats[i].out <= 0) return false;
+            const size_t pitch = mats[i].row_pitch ? mats[i].row_pitch : dtype_row_size(mats[i].dtype, (size_t)K);
+            if ((reinterpret_cast<uintptr_t>(mats[i].W) & 15) || (pitch & 15)) return false;
+            const size_t blk = dtype_row_size(mats[i].dtype, 256);           // bytes per 256 weights
+            const int NBq = K / 256, NCq = (NBq + BS - 1) / BS, last = NBq - (NCq - 1) * BS;
+            if ((size_t)(NCq - 1) * BS * blk + (((size_t)last * blk + 15) & ~(size_t)15) > pitch) return false;   // 16-byte copy tail
+        }
         if (epilogue == MEP_SWIGLU && (n != 2 || ws[0]->rows != ws[1]->rows)) return false;
         const MegaGemvGeom g = mega_gemv_geom(fmts, n, K, ring);
         if (!g.ok) return false;

@@ -17,6 +17,7 @@ template <> struct Fmt<0> { static constexpr int BLK = 144; };   // Q4_K
 template <> struct Fmt<1> { static constexpr int BLK = 176; };   // Q5_K
 template <> struct Fmt<2> { static constexpr int BLK = 210; };   // Q6_K
 template <> struct Fmt<3> { static constexpr int BLK = 272; };   // Q8_0: 8 blocks of 34 B = 256 weights
+template <> struct Fmt<4> { static constexpr int BLK = 144; };   // Q4_0: 8 blocks of 18 B = 256 weights
 
 // The lane's 128 activation elements: three int8 planes (32 words each, natural order), the four 32-block scales and
 // the eight 16-element sums.
@@ -126,6 +127,38 @@ __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_b
                 acc[r] = fmaf(d * X.sx[j], f, acc[r]);
             }
         }
+    } else if (FMT == 4) {
+        // ---------------- Q4_0 (reference K1, gemm.cu:32-90): this lane's 128 weights = 4 blocks of [fp16 d][16 bytes: low
+        // nibbles = weights 0..15, high nibbles = weights 16..31], value = d * (nibble - 8).  72 bytes per lane, 8-byte aligned;
+        // blocks 0 and 2 hold their codes 2 bytes into a word (PRMT realign), blocks 1 and 3 are word aligned.  The -8 offset
+        // goes through the exact 16-element sums of x, like dmin in Q4_K. ----------------
+        const uint8_t* lb = base + h * 72;
+#pragma unroll
+        for (int r = 0; r < RG; r++) {
+            uint32_t w[18];
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                const uint2 v = *reinterpret_cast<const uint2*>(lb + r * ROWP + 8 * i);
+                w[2 * i] = v.x; w[2 * i + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                // block j starts at byte 18 j: word (18 j) / 4 = {0, 4, 9, 13}, byte offset inside it {0, 2, 0, 2}
+                const int w0 = (j == 0) ? 0 : (j == 1) ? 4 : (j == 2) ? 9 : 13;
+                const bool odd = (j & 1) != 0;               // d in the high half of word w0, codes word aligned from w0 + 1
+                const float d = h2f(odd ? (w[w0] >> 16) : (w[w0] & 0xFFFFu));
+                int l0 = 0, l1 = 0, l2 = 0, h0 = 0, h1 = 0, h2 = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t q = odd ? w[w0 + 1 + i] : __byte_perm(w[w0 + i], w[w0 + i + 1], 0x5432u);
+                    const uint32_t lo = q & 0x0F0F0F0Fu, hi = (q >> 4) & 0x0F0F0F0Fu;
+                    l0 = dp4a_us(lo, X.x[0][8 * j + i], l0); l1 = dp4a_us(lo, X.x[1][8 * j + i], l1); l2 = dp4a_us(lo, X.x[2][8 * j + i], l2);
+                    h0 = dp4a_us(hi, X.x[0][8 * j + 4 + i], h0); h1 = dp4a_us(hi, X.x[1][8 * j + 4 + i], h1); h2 = dp4a_us(hi, X.x[2][8 * j + 4 + i], h2);
+                }
+                const float f = (float)combine3(l0 + h0, l1 + h1, l2 + h2) * X.sx[j];
+                acc[r] = fmaf(d, fmaf(-8.0f, X.s16[2 * j] + X.s16[2 * j + 1], f), acc[r]);
+            }
+        }
     } else {
         // ---------------- Q6_K (210-byte blocks: 2-byte aligned, realigned with PRMT) ----------------
         const uint32_t mis = (uint32_t)(blk & 1) * 2u;           // (blk * 210) & 2
@@ -177,7 +210,7 @@ __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_b
     }
 }
 
-__host__ __device__ constexpr int max_blk(int mask) { return (mask & 8) ? 272 : (mask & 4) ? 210 : (mask & 2) ? 176 : 144; }
+__host__ __device__ constexpr int max_blk(int mask) { return (mask & 8) ? 272 : (mask & 4) ? 210 : (mask & 2) ? 176 : 144; }   // bit 16 (Q4_0): 144
 
 // 4-row transpose-reduce over the warp: on return lanes with (lane & 7) == 0 hold row (lane>>4)*2 + ((lane>>3)&1).
 __device__ __forceinline__ float reduce4(const float (&acc)[RG], int lane) {

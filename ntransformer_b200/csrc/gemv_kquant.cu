@@ -40,7 +40,7 @@ struct KqMat {
     float* y;
     int out;
     int groups;        // ceil(out / RG)
-    int fmt;           // 0 Q4_K, 1 Q5_K, 2 Q6_K, 3 Q8_0 (as groups of 8 blocks)
+    int fmt;           // 0 Q4_K, 1 Q5_K, 2 Q6_K, 3 Q8_0 (as groups of 8 blocks), 4 Q4_0 (likewise; opt-in, see fmt_of)
     long long row_pitch;
 };
 struct KqParams {
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
             int mi, gl;
             locate(p_g, p_seg, mi, gl);
             const KqMat& m = p.mat[mi];
-            const int blkb = (MASK == 1) ? 144 : (MASK == 2) ? 176 : (MASK == 4) ? 210 : (MASK == 8) ? 272 : (m.fmt == 0 ? 144 : m.fmt == 1 ? 176 : 210);
+            const int blkb = (MASK == 1) ? 144 : (MASK == 2) ? 176 : (MASK == 4) ? 210 : (MASK == 8) ? 272 : (MASK == 16) ? 144 : (m.fmt == 0 ? 144 : m.fmt == 1 ? 176 : 210);
             // copy size rounded up to 16 B (a 210-byte Q6_K tail may spill into row padding; checked on the host)
             const uint32_t bytes = ((uint32_t)(nbc * blkb) + 15u) & ~15u;
             mbar_expect_tx(bar, bytes * RG);
@@ -220,11 +220,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
                 int mi, gl;
                 locate(g, seg, mi, gl);
                 const uint8_t* slot_base = ring + (size_t)slot * SLOT;
-                const int fmt = (MASK == 1) ? 0 : (MASK == 2) ? 1 : (MASK == 4) ? 2 : (MASK == 8) ? 3 : p.mat[mi].fmt;
+                const int fmt = (MASK == 1) ? 0 : (MASK == 2) ? 1 : (MASK == 4) ? 2 : (MASK == 8) ? 3 : (MASK == 16) ? 4 : p.mat[mi].fmt;
                 if ((MASK & 1) && fmt == 0) process_stage<0>(slot_base, blk, h, X, acc);
                 if ((MASK & 2) && fmt == 1) process_stage<1>(slot_base, blk, h, X, acc);
                 if ((MASK & 4) && fmt == 2) process_stage<2>(slot_base, blk, h, X, acc);
                 if ((MASK & 8) && fmt == 3) process_stage<3>(slot_base, blk, h, X, acc);
+                if ((MASK & 16) && fmt == 4) process_stage<4>(slot_base, blk, h, X, acc);
             }
             __syncwarp();
             if (lane == 0 && issued < n_stages_total) issue_next(slot);
@@ -264,7 +265,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     }
 }
 
-int fmt_of(DType dt) { return dt == DType::Q4_K_M ? 0 : dt == DType::Q5_K ? 1 : dt == DType::Q6_K ? 2 : dt == DType::Q8_0 ? 3 : -1; }
+// Q4_0 on this path is opt-in (NT_B200_Q4_0_TMA=1) until it has run on hardware: written after round 1's GPU budget was
+// spent, verified through the CPU emulation of the persistent kernel (tests/test_mega_sim.py), which shares process_stage<4>.
+// Without the switch Q4_0 keeps the generic kernel (gemv_generic.cu), as before.
+bool q4_0_tma_enabled() {
+    static const bool on = getenv("NT_B200_Q4_0_TMA") != nullptr;
+    return on;
+}
+int fmt_of(DType dt) {
+    return dt == DType::Q4_K_M ? 0 : dt == DType::Q5_K ? 1 : dt == DType::Q6_K ? 2 : dt == DType::Q8_0 ? 3
+         : (dt == DType::Q4_0 && q4_0_tma_enabled()) ? 4 : -1;
+}
 
 int g_num_sms = 0;
 int num_sms() {
@@ -361,7 +372,7 @@ void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpi
         NT_CHECK(n_mat == 2 && mats[0].out == mats[1].out, "gemv_kq: SWIGLU needs gate and up of equal rows");
     int mask = 0;
     for (int i = 0; i < n_mat; i++) mask |= 1 << fmt_of(mats[i].dtype);
-    const bool plain = mask == 1 || mask == 2 || mask == 4 || mask == 8 || mask == 3 || mask == 5;
+    const bool plain = mask == 1 || mask == 2 || mask == 4 || mask == 8 || mask == 3 || mask == 5 || mask == 16;
     if (!plain && ep != GEMV_SWIGLU) {                         // rare mixes: one launch per matrix
         for (int i = 0; i < n_mat; i++) gemv_kq(&mats[i], 1, K, in, ep, s);
         return;
@@ -392,6 +403,7 @@ void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpi
         case 4: launch_fmt<4>(p, s); break;
         case 3: launch_fmt<3>(p, s); break;
         case 8: launch_fmt<8>(p, s); break;
+        case 16: launch_fmt<16>(p, s); break;
         default: launch_fmt<5>(p, s); break;
     }
 }

@@ -70,7 +70,9 @@ def test_small_grids_and_odd_grids_keep_the_schedule_consistent():
 def test_uncovered_shapes_are_rejected_not_mangled():
     rc, _, msg = selftest(LLAMA3_8B, "F16")                           # F16 weights are not on the K-quant TMA path
     assert rc == 1 and "K-quant" in msg
-    rc, _, msg = selftest(LLAMA3_8B, "Q4_0")
+    rc, _, msg = selftest(LLAMA3_8B, "Q4_0")                          # Q4_0 is on the dp4a path of the persistent kernel
+    assert rc == 0, msg
+    rc, _, msg = selftest(LLAMA3_8B, "F32")
     assert rc == 1
     odd = LlamaConfig(vocab_size=512, hidden_size=512, intermediate_size=1024, n_layers=2, n_heads=6, n_kv_heads=2, head_dim=64, max_seq_len=128)
     rc, _, msg = selftest(odd, "Q4_K_M")                              # 3 query heads per KV head: attention not instantiated

@@ -209,3 +209,10 @@ def test_distributed_reduce_phase_single_rank(sim, tmp_path, fuse):
     every test above with tp > 1 already runs them); here at one rank, alone and with the quantiser/combine fusions."""
     check_against_oracle(sim, tmp_path, SMALL128, "Q4_K_M", steps=3, grid=5, copy_delay=4, fuse=fuse)
     check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=6, grid=1, fuse=fuse)      # a single CTA is a valid grid now
+
+
+def test_q4_0_blocks_on_the_dp4a_path(sim, tmp_path):
+    """Q4_0 (18-byte blocks, reference K1 gemm.cu:32-90) through process_stage<4>: the format the stand-alone GEMV still sends
+    to the generic kernel unless NT_B200_Q4_0_TMA=1."""
+    check_against_oracle(sim, tmp_path, TINY, "Q4_0", steps=4, grid=3, copy_delay=2)
+    check_against_oracle(sim, tmp_path, SMALL128, "Q4_0", steps=1, grid=8, fuse=3)
