@@ -1,5 +1,6 @@
 // cusim.cpp — scheduler of the CPU emulator (see cusim.h).  Test infrastructure.
 #include "cusim.h"
+#include <algorithm>
 #include <mutex>
 
 namespace cusim {
@@ -51,8 +52,20 @@ static bool run_cta(Cta& c, size_t stack_bytes) {
     }
     const double t0 = now_s();
     unsigned pass = 0;
+    // CUSIM_SHUFFLE=<seed>: visit the fibers in a fresh pseudo-random order every pass (warps interleave arbitrarily, later
+    // threads may run before earlier ones) to expose missing __syncthreads / __syncwarp that round-robin order would hide.
+    static const char* shuffle_env = getenv("CUSIM_SHUFFLE");
+    unsigned rs = shuffle_env ? (unsigned)atoi(shuffle_env) * 2654435761u + c.bid.x * 40503u + 1u : 0u;
+    const size_t nf = c.fibers.size();
     while (c.alive > 0) {
-        for (size_t i = 0; i < c.fibers.size(); i++) {
+        size_t start = 0, step = 1;
+        if (shuffle_env) {                                   // i -> (start + i * step) mod nf with step coprime to nf
+            rs = rs * 1664525u + 1013904223u;
+            start = (rs >> 8) % nf;
+            do { rs = rs * 1664525u + 1013904223u; step = 1 + (rs >> 8) % (nf - 1 ? nf - 1 : 1); } while (std::__gcd(step, nf) != 1);
+        }
+        for (size_t k = 0; k < nf; k++) {
+            const size_t i = (start + k * step) % nf;
             Fiber& f = c.fibers[i];
             if (f.done) continue;
             if (f.wait_addr && *f.wait_addr == f.wait_val) continue;

@@ -5,7 +5,9 @@ barriers, mbarrier parities, grid barriers, split attention with in-phase RoPE/K
 the tensor-parallel flag exchange — was debugged while no GPU was available.  It says nothing about the memory model, the
 hardware TMA path or speed; tests/test_mega_gpu.py covers the real thing."""
 import ctypes as C
+import os
 import subprocess
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -216,3 +218,15 @@ def test_q4_0_blocks_on_the_dp4a_path(sim, tmp_path):
     to the generic kernel unless NT_B200_Q4_0_TMA=1."""
     check_against_oracle(sim, tmp_path, TINY, "Q4_0", steps=4, grid=3, copy_delay=2)
     check_against_oracle(sim, tmp_path, SMALL128, "Q4_0", steps=1, grid=8, fuse=3)
+
+
+@pytest.mark.skipif(os.environ.get("CUSIM_SHUFFLE") is not None, reason="already running under a shuffled schedule")
+def test_results_do_not_depend_on_the_thread_schedule(sim):
+    """CUSIM_SHUFFLE: the emulator visits the threads of a CTA in a fresh pseudo-random order every scheduling pass, so a
+    missing __syncthreads / __syncwarp that in-order execution would hide shows up as a wrong result.  (The switch is read
+    once per process: run a slice of this file in a child.)"""
+    env = dict(os.environ, CUSIM_SHUFFLE="7")
+    r = subprocess.run([sys.executable, "-m", "pytest", str(Path(__file__)), "-x", "-q", "-k",
+                        "tiny_hd64 or producer_side_fusions or eight_way or fused_residual"], capture_output=True, text=True, env=env,
+                       cwd=str(ROOT), timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:]
