@@ -47,7 +47,8 @@ enum MegaPhaseKind : int { MPH_NORM_XQ = 0, MPH_QUANT = 1, MPH_GEMV = 2, MPH_ATT
 enum MegaBarrierKind : int { MBAR_NONE = 0, MBAR_GRID = 1, MBAR_EXCHANGE = 2 };
 enum MegaEpilogue : int { MEP_STORE = 0, MEP_SWIGLU = 2, MEP_SLOT = 3 };
 enum MegaFuse : int { MEGA_FUSE_QUANT = 1, MEGA_FUSE_COMBINE = 2, MEGA_FUSE_NORM = 4 /* single rank only */,
-                      MEGA_DEFER_RMS = 8 /* always on under tensor parallelism */ };
+                      MEGA_DEFER_RMS = 8 /* always on under tensor parallelism */,
+                      MEGA_OVERLAP_ATTN = 16 /* needs MEGA_FUSE_COMBINE: stream the o-projection's weights during attention */ };
 
 struct MegaMat {
     const uint8_t* W;
@@ -114,6 +115,8 @@ struct MegaParams {
     int n_splits_max;           // stride of the split dimension in attn_scratch
     int split_fixed;            // > 0: the graph path's rule (ctx cut into this many splits); 0: adaptive
     int min_split, max_split;   // adaptive rule: keys per split; max_split also sizes the score area in shared memory
+    int attn_smem_off;          // byte offset of the attention phase's scratch inside the dynamic shared memory (0 = aliases the rings)
+    int pad3_;
     unsigned* sync;             // MEGA_SYNC_WORDS words
     unsigned long long timeout_ns;
     int tp_rank, tp_size;
@@ -160,6 +163,7 @@ struct MegaPlan {
     int first_gemv = -1;
     int gc = 0;                     // query heads per attention unit
     int n_splits_max = 0, split_fixed = 0, min_split = 0, max_split = 0;
+    int attn_smem_off = 0;          // MEGA_OVERLAP_ATTN: the attention scratch sits above the (smaller) o-projection rings
     int fuse = 0;                   // MegaFuse bits in effect
 };
 // Pure host functions (no CUDA calls; unit-tested on the CPU through nt_b200_mega_selftest).

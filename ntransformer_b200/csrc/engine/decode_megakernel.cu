@@ -722,7 +722,7 @@ __device__ void attn_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
         const int k_begin = split * sr.split_len, k_end = min(ctx, k_begin + sr.split_len);
         // the unit that holds the token's own position writes the cache row; one writer per KV head
         const bool write_cache = (k_end == ctx) && (head0 % ratio == 0);
-        attend_unit<DPL, GC>(P, S, d, reinterpret_cast<float*>(smem), head0, kv_head, split, k_begin, k_end, pos, write_cache, grp, sr.used);
+        attend_unit<DPL, GC>(P, S, d, reinterpret_cast<float*>(smem + P.attn_smem_off), head0, kv_head, split, k_begin, k_end, pos, write_cache, grp, sr.used);
     }
 }
 
@@ -928,6 +928,17 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
     }
     pl.max_split = max_split;
     pl.split_fixed = split_fixed;
+    // MEGA_OVERLAP_ATTN: keep the attention scratch out of the way of the o-projection's (smaller) rings, so that those can
+    // be primed at the end of the q/k/v phase and HBM keeps streaming weights through the barrier and the attention phase.
+    const size_t attn_bytes = ((fixed + (size_t)gc * max_split * sizeof(float)) + 127) & ~(size_t)127;
+    size_t o_ring = MEGA_DYN_SMEM;
+    if ((fuse & MEGA_OVERLAP_ATTN) && (fuse & MEGA_FUSE_COMBINE) && attn_bytes + 4 * RG * BS * 144 <= MEGA_DYN_SMEM) {
+        pl.attn_smem_off = (int)(MEGA_DYN_SMEM - attn_bytes);
+        o_ring = (size_t)pl.attn_smem_off;
+    } else {
+        fuse &= ~MEGA_OVERLAP_ATTN;
+    }
+    pl.fuse = fuse;
 
     // ---- phase list ----
     const size_t ring = MEGA_DYN_SMEM;
@@ -938,7 +949,7 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
         return ph;
     };
     auto gemv_phase = [&](int layer, const MegaWeight* const* ws, float* const* ys, int n, int epilogue, const int8_t* xq,
-                          int slot_parity, MegaPhase* outp) -> bool {
+                          int slot_parity, MegaPhase* outp, size_t ring_budget = MEGA_DYN_SMEM) -> bool {
         MegaPhase ph = base_phase(MPH_GEMV, layer);
         GemvMat mats[3];
         int fmts[3];
@@ -959,7 +970,7 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
             if ((size_t)(NCq - 1) * BS * blk + (((size_t)last * blk + 15) & ~(size_t)15) > pitch) return false;   // 16-byte copy tail
         }
         if (epilogue == MEP_SWIGLU && (n != 2 || ws[0]->rows != ws[1]->rows)) return false;
-        const MegaGemvGeom g = mega_gemv_geom(fmts, n, K, ring);
+        const MegaGemvGeom g = mega_gemv_geom(fmts, n, K, ring_budget);
         if (!g.ok) return false;
         int total = 0;
         for (int i = 0; i < n; i++) {
@@ -1019,7 +1030,7 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
         if (!(fuse & MEGA_FUSE_COMBINE)) { ph = base_phase(MPH_COMBINE, l); plan.push_back(ph); }
         { const MegaWeight* ws[1] = {&L.wo}; float* ys[1] = {nullptr};
           if (L.wo.rows != hidden || L.wo.cols != qdim) return fail("attn_output shape");
-          if (!gemv_phase(l, ws, ys, 1, MEP_SLOT, B.xq_a, 0, &ph)) return fail("attn_output weight not on the K-quant TMA path");
+          if (!gemv_phase(l, ws, ys, 1, MEP_SLOT, B.xq_a, 0, &ph, o_ring)) return fail("attn_output weight not on the K-quant TMA path");
           ph.barrier = MBAR_EXCHANGE;
           if (fnorm) fold_norm(ph, L.ffn_norm); else pending = 0;
           plan.push_back(ph); }
@@ -1055,11 +1066,13 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
     // ring priming: at the end of a phase, start the next GEMV phase's weight stream unless an attention phase (which
     // aliases the ring area) still lies in between; the attention phase itself primes the GEMV that follows it.
     pl.first_gemv = -1;
+    const bool overlap = (pl.fuse & MEGA_OVERLAP_ATTN) != 0;
     for (int i = 0; i < (int)plan.size(); i++) {
         if (plan[i].kind == MPH_GEMV && pl.first_gemv < 0) pl.first_gemv = i;
         if (plan[i].kind != MPH_GEMV && plan[i].kind != MPH_ATTN) continue;
+        if (plan[i].kind == MPH_ATTN && overlap) continue;       // its successor was primed by the q/k/v phase already
         for (int j = i + 1; j < (int)plan.size(); j++) {
-            if (plan[j].kind == MPH_ATTN) break;
+            if (plan[j].kind == MPH_ATTN && !overlap) break;
             if (plan[j].kind == MPH_GEMV) { plan[i].prime = j; break; }
         }
     }
@@ -1153,7 +1166,13 @@ std::string mega_check_plan(const MegaPlan& pl, int grid, int tp_size) {
             } else if (d.barrier == MBAR_EXCHANGE) return "exchange barrier after a non-slot phase";
 
         } else if (d.kind == MPH_ATTN) {
-            if (primed >= 0) { snprintf(msg, sizeof(msg), "attention phase %d would overwrite rings primed for %d", i, primed); return msg; }
+            if (primed >= 0) {                                   // allowed only when the scratch sits above the primed rings
+                const MegaPhase& g = ph[(size_t)primed];
+                if (pl.attn_smem_off <= 0 || (size_t)g.warps * g.stages * g.slot_bytes > (size_t)pl.attn_smem_off) {
+                    snprintf(msg, sizeof(msg), "attention phase %d would overwrite rings primed for %d", i, primed);
+                    return msg;
+                }
+            }
         } else if (d.kind == MPH_NORM_XQ || d.kind == MPH_REDUCE_XQ) {
             if (stream && d.hid_in != stream) { snprintf(msg, sizeof(msg), "norm phase %d does not read the current residual stream", i); return msg; }
             if (d.pending_parity != pending) { snprintf(msg, sizeof(msg), "norm phase %d: pending parity %d, expected %d", i, d.pending_parity, pending); return msg; }
@@ -1169,7 +1188,9 @@ std::string mega_check_plan(const MegaPlan& pl, int grid, int tp_size) {
             if (d.prime <= i || d.prime >= n || ph[(size_t)d.prime].kind != MPH_GEMV) return "prime target is not a later GEMV phase";
             if (d.prime > i + 2) return "prime target beyond the descriptor prefetch window (i + 2)";
             if (primed >= 0) return "rings primed twice";
-            for (int j = i + 1; j < d.prime; j++) if (ph[(size_t)j].kind == MPH_ATTN || ph[(size_t)j].kind == MPH_GEMV) return "phases between a prime and its GEMV touch the rings";
+            for (int j = i + 1; j < d.prime; j++)
+                if (ph[(size_t)j].kind == MPH_GEMV || (ph[(size_t)j].kind == MPH_ATTN && pl.attn_smem_off <= 0))
+                    return "phases between a prime and its GEMV touch the rings";
             primed = d.prime;
         }
     }
@@ -1237,6 +1258,7 @@ bool DecodeMega::build(const MegaModelView& mv) {
     p_.step = mv.step;
     p_.q = q_; p_.k = k_; p_.v = v_; p_.attn_out = attn_; p_.attn_scratch = scratch_; p_.xq_a = xq_a_;
     p_.n_splits_max = plan_.n_splits_max; p_.split_fixed = plan_.split_fixed; p_.min_split = plan_.min_split; p_.max_split = plan_.max_split;
+    p_.attn_smem_off = plan_.attn_smem_off;
     p_.sync = sync_;
     p_.timeout_ns = 2000000000ull;
     if (const char* t = getenv("NT_B200_MEGA_TIMEOUT_MS")) p_.timeout_ns = (unsigned long long)atoll(t) * 1000000ull;

@@ -154,6 +154,7 @@ void* mega_sim_create(const char* gguf_path, int max_seq, int tp_size, int grid,
         P.step = R.step.as<int>();
         P.q = B.q; P.k = B.k; P.v = B.v; P.attn_out = R.attn.as<float>(); P.attn_scratch = R.scratch.as<float>(); P.xq_a = B.xq_a;
         P.n_splits_max = R.plan.n_splits_max; P.split_fixed = R.plan.split_fixed; P.min_split = R.plan.min_split; P.max_split = R.plan.max_split;
+        P.attn_smem_off = R.plan.attn_smem_off;
         P.sync = R.sync.as<unsigned>();
         P.timeout_ns = 60ull * 1000000000ull;
         P.tp_rank = r; P.tp_size = tp_size;

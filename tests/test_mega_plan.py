@@ -92,3 +92,11 @@ def test_fusion_flags_shorten_the_program():
     assert info[1] == 5 * L + 1 and info[0] == info[1] + 1 and info[2] == 4 * L + 1
     rc, info, msg = selftest(LLAMA3_8B, "Q4_K_M", fuse=4)
     assert rc == 0 and info[1] == 7 * LLAMA3_8B.n_layers + 1, msg
+
+
+def test_overlap_flag_keeps_the_plan_consistent_at_benchmark_shapes():
+    for cfg in (LLAMA3_70B, LLAMA3_8B):
+        for tp in (1, 8):
+            rc, info, msg = selftest(cfg, "Q4_K_M", 0, tp, fuse=31)
+            assert rc == 0, (cfg.hidden_size, tp, msg)
+            assert info[3] >= 4 and info[4] >= 2           # the o-projection keeps >= 4 warps and a double-buffered ring

@@ -220,6 +220,26 @@ def test_q4_0_blocks_on_the_dp4a_path(sim, tmp_path):
     check_against_oracle(sim, tmp_path, SMALL128, "Q4_0", steps=1, grid=8, fuse=3)
 
 
+@pytest.mark.parametrize("fuse", [18, 31])
+def test_weights_stream_through_the_attention_phase(sim, tmp_path, fuse):
+    """MEGA_OVERLAP_ATTN (16, with the fused combine): the attention scratch sits above the o-projection's smaller rings, which
+    are primed at the end of the q/k/v phase — TMA copies land in shared memory while the attention phase computes next to them."""
+    check_against_oracle(sim, tmp_path, SMALL128, "Q4_K_M", steps=3, grid=8, copy_delay=9, fuse=fuse)
+    check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=4, tp=2, grid=3, copy_delay=5, fuse=fuse, tol=5e-4)
+    cfg = LlamaConfig(**{**TINY.dict(), "n_layers": 1, "max_seq_len": 160})      # contexts of 2-3 splits
+    path, host = make_case(tmp_path, cfg, "Q4_K")
+    om = O.Model(cfg.dict(), host)
+    m = SimModel(sim, path, cfg, host, grid=4, fuse=fuse, copy_delay=6)
+    rng = np.random.default_rng(2)
+    for pos, t in enumerate(int(t) for t in rng.integers(3, cfg.vocab_size, size=131)):
+        head = pos in (0, 64, 65, 130)
+        got = m.step(t, pos, with_head=head)
+        want = om.forward([t], pos)
+        if head:
+            assert rel(got, want) <= 2e-4, pos
+    m.close()
+
+
 @pytest.mark.skipif(os.environ.get("CUSIM_SHUFFLE") is not None, reason="already running under a shuffled schedule")
 def test_results_do_not_depend_on_the_thread_schedule(sim):
     """CUSIM_SHUFFLE: the emulator visits the threads of a CTA in a fresh pseudo-random order every scheduling pass, so a
