@@ -250,3 +250,24 @@ def test_results_do_not_depend_on_the_thread_schedule(sim):
                         "tiny_hd64 or producer_side_fusions or eight_way or fused_residual"], capture_output=True, text=True, env=env,
                        cwd=str(ROOT), timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+@pytest.mark.skipif(_mem_available_gb() < 24 and os.environ.get("NT_B200_SIM_FULLSIZE") != "1",
+                    reason="one Llama-3 70B layer on 148 emulated CTAs needs ~8 GB of fiber stacks (NT_B200_SIM_FULLSIZE=1 forces it)")
+def test_one_70b_layer_on_148_ctas(sim, tmp_path):
+    """Production geometry: hidden 8192, 64 query / 8 KV heads, intermediate 28672 (7 chunks per down-projection row), Q4_K_M
+    mix, 148 CTAs x 384 threads — one layer, small vocabulary."""
+    cfg = LlamaConfig(vocab_size=1024, hidden_size=8192, intermediate_size=28672, n_layers=1, n_heads=64, n_kv_heads=8, head_dim=128,
+                      max_seq_len=64, bos_token_id=1, eos_token_id=2)
+    for fuse in (0, 31):
+        check_against_oracle(sim, tmp_path, cfg, "Q6_K" if fuse == 0 else "Q4_K", steps=1, grid=148, copy_delay=3, fuse=fuse)
