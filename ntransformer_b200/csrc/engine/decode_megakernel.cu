@@ -86,7 +86,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // caller issues one system fence after all of its peers have arrived); otherwise acquire loads at GPU scope.  A time-out (or
 // an abort raised elsewhere) sets the abort word and returns: every later barrier then falls through and the host reports it.
 template <bool SYS>
-__device__ NT_NOINLINE void spin_until(const unsigned* p, unsigned target, unsigned* abort_word, unsigned long long timeout_ns) {
+__device__ NT_NOINLINE void spin_until(const unsigned* p, unsigned target, unsigned* abort_word, unsigned long long timeout_ns, unsigned tag) {
     if (ld_relaxed_gpu(abort_word)) return;
     const unsigned long long t0 = global_timer_ns();
     unsigned n = 0;
@@ -95,7 +95,15 @@ __device__ NT_NOINLINE void spin_until(const unsigned* p, unsigned target, unsig
         if ((int)(v - target) >= 0) return;
         if ((++n & 255u) == 0) {
             if (ld_relaxed_gpu(abort_word)) return;
-            if (global_timer_ns() - t0 > timeout_ns) { atomicExch(abort_word, 1u + (SYS ? 1u : 0u)); return; }
+            if (global_timer_ns() - t0 > timeout_ns) {
+                if (atomicExch(abort_word, 1u + (SYS ? 1u : 0u)) == 0u) {    // first to give up: leave a note for the host
+                    abort_word[1] = tag;                                      // barrier index of this launch
+                    abort_word[2] = blockIdx.x;
+                    abort_word[3] = target;
+                    abort_word[4] = SYS ? ld_relaxed_sys(p) : ld_relaxed_gpu(p);
+                }
+                return;
+            }
         }
     }
 }
@@ -125,19 +133,19 @@ __device__ void mega_barrier(const MegaParams& P, int kind, SyncState& st) {
         if (xchg) {
             const unsigned seq = st.xchg_base + st.xchg_idx;
             if (blockIdx.x == 0) {
-                spin_until<false>(counter, target, abort_word, P.timeout_ns);       // every local CTA has pushed its rows
+                spin_until<false>(counter, target, abort_word, P.timeout_ns, st.bar_idx);       // every local CTA has pushed its rows
                 __threadfence_system();                                             // ... before the flags become visible
                 for (int r = 0; r < P.tp_size; r++)
                     if (r != P.tp_rank) st_relaxed_sys(P.flags[r] + 32 * P.tp_rank, seq);      // posted NVLink writes
                 for (int r = 0; r < P.tp_size; r++)
-                    if (r != P.tp_rank) spin_until<true>(P.flags[P.tp_rank] + 32 * r, seq, abort_word, P.timeout_ns);   // local polls
+                    if (r != P.tp_rank) spin_until<true>(P.flags[P.tp_rank] + 32 * r, seq, abort_word, P.timeout_ns, st.bar_idx);   // local polls
                 __threadfence_system();                                             // acquire side: the peers' rows are visible
                 st_release_gpu(go, st.bar_idx);
             } else {
-                spin_until<false>(go, st.bar_idx, abort_word, P.timeout_ns);
+                spin_until<false>(go, st.bar_idx, abort_word, P.timeout_ns, st.bar_idx);
             }
         } else {
-            spin_until<false>(counter, target, abort_word, P.timeout_ns);
+            spin_until<false>(counter, target, abort_word, P.timeout_ns, st.bar_idx);
         }
     }
     __syncthreads();
@@ -1300,6 +1308,8 @@ void DecodeMega::launch(bool with_head, cudaStream_t s) {
     NT_CUDA_CHECK(cudaMemsetAsync(sync_, 0, 64 * sizeof(unsigned), s));
     MegaParams p = p_;
     p.n_phases = n_phases(with_head);
+    if (const char* mp = getenv("NT_B200_MEGA_MAX_PHASES"))      // bisect aid: stop after k phases, then nt_model_debug_read
+        p.n_phases = std::max(1, std::min(p.n_phases, atoi(mp)));
     p.trace = trace_on_ ? trace_ : nullptr;     // laid out for the full program; a body-only launch fills a prefix per CTA
     p.trace_stride = (int)plan_.phases.size() * 3;
     cudaLaunchConfig_t cfg{};
@@ -1324,10 +1334,11 @@ size_t DecodeMega::read_trace(unsigned long long* out_host, size_t cap) const {
 }
 
 void DecodeMega::check_abort() {
-    unsigned v = 0;
-    NT_CUDA_CHECK(cudaMemcpy(&v, sync_ + 64, sizeof(unsigned), cudaMemcpyDeviceToHost));
-    if (v) {
-        fprintf(stderr, "decode_step_kernel: a %s barrier timed out (abort word %u)\n", v == 2 ? "tensor-parallel exchange" : "grid", v);
+    unsigned v[5] = {0, 0, 0, 0, 0};
+    NT_CUDA_CHECK(cudaMemcpy(v, sync_ + 64, sizeof(v), cudaMemcpyDeviceToHost));
+    if (v[0]) {
+        fprintf(stderr, "decode_step_kernel (rank %d): a %s wait timed out at barrier #%u of the launch, CTA %u: waiting for %u, saw %u\n", tp_rank_,
+                v[0] == 2 ? "tensor-parallel exchange" : "grid-barrier", v[1], v[2], v[3], v[4]);
         NT_CHECK(false, "decode megakernel aborted");
     }
 }

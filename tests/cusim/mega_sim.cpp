@@ -188,7 +188,13 @@ int mega_sim_step(void* h, const float* embed_row, int token, int pos, int with_
         memset(R.sync.ptr, 0, 64 * 4);                                   // DecodeMega::launch's cudaMemsetAsync
         R.P.n_phases = with_head ? (int)R.plan.phases.size() : R.plan.n_body;
     }
+    // fault injection for the time-out test: one rank never launches (its peers must give up, not hang)
+    const char* skip_env = getenv("CUSIM_MEGA_SKIP_RANK");
+    const int skip_rank = skip_env ? atoi(skip_env) : -1;
+    const char* to_env = getenv("CUSIM_MEGA_TIMEOUT_MS");
     for (int r = 0; r < S.tp; r++) {
+        if (to_env) S.ranks[(size_t)r]->P.timeout_ns = (unsigned long long)atoll(to_env) * 1000000ull;
+        if (r == skip_rank) continue;
         th.emplace_back([&, r]() {
             Rank& R = *S.ranks[(size_t)r];
             const MegaParams P = R.P;

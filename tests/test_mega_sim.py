@@ -240,6 +240,20 @@ def test_weights_stream_through_the_attention_phase(sim, tmp_path, fuse):
     m.close()
 
 
+def test_a_missing_peer_times_out_instead_of_hanging(sim, tmp_path, monkeypatch):
+    """Rank 1 never launches: rank 0's master CTA gives up on the flag after the time-out, raises the abort word, every later
+    barrier falls through and the launch ends (the host then reports 'decode megakernel aborted')."""
+    path, host = make_case(tmp_path, TINY, "Q4_K")
+    m = SimModel(sim, path, TINY, host, tp=2, grid=3)
+    monkeypatch.setenv("CUSIM_MEGA_SKIP_RANK", "1")
+    monkeypatch.setenv("CUSIM_MEGA_TIMEOUT_MS", "200")
+    row = np.ascontiguousarray(m.table[1], dtype=np.float32)
+    out = np.zeros(TINY.vocab_size, dtype=np.float32)
+    rc = sim.mega_sim_step(m.h, row.ctypes.data_as(C.c_void_p), 1, 0, 1, out.ctypes.data_as(C.c_void_p))
+    assert rc == 2                                       # the abort word, not the emulator's watchdog (1) and not success
+    m.close()
+
+
 @pytest.mark.skipif(os.environ.get("CUSIM_SHUFFLE") is not None, reason="already running under a shuffled schedule")
 def test_results_do_not_depend_on_the_thread_schedule(sim):
     """CUSIM_SHUFFLE: the emulator visits the threads of a CTA in a fresh pseudo-random order every scheduling pass, so a
