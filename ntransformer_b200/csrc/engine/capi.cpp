@@ -79,7 +79,7 @@ int nt_model_forward_async(nt_model_t m, const int* tokens, int n, int start_pos
     H(m)->model.forward_async(tokens, n, start_pos);
     return 0;
 }
-int nt_model_sync(nt_model_t m) { return m ? (int)cudaStreamSynchronize(H(m)->model.stream()) : -1; }
+int nt_model_sync(nt_model_t m) { return m ? H(m)->model.sync() : -1; }
 float* nt_model_logits_device(nt_model_t m) { return m ? H(m)->model.logits_device() : nullptr; }
 void* nt_model_stream(nt_model_t m) { return m ? (void*)H(m)->model.stream() : nullptr; }
 int nt_model_argmax(nt_model_t m) { return m ? H(m)->model.argmax_last() : -1; }

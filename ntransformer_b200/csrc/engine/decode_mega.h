@@ -191,7 +191,9 @@ public:
     // Enqueues [reset of the barrier words] + the kernel.  Capturable in a CUDA graph.
     void launch(bool with_head, cudaStream_t s);
     int launches_per_step() const { return 1; }
-    // Raises (NT_CHECK) when a spin inside the kernel timed out.  Call after synchronising the stream.
+    // Raises (NT_CHECK) when a spin inside the kernel timed out.  enqueue_abort_read copies the abort words to pinned host memory
+    // on the stream (no extra synchronisation); check_abort inspects that copy after the caller has synchronised the stream.
+    void enqueue_abort_read(cudaStream_t s);
     void check_abort();
 
     // Tensor parallel: exchange of the IPC handle of the slot/flag allocation (64 bytes per rank).
@@ -224,6 +226,7 @@ private:
     int split_fixed_ = 0, fuse_ = 0;
     unsigned *cnt_quant_ = nullptr, *cnt_attn_ = nullptr, *cnt_norm_ = nullptr;
     unsigned long long* trace_ = nullptr;
+    unsigned* abort_host_ = nullptr;   // pinned copy of the abort words
     bool trace_on_ = false;
     float* ssq_ = nullptr;
     bool peers_ready_ = false;

@@ -1210,6 +1210,7 @@ std::string mega_check_plan(const MegaPlan& pl, int grid, int tp_size) {
 #ifndef NT_CUSIM   // everything below talks to the CUDA runtime; the CPU emulation (tests/cusim) stops here
 
 DecodeMega::~DecodeMega() {
+    if (abort_host_) cudaFreeHost(abort_host_);
     for (size_t r = 0; r < peer_maps_.size(); r++)
         if (peer_maps_[r] && (int)r != tp_rank_) cudaIpcCloseMemHandle(peer_maps_[r]);
     for (void* p : {(void*)phases_dev_, (void*)hid_[0], (void*)hid_[1], (void*)q_, (void*)k_, (void*)v_, (void*)attn_, (void*)act_,
@@ -1333,9 +1334,14 @@ size_t DecodeMega::read_trace(unsigned long long* out_host, size_t cap) const {
     return n;
 }
 
+void DecodeMega::enqueue_abort_read(cudaStream_t s) {
+    if (!abort_host_) { NT_CUDA_CHECK(cudaMallocHost(&abort_host_, 8 * sizeof(unsigned))); memset(abort_host_, 0, 8 * sizeof(unsigned)); }
+    NT_CUDA_CHECK(cudaMemcpyAsync(abort_host_, sync_ + 64, 5 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+}
+
 void DecodeMega::check_abort() {
-    unsigned v[5] = {0, 0, 0, 0, 0};
-    NT_CUDA_CHECK(cudaMemcpy(v, sync_ + 64, sizeof(v), cudaMemcpyDeviceToHost));
+    if (!abort_host_) return;
+    const unsigned* v = abort_host_;
     if (v[0]) {
         fprintf(stderr, "decode_step_kernel (rank %d): a %s wait timed out at barrier #%u of the launch, CTA %u: waiting for %u, saw %u\n", tp_rank_,
                 v[0] == 2 ? "tensor-parallel exchange" : "grid-barrier", v[1], v[2], v[3], v[4]);

@@ -570,18 +570,23 @@ void Model::forward_async(const int* tokens, int seq_len, int start_pos) {
     }
 }
 
+int Model::sync() {
+    if (mega_) mega_->enqueue_abort_read(stream_);
+    const cudaError_t e = cudaStreamSynchronize(stream_);
+    if (e == cudaSuccess && mega_) mega_->check_abort();
+    return (int)e;
+}
+
 float* Model::forward(const int* tokens, int seq_len, int start_pos) {
     forward_async(tokens, seq_len, start_pos);
-    NT_CUDA_CHECK(cudaStreamSynchronize(stream_));                           // transformer.cpp:667
-    if (mega_) mega_->check_abort();
+    NT_CUDA_CHECK((cudaError_t)sync());                                      // transformer.cpp:667
     return logits_;
 }
 
 int Model::argmax_last() {
     argmax_kernel<<<1, 1024, 0, stream_>>>(logits_, cfg_.vocab_size, argmax_dev_);
     NT_CUDA_CHECK(cudaMemcpyAsync(argmax_host_, argmax_dev_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
-    if (mega_) mega_->check_abort();
+    NT_CUDA_CHECK((cudaError_t)sync());
     return *argmax_host_;
 }
 
@@ -596,8 +601,7 @@ int Model::sample_last(float temperature, int top_k, float top_p, float repeat_p
     NT_CHECK(sample_topk(logits_, cfg_.vocab_size, temperature, top_k, top_p, repeat_penalty, recent_dev_, n_window, r, argmax_dev_, stream_),
              "sample_topk rejected supported settings");
     NT_CUDA_CHECK(cudaMemcpyAsync(argmax_host_, argmax_dev_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
-    if (mega_) mega_->check_abort();
+    NT_CUDA_CHECK((cudaError_t)sync());
     return *argmax_host_;
 }
 

@@ -58,6 +58,7 @@ public:
     void forward_async(const int* tokens, int seq_len, int start_pos);
     // Greedy next token computed on the GPU from the last logits (argmax, lowest index on ties like Sampler::argmax).
     int argmax_last();
+    int sync();                            // waits for the model's stream: returns the cudaError_t; reports a persistent-kernel time-out
     // Samples the next token from the last logits on the GPU (csrc/sample.cu; penalty is applied in place to the device
     // logits).  recent_window: the ids the repeat penalty looks at, oldest first.  Returns -1 when the settings are not
     // covered (top_k <= 0, > 1024 or >= vocab, temperature <= 0): the caller samples on the host.
