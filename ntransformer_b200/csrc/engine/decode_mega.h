@@ -1,8 +1,9 @@
 // decode_mega.h — the whole decode step (all layers of one token) as ONE persistent kernel.
 //
-// STATUS: written at the end of round 1 after the round's GPU budget was spent.  It compiles for sm_100a and its
-// host-side plan is unit-tested on the CPU, but it has NOT run on hardware yet: it is opt-in
-// (NT_B200_MEGAKERNEL=1 or nt_model_use_megakernel) and the graph of fused launches in model.cu stays the default.
+// STATUS: written at the end of round 1 after the round's GPU budget was spent.  It compiles for sm_100a, its host-side
+// plan is unit-tested on the CPU and its device code runs — as is, compiled with g++ — on a CPU emulator against the oracle
+// (tests/cusim, tests/test_mega_sim.py), but it has NOT run on hardware yet: it is opt-in (NT_B200_MEGAKERNEL=1 or
+// nt_model_use_megakernel) and the graph of fused launches in model.cu stays the default.
 //
 // Why: profiles/r01_launches_70b_summary.txt — the per-layer launches of the decode graph (reference:
 // Attention::forward attention.cpp:120-211, FFN::forward ffn.cpp:85-134, called from transformer.cpp:604-669) cost

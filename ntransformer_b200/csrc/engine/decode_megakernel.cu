@@ -9,6 +9,12 @@
 //                   rotary.cu:16-62, attention.cu:316-342, attention.cu:108-202)
 //   MPH_COMBINE  <- decode_combine_kernel  (attention.cu)
 // Compiled with --use_fast_math like those files so the transcendental expressions lower to the same instructions.
+// Beyond the transplant (all optional, MegaFuse bits in decode_mega.h): last-arriver fusions of the activation quantiser, the
+// split combine and (one rank) the residual add + next norm into their producers; MPH_REDUCE_XQ, the distributed form of the
+// norm phase with the 1/rms factor applied by the consumer (always used under tensor parallelism); weight prefetch across the
+// attention phase.  File layout: memory-model helpers and barriers, the GEMV phase (producer cursor shared with the host-side
+// schedule check), norm / quantise / reduce phases, attention, the kernel, then the pure host functions (plan builder and
+// checkers, also compiled for the CPU emulator in tests/cusim) and, last, the CUDA-runtime-facing DecodeMega class.
 #include "decode_mega.h"
 #include "../ring.cuh"
 #include "../xquant.cuh"
