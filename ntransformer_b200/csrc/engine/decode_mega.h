@@ -49,7 +49,8 @@ enum MegaBarrierKind : int { MBAR_NONE = 0, MBAR_GRID = 1, MBAR_EXCHANGE = 2 };
 enum MegaEpilogue : int { MEP_STORE = 0, MEP_SWIGLU = 2, MEP_SLOT = 3 };
 enum MegaFuse : int { MEGA_FUSE_QUANT = 1, MEGA_FUSE_COMBINE = 2, MEGA_FUSE_NORM = 4 /* single rank only */,
                       MEGA_DEFER_RMS = 8 /* always on under tensor parallelism */,
-                      MEGA_OVERLAP_ATTN = 16 /* needs MEGA_FUSE_COMBINE: stream the o-projection's weights during attention */ };
+                      MEGA_OVERLAP_ATTN = 16 /* needs MEGA_FUSE_COMBINE: stream the o-projection's weights during attention */,
+                      MEGA_SPLIT_TAIL = 32 /* cut a partly filled last round into 1- or 2-row stages spread over all warp slots */ };
 
 struct MegaMat {
     const uint8_t* W;
@@ -72,6 +73,7 @@ struct MegaPhase {
     int n_mat, K, NB, NC;
     int n_seg, total_groups, epilogue, warps;
     int gpc, stages, slot_bytes, slot_parity;
+    int n_rounds, full_rounds, tail_groups, tail_nr;   // lock-step rounds; the last one may be cut into tail_nr-row stages (MEGA_SPLIT_TAIL)
     const int8_t* xq;           // pre-quantised activations (kernels_internal.h "xq")
     // ---- MPH_NORM_XQ: h = hid_in (+ sum_r slot[pending_parity][r]);  hid_out <- h;  xq_out <- quantise(rmsnorm(h) * norm_w)
     //      MPH_QUANT:   xq_out <- quantise(x[0..n))

@@ -184,12 +184,9 @@ __device__ __forceinline__ void load_phase(MegaPhase* dst, const MegaPhase* src)
 // chunk (w % NC) of row-group slot (w / NC).  Flattened stage index = round * n_seg + seg.
 struct Producer {
     int issued;        // stages issued so far in the phase (uniform across the warp)
-    int p_g, p_seg;    // row-group and segment of the next stage to fetch
+    int round, seg;    // round and segment of the next stage to fetch
 };
 
-__host__ __device__ __forceinline__ int phase_rounds(const MegaPhase& d, int grid) {
-    return (d.total_groups + grid * d.gpc - 1) / (grid * d.gpc);
-}
 __host__ __device__ __forceinline__ int blk_bytes(int fmt) { return fmt == 1 ? 176 : fmt == 2 ? 210 : fmt == 3 ? 272 : 144; }   // 0 Q4_K, 4 Q4_0: 144
 
 __host__ __device__ __forceinline__ void locate(const MegaPhase& d, int g, int seg, int& mi, int& gl) {
@@ -199,75 +196,86 @@ __host__ __device__ __forceinline__ void locate(const MegaPhase& d, int g, int s
     gl = g;
 }
 
-// What one ring stage holds: RG rows of chunk `chunk` of row-group gl of matrix mi (shared by the device producer and the
-// host-side schedule check).
+// What the stage (round, seg) of warp slot (cta, gsub) holds: nrows rows, starting at row0, of chunk `chunk` of matrix mi.
+// The one function both the device producer, the device consumer and the host-side schedule check derive the schedule from.
+//   full rounds:  row-group (round * grid + cta) * gpc + gsub, all RG rows;
+//   tail round (MEGA_SPLIT_TAIL, tail_nr < RG): the remaining tail_groups row-groups are dealt out tail_nr rows at a time over
+//   the slots in slot order, so a partly filled last round costs tail_nr / RG of a round instead of a whole one.
 struct StageRef {
-    bool empty;            // beyond the last row-group: the stage only completes its mbarrier phase
-    int mi, gl, row0;
+    bool empty;            // nothing to do: the stage only completes its mbarrier phase
+    int mi, gl, row0, nrows;
     int blkb;              // bytes per 256 weights of the matrix's format
     uint32_t bytes;        // bytes copied per row (multiple of 16)
     long long src_off;     // offset of row row0's part inside the matrix
 };
-__host__ __device__ __forceinline__ StageRef stage_ref(const MegaPhase& d, int p_g, int p_seg, int chunk, int nbc) {
+__host__ __device__ __forceinline__ StageRef stage_ref(const MegaPhase& d, int grid, int cta, int gsub, int round, int seg, int chunk,
+                                                       int nbc) {
     StageRef r;
-    r.empty = p_g >= d.total_groups;
-    r.mi = 0; r.gl = 0; r.row0 = 0; r.blkb = 0; r.bytes = 0; r.src_off = 0;
-    if (r.empty) return r;
-    locate(d, p_g, p_seg, r.mi, r.gl);
-    r.blkb = blk_bytes(d.mat[r.mi].fmt);
+    r.empty = true; r.mi = 0; r.gl = 0; r.row0 = 0; r.nrows = RG; r.blkb = 0; r.bytes = 0; r.src_off = 0;
+    int g, row_sub = 0, nr = RG;
+    if (round < d.full_rounds || d.tail_nr >= RG) {
+        g = (round * grid + cta) * d.gpc + gsub;
+        if (g >= d.total_groups) return r;
+    } else {
+        nr = d.tail_nr;
+        const int per = RG / nr, u = cta * d.gpc + gsub;
+        if (u >= d.tail_groups * per) return r;
+        g = d.full_rounds * grid * d.gpc + u / per;
+        row_sub = u % per;
+    }
+    locate(d, g, seg, r.mi, r.gl);
+    const MegaMat& m = d.mat[r.mi];
+    r.row0 = r.gl * RG + row_sub * nr;
+    if (r.row0 >= m.out) return r;                           // a slice of a ragged last group that holds no row
+    r.empty = false;
+    r.nrows = nr;
+    r.blkb = blk_bytes(m.fmt);
     r.bytes = ((uint32_t)(nbc * r.blkb) + 15u) & ~15u;       // a 210-byte tail may spill into row padding (host-checked)
-    r.row0 = r.gl * RG;
-    r.src_off = (long long)chunk * (BS * r.blkb) + (long long)r.row0 * d.mat[r.mi].pitch;
+    r.src_off = (long long)chunk * (BS * r.blkb) + (long long)r.row0 * m.pitch;
     return r;
 }
-__host__ __device__ __forceinline__ void producer_advance(const MegaPhase& d, Producer& pr, int grid) {
-    if (++pr.p_seg == d.n_seg) { pr.p_seg = 0; pr.p_g += grid * d.gpc; }
+__host__ __device__ __forceinline__ void producer_advance(const MegaPhase& d, Producer& pr) {
+    if (++pr.seg == d.n_seg) { pr.seg = 0; pr.round++; }
 }
 
 // Lane 0 of an active warp: TMA copies of the producer's next stage into ring slot `slot`; every lane advances the cursor.
 __device__ __forceinline__ void issue_next(const MegaPhase& d, Producer& pr, uint8_t* ring, uint64_t* bars, int slot, int chunk,
-                                           int nbc, int lane) {
+                                           int gsub, int nbc, int lane) {
     if (lane == 0) {
         uint64_t* bar = bars + slot;
-        const StageRef sr = stage_ref(d, pr.p_g, pr.p_seg, chunk, nbc);
+        const StageRef sr = stage_ref(d, (int)gridDim.x, (int)blockIdx.x, gsub, pr.round, pr.seg, chunk, nbc);
         if (sr.empty) {
             mbar_expect_tx(bar, 0);                          // nothing to fetch: just complete the phase
         } else {
             const MegaMat& m = d.mat[sr.mi];
-            mbar_expect_tx(bar, sr.bytes * RG);
+            mbar_expect_tx(bar, sr.bytes * sr.nrows);
             uint8_t* dst = ring + (size_t)slot * d.slot_bytes;
             const uint8_t* src = m.W + sr.src_off;
-            if (sr.row0 + RG <= m.out) {
-#pragma unroll
-                for (int r = 0; r < RG; r++) bulk_g2s(dst + r * (BS * sr.blkb), src + r * m.pitch, sr.bytes, bar);
-            } else {                                         // ragged last group: re-read the last valid row
-#pragma unroll
-                for (int r = 0; r < RG; r++)
-                    bulk_g2s(dst + r * (BS * sr.blkb), src + (long long)min(r, m.out - 1 - sr.row0) * m.pitch, sr.bytes, bar);
-            }
+            const int last = m.out - 1 - sr.row0;            // rows past the end of a ragged group re-read the last valid row
+            for (int r = 0; r < sr.nrows; r++)
+                bulk_g2s(dst + r * (BS * sr.blkb), src + (long long)min(r, last) * m.pitch, sr.bytes, bar);
         }
     }
-    producer_advance(d, pr, (int)gridDim.x);
+    producer_advance(d, pr);
 }
 
 // Start streaming the weights of GEMV phase `d` (already in shared memory): fill this warp's ring.
 __device__ __forceinline__ void prime_rings(const MegaPhase& d, Producer& pr, uint8_t* smem, uint64_t* bars_all, int warp, int lane) {
-    pr.issued = 0; pr.p_g = 0; pr.p_seg = 0;
+    pr.issued = 0; pr.round = 0; pr.seg = 0;
     if (warp >= d.warps) return;
     const int chunk = warp % d.NC, gsub = warp / d.NC;
     const int nbc = min(BS, d.NB - chunk * BS);
     uint8_t* ring = smem + (size_t)warp * d.stages * d.slot_bytes;
     uint64_t* bars = bars_all + warp * MEGA_MAX_STAGES;
-    pr.p_g = (int)blockIdx.x * d.gpc + gsub;
-    const int n_total = phase_rounds(d, (int)gridDim.x) * d.n_seg;
+    const int n_total = d.n_rounds * d.n_seg;
     if (lane == 0) fence_proxy_async_smem();                 // the ring area may have been written by generic-proxy stores
-    for (; pr.issued < d.stages && pr.issued < n_total; pr.issued++) issue_next(d, pr, ring, bars, pr.issued, chunk, nbc, lane);
+    for (; pr.issued < d.stages && pr.issued < n_total; pr.issued++) issue_next(d, pr, ring, bars, pr.issued, chunk, gsub, nbc, lane);
 }
 
 // ---- GEMV phase: consumer ------------------------------------------------------------------------------------------------
 __device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, uint8_t* smem, Producer& pr, uint32_t& parity_bits,
                            int warp, int lane) {
-    const int n_rounds = phase_rounds(d, (int)gridDim.x);
+    const int n_rounds = d.n_rounds;
     float rms_inv = 1.0f;
     if (d.ssq_in) {
         // MEGA_FUSE_NORM consumer: the activations were quantised as h * norm_w; the missing 1/rms factor is a scalar of the
@@ -285,7 +293,7 @@ __device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
         for (int round = 0; round < n_rounds; round++) __syncthreads();
         return;
     }
-    const int K = d.K, NC = d.NC, n_seg = d.n_seg, gpc = d.gpc, stages = d.stages;
+    const int K = d.K, NC = d.NC, n_seg = d.n_seg, stages = d.stages;
     const int chunk = warp % NC, gsub = warp / NC;
     const int nbc = min(BS, d.NB - chunk * BS);
     uint8_t* ring = smem + (size_t)warp * stages * d.slot_bytes;
@@ -317,26 +325,40 @@ __device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
 
     int slot = 0;
     for (int round = 0; round < n_rounds; round++) {
-        const int g = (round * (int)gridDim.x + (int)blockIdx.x) * gpc + gsub;
-        const bool live = g < d.total_groups;
+        // this slot's work in the round (segment 1, when there is one, is the same rows of the second matrix)
+        const StageRef sr = stage_ref(d, (int)gridDim.x, (int)blockIdx.x, gsub, round, 0, chunk, nbc);
+        const bool live = !sr.empty;
         float res[2] = {0.f, 0.f};
         for (int seg = 0; seg < n_seg; seg++) {
             float acc[RG] = {0.f, 0.f, 0.f, 0.f};
             mbar_wait(bars + slot, (parity_bits >> slot) & 1u);
             parity_bits ^= 1u << slot;
             if (live && blk < nbc) {
-                int mi, gl;
-                locate(d, g, seg, mi, gl);
                 const uint8_t* slot_base = ring + (size_t)slot * d.slot_bytes;
-                const int fmt = d.mat[mi].fmt;
-                if (fmt == 0) process_stage<0>(slot_base, blk, h, X, acc);
-                else if (fmt == 1) process_stage<1>(slot_base, blk, h, X, acc);
-                else if (fmt == 2) process_stage<2>(slot_base, blk, h, X, acc);
-                else if (fmt == 3) process_stage<3>(slot_base, blk, h, X, acc);
-                else process_stage<4>(slot_base, blk, h, X, acc);
+                const int fmt = d.mat[n_seg == 2 ? seg : sr.mi].fmt;
+                if (sr.nrows == RG) {
+                    if (fmt == 0) process_stage<0>(slot_base, blk, h, X, acc);
+                    else if (fmt == 1) process_stage<1>(slot_base, blk, h, X, acc);
+                    else if (fmt == 2) process_stage<2>(slot_base, blk, h, X, acc);
+                    else if (fmt == 3) process_stage<3>(slot_base, blk, h, X, acc);
+                    else process_stage<4>(slot_base, blk, h, X, acc);
+                } else {                                     // tail stage of 1 or 2 rows: one row at a time
+                    const int rowp = BS * blk_bytes(fmt);
+#pragma unroll 1
+                    for (int r = 0; r < sr.nrows; r++) {
+                        float a1[RG] = {0.f, 0.f, 0.f, 0.f};
+                        const uint8_t* rb = slot_base + r * rowp;
+                        if (fmt == 0) process_stage<0, 1>(rb, blk, h, X, a1);
+                        else if (fmt == 1) process_stage<1, 1>(rb, blk, h, X, a1);
+                        else if (fmt == 2) process_stage<2, 1>(rb, blk, h, X, a1);
+                        else if (fmt == 3) process_stage<3, 1>(rb, blk, h, X, a1);
+                        else process_stage<4, 1>(rb, blk, h, X, a1);
+                        acc[r] = a1[0];
+                    }
+                }
             }
             __syncwarp();
-            if (pr.issued < n_stages_total) issue_next(d, pr, ring, bars, slot, chunk, nbc, lane);
+            if (pr.issued < n_stages_total) issue_next(d, pr, ring, bars, slot, chunk, gsub, nbc, lane);
             pr.issued++;
             if (++slot == stages) slot = 0;
             res[seg] = reduce4(acc, lane);
@@ -350,68 +372,57 @@ __device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
         }
         __syncthreads();
         if (live && chunk == 0) {                            // warp-uniform
-            int mi, gl;
-            locate(d, g, 0, mi, gl);
-            const MegaMat& m = d.mat[mi];
-            if (lane < RG) {
+            const MegaMat& m = d.mat[sr.mi];
+            const int n_valid = min(sr.nrows, m.out - sr.row0);       // rows of this stage that exist (ragged last group)
+            if (lane < n_valid) {
                 float v0 = 0.f, v1 = 0.f;
                 for (int c = 0; c < NC; c++) {
                     v0 += S.partial[buf][gsub * NC + c][0][lane];
                     if (n_seg == 2) v1 += S.partial[buf][gsub * NC + c][1][lane];
                 }
                 v0 *= rms_inv; v1 *= rms_inv;                // 1.0 unless the input came from a fused norm
-                const int row = gl * RG + lane;
-                if (row < m.out) {
-                    if (d.epilogue == MEP_SWIGLU) {
-                        m.y[row] = __fdividef(v0, 1.0f + __expf(-v0)) * v1;       // reference gemm.cu:713-725
-                    } else if (d.epilogue == MEP_SLOT) {
-                        // partial result of this rank -> slot [parity][this rank] on every tensor-parallel peer (NVLink stores)
-                        const size_t off = ((size_t)d.slot_parity * P.tp_size + P.tp_rank) * (size_t)P.hidden + (size_t)row;
-                        for (int r = 0; r < P.tp_size; r++) P.slots[r][off] = v0;
+                const int row = sr.row0 + lane;
+                if (d.epilogue == MEP_SWIGLU) {
+                    m.y[row] = __fdividef(v0, 1.0f + __expf(-v0)) * v1;           // reference gemm.cu:713-725
+                } else if (d.epilogue == MEP_SLOT) {
+                    // partial result of this rank -> slot [parity][this rank] on every tensor-parallel peer (NVLink stores)
+                    const size_t off = ((size_t)d.slot_parity * P.tp_size + P.tp_rank) * (size_t)P.hidden + (size_t)row;
+                    for (int r = 0; r < P.tp_size; r++) P.slots[r][off] = v0;
+                } else {
+                    m.y[row] = v0;
+                }
+            }
+            const bool fq = d.epilogue == MEP_SWIGLU && (d.fuse & MEGA_FUSE_QUANT);
+            const bool fn = d.epilogue == MEP_SLOT && (d.fuse & MEGA_FUSE_NORM);
+            if (fq || fn) {
+                // Last arriver of a 32-row block (tickets count rows: stages of the tail round hold fewer than RG).  Writers fence
+                // before the ticket, the last arriver fences before it reads the block back.
+                __threadfence();
+                __syncwarp();
+                const int block = sr.row0 >> 5;
+                const int rows_in_block = min(32, m.out - block * 32);
+                unsigned prev = 0;
+                if (lane == 0) prev = atomicAdd(d.cnt + block, (unsigned)n_valid);
+                prev = __shfl_sync(0xFFFFFFFFu, prev, 0);
+                if ((int)prev + n_valid == rows_in_block) {
+                    __threadfence();
+                    const int e = block * 32 + lane;
+                    if (fq) {
+                        // the SwiGLU output block -> xq (same quantize_block32 as the stand-alone phase => same bytes): the down
+                        // projection needs no separate quantise phase and barrier
+                        const float v = (e < d.n) ? __ldcg(d.x + e) : 0.f;
+                        quantize_block32(v, block, lane, d.xq_out, d.n);
                     } else {
-                        m.y[row] = v0;
+                        // single rank: the slot rows ARE the full projection.  Residual add, the block's sum of squares, and the
+                        // next norm's quantiser input h * w (1/rms is applied by the consumer)
+                        const float* sl = P.slots[P.tp_rank] + (size_t)d.slot_parity * P.tp_size * (size_t)P.hidden;
+                        const float hval = __ldcg(d.hid_in + e) + __ldcg(sl + e);
+                        d.hid_out[e] = hval;
+                        const float ss = warp_sum(hval * hval);
+                        if (lane == 0) d.ssq_out[block] = ss;
+                        quantize_block32(hval * d.norm_w[e], block, lane, d.xq_out, P.hidden);
                     }
-                }
-            }
-            if (d.epilogue == MEP_SWIGLU && (d.fuse & MEGA_FUSE_QUANT)) {
-                // Last-arriver quantiser: the warp that completes the 8th row-group of a 32-row block turns the block into xq
-                // (same quantize_block32 as the stand-alone phase => same bytes), so the down projection needs no separate
-                // quantise phase and barrier.  Writers fence before the ticket, the last arriver fences before it reads back.
-                __threadfence();
-                __syncwarp();
-                const int block = gl >> 3;
-                const int groups_in_block = min(8, m.groups - block * 8);
-                unsigned prev = 0;
-                if (lane == 0) prev = atomicAdd(d.cnt + block, 1u);
-                prev = __shfl_sync(0xFFFFFFFFu, prev, 0);
-                if ((int)prev == groups_in_block - 1) {
-                    __threadfence();
-                    const int e = block * 32 + lane;
-                    const float v = (e < d.n) ? __ldcg(d.x + e) : 0.f;
-                    quantize_block32(v, block, lane, d.xq_out, d.n);
                     if (lane == 0) d.cnt[block] = 0;         // ready for the next layer
-                }
-            }
-            if (d.epilogue == MEP_SLOT && (d.fuse & MEGA_FUSE_NORM)) {
-                // Single rank: the slot rows ARE the full projection.  Last arriver of a 32-row block: residual add, the block's
-                // sum of squares, and the next norm's quantiser input h * w (1/rms is applied by the consumer).
-                __threadfence();
-                __syncwarp();
-                const int block = gl >> 3;
-                const int groups_in_block = min(8, m.groups - block * 8);
-                unsigned prev = 0;
-                if (lane == 0) prev = atomicAdd(d.cnt + block, 1u);
-                prev = __shfl_sync(0xFFFFFFFFu, prev, 0);
-                if ((int)prev == groups_in_block - 1) {
-                    __threadfence();
-                    const int e = block * 32 + lane;
-                    const float* sl = P.slots[P.tp_rank] + (size_t)d.slot_parity * P.tp_size * (size_t)P.hidden;
-                    const float hval = __ldcg(d.hid_in + e) + __ldcg(sl + e);
-                    d.hid_out[e] = hval;
-                    const float ss = warp_sum(hval * hval);
-                    if (lane == 0) d.ssq_out[block] = ss;
-                    quantize_block32(hval * d.norm_w[e], block, lane, d.xq_out, P.hidden);
-                    if (lane == 0) d.cnt[block] = 0;
                 }
             }
         }
@@ -807,7 +818,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_c
     st.xchg_base = (P.tp_size > 1) ? P.sync[96] : 0u;        // written by the previous launch (stream order)
     uint32_t parity_bits = 0;                                // mbarrier phase parity of this warp's ring stages
     Producer pr;
-    pr.issued = 0; pr.p_g = 0; pr.p_seg = 0;
+    pr.issued = 0; pr.round = 0; pr.seg = 0;
 
     if (lane == 0) {
         for (int s = 0; s < MEGA_MAX_STAGES; s++) mbar_init(S.bars + warp * MEGA_MAX_STAGES + s, 1);
@@ -1000,6 +1011,14 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
         else { ph.n_seg = 1; ph.total_groups = total; }
         ph.warps = g.warps; ph.gpc = g.gpc; ph.stages = g.stages; ph.slot_bytes = g.slot_bytes;
         ph.slot_parity = slot_parity;
+        // lock-step rounds over grid * gpc warp slots; a partly filled last round is cut into 1- or 2-row stages
+        const int slots = grid * g.gpc;
+        ph.full_rounds = ph.total_groups / slots;
+        ph.tail_groups = ph.total_groups % slots;
+        ph.n_rounds = ph.full_rounds + (ph.tail_groups ? 1 : 0);
+        ph.tail_nr = RG;
+        if ((fuse & MEGA_SPLIT_TAIL) && ph.tail_groups > 0)
+            ph.tail_nr = (ph.tail_groups * 4 <= slots) ? 1 : (ph.tail_groups * 2 <= slots) ? 2 : RG;
         ph.xq = xq;
         *outp = ph;
         return true;
@@ -1103,34 +1122,46 @@ std::string mega_check_gemv_schedule(const MegaPhase& d, int grid, size_t ring_b
     if (d.stages < 1 || d.stages > MEGA_MAX_STAGES) return "ring depth out of range";
     if ((size_t)d.warps * d.stages * d.slot_bytes > ring_bytes) return "rings exceed the dynamic shared memory";
     if (d.NB != d.K / 256 || d.NC != (d.NB + BS - 1) / BS) return "NB / NC inconsistent with K";
-    const int n_rounds = phase_rounds(d, grid), n_total = n_rounds * d.n_seg;
-    std::vector<std::vector<unsigned char>> seen((size_t)d.n_mat);
-    for (int i = 0; i < d.n_mat; i++) seen[(size_t)i].assign((size_t)d.mat[i].groups * d.NC, 0);
+    const int slots = grid * d.gpc;
+    if (d.full_rounds != d.total_groups / slots || d.tail_groups != d.total_groups % slots ||
+        d.n_rounds != d.full_rounds + (d.tail_groups ? 1 : 0)) return "round bookkeeping inconsistent with the grid";
+    if (d.tail_nr != 1 && d.tail_nr != 2 && d.tail_nr != RG) return "tail stage height must be 1, 2 or RG rows";
+    if (d.tail_nr < RG && d.tail_groups * (RG / d.tail_nr) > slots) return "tail round does not fit the warp slots";
+    const int n_total = d.n_rounds * d.n_seg;
+    std::vector<std::vector<unsigned char>> seen((size_t)d.n_mat);          // per matrix: [row][chunk]
+    for (int i = 0; i < d.n_mat; i++) seen[(size_t)i].assign((size_t)d.mat[i].out * d.NC, 0);
     for (int b = 0; b < grid; b++) {
         for (int w = 0; w < d.warps; w++) {
             const int chunk = w % d.NC, gsub = w / d.NC, nbc = std::min(BS, d.NB - chunk * BS);
             Producer pr;
-            pr.issued = 0; pr.p_seg = 0; pr.p_g = b * d.gpc + gsub;
+            pr.issued = 0; pr.round = 0; pr.seg = 0;
             int s = 0;
-            for (int round = 0; round < n_rounds; round++) {
-                const int g = (round * grid + b) * d.gpc + gsub;              // what the consumer expects in this round
+            for (int round = 0; round < d.n_rounds; round++) {
+                const StageRef first = stage_ref(d, grid, b, gsub, round, 0, chunk, nbc);   // what the consumer derives for the round
                 for (int seg = 0; seg < d.n_seg; seg++, s++) {
-                    if (pr.p_g != g || pr.p_seg != seg) {
-                        snprintf(msg, sizeof(msg), "cta %d warp %d stage %d: producer (%d,%d) != consumer (%d,%d)", b, w, s, pr.p_g, pr.p_seg, g, seg);
+                    if (pr.round != round || pr.seg != seg) {
+                        snprintf(msg, sizeof(msg), "cta %d warp %d stage %d: producer (%d,%d) != consumer (%d,%d)", b, w, s, pr.round, pr.seg, round, seg);
                         return msg;
                     }
-                    const StageRef sr = stage_ref(d, pr.p_g, pr.p_seg, chunk, nbc);
+                    const StageRef sr = stage_ref(d, grid, b, gsub, pr.round, pr.seg, chunk, nbc);
+                    if (sr.empty != first.empty || (!sr.empty && (sr.row0 != first.row0 || sr.nrows != first.nrows)))
+                        return "segments of one round disagree on their rows";
                     if (!sr.empty) {
                         const MegaMat& m = d.mat[sr.mi];
-                        if (sr.gl < 0 || sr.gl >= m.groups) return "row-group outside its matrix";
-                        if ((size_t)RG * BS * sr.blkb > (size_t)d.slot_bytes) return "stage larger than its ring slot";
+                        if (d.n_seg == 2 && sr.mi != seg) return "SwiGLU segment does not select its matrix";
+                        if (sr.gl < 0 || sr.gl >= m.groups || sr.row0 < 0 || sr.row0 >= m.out) return "rows outside their matrix";
+                        if (sr.nrows != RG && sr.nrows != d.tail_nr) return "unexpected stage height";
+                        if ((sr.row0 >> 5) != ((sr.row0 + sr.nrows - 1) >> 5)) return "a stage straddles two 32-row blocks";
+                        if ((size_t)sr.nrows * BS * sr.blkb > (size_t)d.slot_bytes) return "stage larger than its ring slot";
                         if ((long long)chunk * (BS * sr.blkb) + (long long)sr.bytes > m.pitch) return "copy runs past the row pitch";
                         if ((sr.src_off & 15) || (m.pitch & 15) || (sr.bytes & 15)) return "copy is not 16-byte aligned";
-                        unsigned char& c = seen[(size_t)sr.mi][(size_t)sr.gl * d.NC + chunk];
-                        if (c) { snprintf(msg, sizeof(msg), "matrix %d row-group %d chunk %d fetched twice", sr.mi, sr.gl, chunk); return msg; }
-                        c = 1;
+                        for (int r = 0; r < sr.nrows && sr.row0 + r < m.out; r++) {
+                            unsigned char& c = seen[(size_t)sr.mi][(size_t)(sr.row0 + r) * d.NC + chunk];
+                            if (c) { snprintf(msg, sizeof(msg), "matrix %d row %d chunk %d fetched twice", sr.mi, sr.row0 + r, chunk); return msg; }
+                            c = 1;
+                        }
                     }
-                    producer_advance(d, pr, grid);
+                    producer_advance(d, pr);
                 }
             }
             if (s != n_total) return "stage count mismatch";
@@ -1138,7 +1169,7 @@ std::string mega_check_gemv_schedule(const MegaPhase& d, int grid, size_t ring_b
     }
     for (int i = 0; i < d.n_mat; i++)
         for (size_t j = 0; j < seen[(size_t)i].size(); j++)
-            if (!seen[(size_t)i][j]) { snprintf(msg, sizeof(msg), "matrix %d row-group %zu chunk %zu never fetched", i, j / d.NC, j % d.NC); return msg; }
+            if (!seen[(size_t)i][j]) { snprintf(msg, sizeof(msg), "matrix %d row %zu chunk %zu never fetched", i, j / d.NC, j % d.NC); return msg; }
     return "";
 }
 

@@ -36,7 +36,9 @@ __device__ __forceinline__ float byte_to_float(uint32_t w, int idx) {
 }
 
 // One stage (RG rows x up to BS super-blocks) of format FMT: this lane's half super-block (blk, h) against X.
-template <int FMT>
+// NR (default RG): rows of the stage that hold data — the persistent kernel cuts the last, partly filled round of a phase
+// into 1- or 2-row stages so that its tail costs a fraction of a round (engine/decode_megakernel.cu).
+template <int FMT, int NR = RG>
 __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_base, int blk, int h, const XRegs& X,
                                               float (&acc)[RG]) {
     constexpr int BLK = Fmt<FMT>::BLK;
@@ -46,7 +48,7 @@ __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_b
         // ---------------- Q4_K / Q5_K ----------------
         constexpr int QS = (FMT == 0) ? 16 : 48;
 #pragma unroll
-        for (int r = 0; r < RG; r++) {
+        for (int r = 0; r < NR; r++) {
             const int4 hd = *reinterpret_cast<const int4*>(base + r * ROWP);
             const uint32_t w0 = hd.y, w1 = hd.z, w2 = hd.w;
             // packed 6-bit scales / mins of the 4 sub-blocks of this half
@@ -102,7 +104,7 @@ __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_b
         // Blocks 0 and 2 start 2 bytes into a word: realign with PRMT; blocks 1 and 3 are word aligned. ----------------
         const uint8_t* lb = base + h * 136;
 #pragma unroll
-        for (int r = 0; r < RG; r++) {
+        for (int r = 0; r < NR; r++) {
             uint32_t w[34];
 #pragma unroll
             for (int i = 0; i < 17; i++) {
@@ -134,7 +136,7 @@ __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_b
         // goes through the exact 16-element sums of x, like dmin in Q4_K. ----------------
         const uint8_t* lb = base + h * 72;
 #pragma unroll
-        for (int r = 0; r < RG; r++) {
+        for (int r = 0; r < NR; r++) {
             uint32_t w[18];
 #pragma unroll
             for (int i = 0; i < 9; i++) {
@@ -165,7 +167,7 @@ __device__ __forceinline__ void process_stage(const uint8_t* __restrict__ slot_b
         const uint32_t sel = mis ? 0x5432u : 0x3210u;
         const uint8_t* ab = base - mis;                            // 4-byte aligned view of the block
 #pragma unroll
-        for (int r = 0; r < RG; r++) {
+        for (int r = 0; r < NR; r++) {
             const uint32_t* sp = reinterpret_cast<const uint32_t*>(ab + r * ROWP + 192 + 8 * h);
             const uint32_t a0 = sp[0], a1 = sp[1], a2 = sp[2];
             const uint32_t sc0 = __byte_perm(a0, a1, sel), sc1 = __byte_perm(a1, a2, sel);

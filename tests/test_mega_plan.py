@@ -97,6 +97,18 @@ def test_fusion_flags_shorten_the_program():
 def test_overlap_flag_keeps_the_plan_consistent_at_benchmark_shapes():
     for cfg in (LLAMA3_70B, LLAMA3_8B):
         for tp in (1, 8):
-            rc, info, msg = selftest(cfg, "Q4_K_M", 0, tp, fuse=31)
+            rc, info, msg = selftest(cfg, "Q4_K_M", 0, tp, fuse=63)
             assert rc == 0, (cfg.hidden_size, tp, msg)
             assert info[3] >= 4 and info[4] >= 2           # the o-projection keeps >= 4 warps and a double-buffered ring
+
+
+def test_split_tail_schedules_cover_every_row_once():
+    """fuse bit 32 on the benchmark shapes and a few awkward grids: the CPU replay inside nt_mega_plan_selftest checks that the
+    1- and 2-row tail stages fetch every row of every matrix exactly once and never straddle a 32-row block."""
+    for cfg, mix in ((LLAMA3_70B, "Q4_K_M"), (LLAMA3_70B, "Q6_K"), (LLAMA3_8B, "Q4_K_M"), (LLAMA3_8B, "Q8_0")):
+        for tp in (1, 2, 8):
+            rc, info, msg = selftest(cfg, mix, tp - 1, tp, fuse=32)
+            assert rc == 0, (mix, tp, msg)
+    for grid in (33, 100, 132, 160):
+        rc, info, msg = selftest(LLAMA3_8B, "Q4_K_M", grid=grid, fuse=63)
+        assert rc == 0, (grid, msg)

@@ -240,6 +240,19 @@ def test_weights_stream_through_the_attention_phase(sim, tmp_path, fuse):
     m.close()
 
 
+@pytest.mark.parametrize("fuse", [32, 63])
+def test_split_tail_rounds(sim, tmp_path, fuse):
+    """MEGA_SPLIT_TAIL (32): the partly filled last round of a GEMV phase is dealt out 1 or 2 rows at a time over all warp slots
+    (process_stage<FMT, 1>), tickets of the last-arriver fusions count rows.  Different grids give different tail shapes."""
+    for grid in (3, 4, 5, 7):
+        check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=2, grid=grid, copy_delay=3, fuse=fuse)
+    check_against_oracle(sim, tmp_path, SMALL128, "Q4_K_M", steps=2, grid=8, copy_delay=4, fuse=fuse)
+    check_against_oracle(sim, tmp_path, SMALL128_G8, "Q8_0", steps=1, grid=11, fuse=fuse)
+    cfg = LlamaConfig(**{**TINY.dict(), "vocab_size": 510, "n_layers": 2})     # ragged LM head + uneven TP shards
+    check_against_oracle(sim, tmp_path, cfg, "Q4_K", steps=2, tp=2, grid=3, copy_delay=3, fuse=fuse, tol=5e-4)
+    check_against_oracle(sim, tmp_path, cfg, "Q4_0", steps=2, grid=5, fuse=fuse)
+
+
 def test_a_missing_peer_times_out_instead_of_hanging(sim, tmp_path, monkeypatch):
     """Rank 1 never launches: rank 0's master CTA gives up on the flag after the time-out, raises the abort word, every later
     barrier falls through and the launch ends (the host then reports 'decode megakernel aborted')."""
@@ -283,5 +296,5 @@ def test_one_70b_layer_on_148_ctas(sim, tmp_path):
     mix, 148 CTAs x 384 threads — one layer, small vocabulary."""
     cfg = LlamaConfig(vocab_size=1024, hidden_size=8192, intermediate_size=28672, n_layers=1, n_heads=64, n_kv_heads=8, head_dim=128,
                       max_seq_len=64, bos_token_id=1, eos_token_id=2)
-    for fuse in (0, 31):
+    for fuse in (0, 63):
         check_against_oracle(sim, tmp_path, cfg, "Q6_K" if fuse == 0 else "Q4_K", steps=1, grid=148, copy_delay=3, fuse=fuse)
