@@ -966,7 +966,6 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
     pl.fuse = fuse;
 
     // ---- phase list ----
-    const size_t ring = MEGA_DYN_SMEM;
     auto base_phase = [&](int kind, int layer) {
         MegaPhase ph;
         memset(&ph, 0, sizeof(ph));

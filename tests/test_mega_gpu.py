@@ -116,7 +116,7 @@ def test_adaptive_split_vs_oracle_and_graph_ids(case):
         assert rel(got[i + 1], lo) <= 1e-3
 
 
-@pytest.mark.parametrize("fuse", [3, 7, 31])
+@pytest.mark.parametrize("fuse", [3, 7, 31, 63])
 def test_producer_side_fusions_keep_the_greedy_ids(case, monkeypatch, fuse):
     """NT_B200_MEGA_FUSE: 1 activation quantiser, 2 split combine (same arithmetic as the separate phases), 4 residual add +
     next norm at one rank (1/rms applied by the consumer: equal up to round-off, not bit-equal)."""
@@ -130,7 +130,7 @@ def test_producer_side_fusions_keep_the_greedy_ids(case, monkeypatch, fuse):
     m.use_megakernel(True)
     got, ids_m = run(m, prompt, 70)
     assert m.megakernel_active
-    per_layer = {3: 7, 7: 5, 31: 5}[fuse]
+    per_layer = {3: 7, 7: 5, 31: 5, 63: 5}[fuse]
     assert len(m.megakernel_plan()) == per_layer * cfg.n_layers + 2      # + first/final norm and the LM head
     m.close()
     assert max(rel(a, b) for a, b in zip(got, want)) <= 1e-3
