@@ -51,6 +51,7 @@ inline void st_release_gpu(unsigned* p, unsigned v) { __atomic_store_n(p, v, __A
 inline void st_relaxed_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline unsigned long long global_timer_ns() { return (unsigned long long)(cusim::now_s() * 1e9); }
 inline void fence_proxy_async_smem() {}
+inline void prefetch_l2(const void*) {}
 #else
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
@@ -85,6 +86,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 #endif
 
@@ -609,7 +611,11 @@ __device__ void attend_unit(const MegaParams& P, Shared& S, const MegaPhase& d, 
                 const int p = p0 + u * AW;
                 if (p < n_keys) {
                     if (k_begin + p == pos) load_row<DPL>(cur_k + lane * DPL, kf[u]);
-                    else load_row<DPL>(kbase + (size_t)(k_begin + p) * row_stride, kf[u]);
+                    else {
+                        load_row<DPL>(kbase + (size_t)(k_begin + p) * row_stride, kf[u]);
+                        // the matching V row is needed two CTA barriers from now: start pulling it from HBM into L2
+                        if ((lane & (32 / DPL - 1)) == 0) prefetch_l2(vbase + (size_t)(k_begin + p) * row_stride);
+                    }
                 }
             }
 #pragma unroll
