@@ -67,8 +67,9 @@ int  nt_model_megakernel_active(nt_model_t m);      /* 1 once the persistent ker
 /* phase kinds of the persistent kernel's per-token program (0 norm+quantise, 1 quantise, 2 GEMV, 3 attention,
  * 4 combine); returns the number of phases (may exceed cap), 0 when the kernel is not active */
 int  nt_model_megakernel_plan(nt_model_t m, int* kinds, int cap);
-/* tuning aid: record %globaltimer at every phase boundary of the persistent kernel on its first 4 CTAs; _read returns the number
- * of values ([4][phases][start, work done, barrier passed], ns) of the most recent launch and copies up to cap of them */
+/* tuning aid: record the SM clock at every phase boundary of the persistent kernel on its first 4 CTAs; _read returns the number of
+ * values (per CTA: [phases][start, work done, barrier passed] ticks, then clock start/end and %globaltimer start/end for the
+ * tick -> ns conversion) of the most recent launch and copies up to cap of them */
 void nt_model_megakernel_trace(nt_model_t m, int on);
 long long nt_model_megakernel_trace_read(nt_model_t m, unsigned long long* out_host, size_t cap);
 /* debug: copies one of the persistent kernel's working vectors ("hid0", "hid1", "q", "attn", "act", "slots") to the host;

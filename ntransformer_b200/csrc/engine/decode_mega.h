@@ -123,10 +123,10 @@ struct MegaParams {
     unsigned* sync;             // MEGA_SYNC_WORDS words
     unsigned long long timeout_ns;
     int tp_rank, tp_size;
-    // Optional timeline (null = off): CTAs 0..MEGA_TRACE_CTAS-1 store %globaltimer at [cta][phase][0 start, 1 work done,
-    // 2 barrier passed], nanoseconds.  tools/mega_trace.py turns it into time per phase kind and time spent waiting in barriers.
+    // Optional timeline (null = off): CTAs 0..MEGA_TRACE_CTAS-1 store the SM clock at [cta][phase][0 start, 1 work done,
+    // 2 barrier passed] followed by 4 calibration values (clock and %globaltimer at kernel start / end).  tools/mega_trace.py turns it into time per phase kind and time spent waiting in barriers.
     unsigned long long* trace;
-    int trace_stride;               // values per CTA (3 x phases of the full program)
+    int trace_stride;               // values per CTA (3 x phases of the full program + 4)
     int pad2_;
     float* slots[MEGA_MAX_TP];      // rank r's slot buffer [2][tp_size][hidden] as mapped into this process
     unsigned* flags[MEGA_MAX_TP];   // rank r's flag words (one 128-byte line per source rank)
@@ -211,7 +211,7 @@ public:
     const float* debug_buffer(const char* name, size_t* count) const;
     void set_split_fixed(int n) { split_fixed_ = n; }      // before build(): use the graph path's split rule (bit-identical attention)
     void set_fuse(int bits) { fuse_ = bits; }              // before build(): MegaFuse bits (default 0: the plain 9-phase program)
-    // Phase timeline of the most recent launch ([MEGA_TRACE_CTAS][n_phases][3] ns); enabling it costs three timer reads per phase.
+    // Phase timeline of the most recent launch ([MEGA_TRACE_CTAS][3 x phases + 4] values); enabling it costs three clock reads per phase.
     void set_trace(bool on);
     size_t read_trace(unsigned long long* out_host, size_t cap) const;     // returns the number of values available
 

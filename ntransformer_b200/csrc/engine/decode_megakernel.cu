@@ -52,6 +52,7 @@ inline void st_relaxed_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __A
 inline unsigned long long global_timer_ns() { return (unsigned long long)(cusim::now_s() * 1e9); }
 inline void fence_proxy_async_smem() {}
 inline void prefetch_l2(const void*) {}
+inline unsigned long long sm_clock() { return (unsigned long long)(cusim::now_s() * 1e9); }
 #else
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
@@ -87,6 +88,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned long long sm_clock() { return (unsigned long long)clock64(); }
 
 #endif
 
@@ -840,12 +842,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_c
     if (P.first_gemv >= 0 && P.first_gemv < P.n_phases) prime_rings(S.ph[P.first_gemv & 3], pr, smem, S.bars, warp, lane);
 
     const bool tracing = P.trace != nullptr && blockIdx.x < MEGA_TRACE_CTAS && threadIdx.x == 0;
+    // per traced CTA: [phase][start, work done, barrier passed] in SM clock ticks (%globaltimer only ticks every ~1 us), then
+    // [clock at start, clock at end, globaltimer at start, globaltimer at end] to convert ticks to time
     unsigned long long* trace = tracing ? P.trace + (size_t)blockIdx.x * P.trace_stride : nullptr;
+    unsigned long long* trace_cal = tracing ? trace + P.trace_stride - 4 : nullptr;
+    if (tracing) { trace_cal[0] = sm_clock(); trace_cal[2] = global_timer_ns(); }
     for (int i = 0; i < P.n_phases; i++) {
         if (i + 2 < P.n_phases) load_phase(&S.ph[(i + 2) & 3], P.phases + i + 2);
         const MegaPhase& d = S.ph[i & 3];
         const int kind = d.kind;
-        if (tracing) trace[3 * i] = global_timer_ns();
+        if (tracing) trace[3 * i] = sm_clock();
         if (kind == MPH_GEMV) {
             gemv_phase(P, S, d, smem, pr, parity_bits, warp, lane);
         } else if (kind == MPH_NORM_XQ) {
@@ -866,10 +872,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_c
             __syncthreads();                                 // every warp is done with the ring area; descriptor i + 2 is visible
             prime_rings(S.ph[prime & 3], pr, smem, S.bars, warp, lane);
         }
-        if (tracing) trace[3 * i + 1] = global_timer_ns();
+        if (tracing) trace[3 * i + 1] = sm_clock();
         mega_barrier(P, d.barrier, st);
-        if (tracing) trace[3 * i + 2] = global_timer_ns();
+        if (tracing) trace[3 * i + 2] = sm_clock();
     }
+    if (tracing) { trace_cal[1] = sm_clock(); trace_cal[3] = global_timer_ns(); }
     if (P.tp_size > 1 && blockIdx.x == 0 && threadIdx.x == 0) P.sync[96] = st.xchg_base + st.xchg_idx;
 }
 
@@ -1354,7 +1361,7 @@ void DecodeMega::launch(bool with_head, cudaStream_t s) {
     if (const char* mp = getenv("NT_B200_MEGA_MAX_PHASES"))      // bisect aid: stop after k phases, then nt_model_debug_read
         p.n_phases = std::max(1, std::min(p.n_phases, atoi(mp)));
     p.trace = trace_on_ ? trace_ : nullptr;     // laid out for the full program; a body-only launch fills a prefix per CTA
-    p.trace_stride = (int)plan_.phases.size() * 3;
+    p.trace_stride = (int)plan_.phases.size() * 3 + 4;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid_); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = MEGA_DYN_SMEM; cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -1367,11 +1374,11 @@ void DecodeMega::launch(bool with_head, cudaStream_t s) {
 
 void DecodeMega::set_trace(bool on) {
     trace_on_ = on;
-    if (on && !trace_) trace_ = dalloc<unsigned long long>((size_t)MEGA_TRACE_CTAS * plan_.phases.size() * 3);
+    if (on && !trace_) trace_ = dalloc<unsigned long long>((size_t)MEGA_TRACE_CTAS * (plan_.phases.size() * 3 + 4));
 }
 
 size_t DecodeMega::read_trace(unsigned long long* out_host, size_t cap) const {
-    const size_t n = trace_ ? (size_t)MEGA_TRACE_CTAS * plan_.phases.size() * 3 : 0;
+    const size_t n = trace_ ? (size_t)MEGA_TRACE_CTAS * (plan_.phases.size() * 3 + 4) : 0;
     if (out_host && n) NT_CUDA_CHECK(cudaMemcpy(out_host, trace_, sizeof(unsigned long long) * std::min(n, cap), cudaMemcpyDeviceToHost));
     return n;
 }

@@ -150,13 +150,16 @@ class Model:
         lib().nt_model_megakernel_trace(self._h, int(on))
 
     def megakernel_trace_read(self):
-        """ns timestamps [4 CTAs, phases, (start, work done, barrier passed)] of the most recent launch."""
+        """(ticks [4 CTAs, phases, (start, work done, barrier passed)] in SM clock ticks, ns_per_tick [4]) of the most recent launch."""
         n = lib().nt_model_megakernel_trace_read(self._h, None, 0)
         if n <= 0:
-            return np.zeros((0, 0, 3), dtype=np.uint64)
+            return np.zeros((0, 0, 3), dtype=np.uint64), np.zeros(0)
         out = np.zeros(n, dtype=np.uint64)
         lib().nt_model_megakernel_trace_read(self._h, out.ctypes.data_as(C.c_void_p), n)
-        return out.reshape(4, -1, 3)
+        per = out.reshape(4, -1)
+        cal = per[:, -4:].astype(np.float64)                     # clock start/end, globaltimer start/end
+        ns_per_tick = (cal[:, 3] - cal[:, 2]) / np.maximum(cal[:, 1] - cal[:, 0], 1.0)
+        return per[:, :-4].reshape(4, -1, 3), ns_per_tick
 
     def debug_read(self, name: str):
         """Host copy of one of the persistent kernel's working vectors (hid0, hid1, q, attn, act, slots)."""

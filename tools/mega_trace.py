@@ -37,12 +37,13 @@ def main():
     m.megakernel_trace(True)
     for pos in range(1, args.tokens):
         m.forward([(pos * 7919) % cfg.vocab_size], pos)
-    t = m.megakernel_trace_read().astype(np.int64)              # [4, phases, 3]
+    ticks, ns_per_tick = m.megakernel_trace_read()
+    t = ticks.astype(np.float64) * ns_per_tick[:, None, None]   # [4, phases, 3] in ns, per-CTA clock (durations only)
     kinds = m.megakernel_plan()
     m.close()
     work = (t[:, :, 1] - t[:, :, 0]).max(axis=0) / 1e3          # us, slowest traced CTA
     wait = (t[:, :, 2] - t[:, :, 1]).min(axis=0) / 1e3          # us, the CTA that arrived last waits least
-    total = (t[:, -1, 2].max() - t[:, 0, 0].min()) / 1e3
+    total = (t[:, -1, 2] - t[:, 0, 0]).max() / 1e3
     out = {"token_us": round(float(total), 1), "phases": len(kinds), "per_kind": {}}
     for k, name in KINDS.items():
         sel = [i for i, kk in enumerate(kinds) if kk == k]
