@@ -45,6 +45,37 @@ def test_sass_is_sm100a_with_tma_and_dp4a():
         assert mnemonic in sass, f"{mnemonic} missing"
 
 
+def test_persistent_decode_kernel_sass():
+    """decode_step_kernel (csrc/engine/decode_megakernel.cu): TMA bulk copies + dp4a in the GEMV phases, GPU-scope release/acquire
+    for the grid barrier, strong L2 loads for data written by other CTAs, system-scope stores/fences for the peer exchange."""
+    obj = ROOT / "ntransformer_b200" / "_build" / "engine__decode_megakernel.cu.o"
+    sass = subprocess.run(["cuobjdump", "-sass", str(obj if obj.exists() else _lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    body = sass[sass.index("decode_step_kernel"):]
+    nxt = body.find("Function :", 10)
+    body = body if nxt < 0 else body[:nxt]
+    for mnemonic in ("UBLKCP", "IDP.4A", "SYNCS.ARRIVE.TRANS64", "REDG.E.ADD.STRONG.GPU", "LDG.E.STRONG.GPU", "CCTL.IVALL", "MEMBAR.SC.SYS",
+                     "STG.E.STRONG.SYS", "LDG.E.STRONG.SYS", "FENCE.VIEW.ASYNC"):
+        assert mnemonic in body, f"{mnemonic} missing from decode_step_kernel"
+    for forbidden in ("HMMA", "UTCHMMA", "IMMA"):                     # no tensor cores on the decode path (north_star)
+        assert forbidden not in body, forbidden
+
+
+def test_emulator_hooks_stay_out_of_the_product():
+    """tests/cusim compiles some product sources with -DNT_CUSIM; the product build never defines it and carries no emulator code."""
+    from ntransformer_b200 import build as nb
+
+    assert not any("NT_CUSIM" in f for f in nb.COMMON + nb.ARCH)
+    syms = subprocess.run(["nm", "-D", "-C", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    assert "cusim" not in syms
+    pkg = ROOT / "ntransformer_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.h")) + list(pkg.rglob("*.cuh")):
+        if "_build" in f.parts:
+            continue
+        text = f.read_text(errors="replace")
+        if re.search(r'cusim::|#include "cusim', text):               # code (not a comment pointing at tests/cusim)
+            assert "#ifdef NT_CUSIM" in text, f
+
+
 def test_product_never_touches_the_oracle():
     """The oracle is test infrastructure: nothing under ntransformer_b200/ may import, link or execute it."""
     pkg = ROOT / "ntransformer_b200"
