@@ -30,7 +30,8 @@ std::string Engine::generate(const std::string& prompt, const GenerateConfig& cf
     // Greedy without a repeat penalty needs no logits on the host: argmax runs on the GPU (4 B D2H instead of 513 KB).
     const bool gpu_greedy = cfg.temperature <= 0.0f && cfg.repeat_penalty <= 1.0f;
     // Opt-in: penalty + top-k/top-p sampling on the GPU with the host's mt19937 stream (4 B D2H per token, csrc/sample.cu).
-    const bool gpu_sample = (cfg.gpu_sampler || getenv("NT_B200_GPU_SAMPLER")) && sample_topk_supported(vocab, cfg.temperature, cfg.top_k);
+    const char* gs_env = getenv("NT_B200_GPU_SAMPLER");
+    const bool gpu_sample = (cfg.gpu_sampler || (gs_env && *gs_env && std::string(gs_env) != "0")) && sample_topk_supported(vocab, cfg.temperature, cfg.top_k);
     auto next_from = [&](float* dev_logits) {
         if (gpu_greedy) return model_.argmax_last();
         if (gpu_sample) {

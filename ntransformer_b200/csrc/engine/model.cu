@@ -53,6 +53,7 @@ template <typename T> T* dmalloc(size_t n) {
     return p;
 }
 size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
+bool env_on(const char* name) { const char* e = getenv(name); return e && *e && strcmp(e, "0") != 0; }   // set and not "0"
 
 }  // namespace
 
@@ -431,7 +432,7 @@ void Model::run_step_mega(bool with_head) {
 }
 
 void Model::run_step(bool with_head) {
-    if ((use_mega_ || getenv("NT_B200_MEGAKERNEL")) && ensure_mega()) { run_step_mega(with_head); return; }
+    if ((use_mega_ || env_on("NT_B200_MEGAKERNEL")) && ensure_mega()) { run_step_mega(with_head); return; }
     if (!use_graph_ || getenv("NT_B200_NO_GRAPH")) {
         step_body(stream_);
         if (with_head) step_head(stream_);

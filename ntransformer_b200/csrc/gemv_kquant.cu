@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
 // spent, verified through the CPU emulation of the persistent kernel (tests/test_mega_sim.py), which shares process_stage<4>.
 // Without the switch Q4_0 keeps the generic kernel (gemv_generic.cu), as before.
 bool q4_0_tma_enabled() {
-    static const bool on = getenv("NT_B200_Q4_0_TMA") != nullptr;
+    static const bool on = [] { const char* e = getenv("NT_B200_Q4_0_TMA"); return e && *e && !(e[0] == '0' && e[1] == 0); }();
     return on;
 }
 int fmt_of(DType dt) {
