@@ -51,6 +51,22 @@ def main():
             out["per_kind"][name] = {"count": len(sel), "work_us_total": round(float(work[sel].sum()), 1),
                                      "barrier_wait_us_total": round(float(wait[sel].sum()), 1),
                                      "work_us_mean": round(float(work[sel].mean()), 2), "wait_us_mean": round(float(wait[sel].mean()), 2)}
+    # streaming rate of each GEMV phase type: algorithmic weight bytes of the phase / its work time (slowest traced CTA)
+    from ntransformer_b200.dtypes import dtype_row_size
+    from ntransformer_b200.model_spec import tensor_table
+
+    nbytes = {name: rows * dtype_row_size(dt, cols) for name, dt, rows, cols in tensor_table(cfg, args.mix)}
+    gemv_idx = [i for i, kk in enumerate(kinds) if kk == 2]
+    groups = {"q/k/v": ("attn_q", "attn_k", "attn_v"), "o": ("attn_output",), "gate/up": ("ffn_gate", "ffn_up"), "down": ("ffn_down",)}
+    rates = {k: [] for k in groups}
+    for layer in range(cfg.n_layers):
+        for j, (gname, tensors) in enumerate(groups.items()):
+            i = gemv_idx[4 * layer + j]
+            b = sum(nbytes[f"blk.{layer}.{t}.weight"] for t in tensors)
+            rates[gname].append(b / (work[i] * 1e-6) / 1e9)
+    out["gemv_GBps"] = {k: {"mean": round(float(np.mean(v)), 1), "min": round(float(np.min(v)), 1), "max": round(float(np.max(v)), 1)} for k, v in rates.items()}
+    head_i = gemv_idx[-1]
+    out["gemv_GBps"]["lm_head"] = round(nbytes["output.weight"] / (work[head_i] * 1e-6) / 1e9, 1)
     print(json.dumps(out, indent=1))
 
 
