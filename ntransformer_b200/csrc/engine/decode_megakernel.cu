@@ -1404,6 +1404,8 @@ const float* DecodeMega::debug_buffer(const char* name, size_t* count) const {
     if (n == "hid0") return ret(hid_[0], (size_t)hidden_);
     if (n == "hid1") return ret(hid_[1], (size_t)hidden_);
     if (n == "q") return ret(q_, (size_t)nh_ * hd_);
+    if (n == "k") return ret(k_, (size_t)(p_.nkv) * hd_);
+    if (n == "v") return ret(v_, (size_t)(p_.nkv) * hd_);
     if (n == "attn") return ret(attn_, (size_t)nh_ * hd_);
     if (n == "act") return ret(act_, (size_t)inter_);
     if (n == "slots") return ret(static_cast<const float*>(xchg_), (size_t)2 * tp_size_ * hidden_);

@@ -187,6 +187,7 @@ int mega_sim_step(void* h, const float* embed_row, int token, int pos, int with_
         R.step.as<int>()[0] = token; R.step.as<int>()[1] = pos;
         memset(R.sync.ptr, 0, 64 * 4);                                   // DecodeMega::launch's cudaMemsetAsync
         R.P.n_phases = with_head ? (int)R.plan.phases.size() : R.plan.n_body;
+        if (const char* mp = getenv("NT_B200_MEGA_MAX_PHASES")) R.P.n_phases = std::max(1, std::min(R.P.n_phases, atoi(mp)));   // same bisect aid as DecodeMega::launch
     }
     // fault injection for the time-out test: one rank never launches (its peers must give up, not hang)
     const char* skip_env = getenv("CUSIM_MEGA_SKIP_RANK");

@@ -12,5 +12,6 @@ case "${1:-}" in
   6) $G --gpus 8 --timeout 1500 -- 'mkdir -p gpurun_out; for v in 0 1; do NT_B200_MEGAKERNEL=$v NT_B200_MEGA_FUSE=51 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 48 --warmup 8 > gpurun_out/bench_tp8_mega_$v.json 2> gpurun_out/bench_tp8_mega_$v.err || true; tail -1 gpurun_out/bench_tp8_mega_$v.json; done' ;;
   7) $G --timeout 900 -- 'mkdir -p gpurun_out; for f in 0 3 7 31 63; do python tools/mega_trace.py --model 70b --fuse $f > gpurun_out/mega_trace_fuse$f.json 2> gpurun_out/mega_trace_fuse$f.err || true; cat gpurun_out/mega_trace_fuse$f.json; done' ;;
   8) $G --timeout 900 -- 'NT_B200_TEST_UNVERIFIED=1 timeout 800 python -m pytest tests/test_sample_gpu.py -x -q -s 2>&1 | tail -20' ;;
-  *) echo "usage: $0 <1..8>  (1 compat parity, 2 all single-GPU mega tests, 3 bench graph vs mega, 4 ncu of the kernel, 5 TP-2 exchange test, 6 TP-8 bench, 7 phase timeline, 8 GPU sampler)"; exit 2 ;;
+  9) $G --timeout 1200 -- 'timeout 1100 python tools/mega_bisect.py --model mid --mix Q4_K_M --fuse ${FUSE:-0} 2>&1 | tail -40' ;;
+  *) echo "usage: $0 <1..9>  (1 compat parity, 2 all single-GPU mega tests, 3 bench graph vs mega, 4 ncu of the kernel, 5 TP-2 exchange test, 6 TP-8 bench, 7 phase timeline, 8 GPU sampler, 9 per-phase GPU-vs-emulator bisect)"; exit 2 ;;
 esac
