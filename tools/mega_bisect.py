@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--model", default="mid", choices=["tiny", "mid"])
     ap.add_argument("--mix", default="Q4_K")
     ap.add_argument("--fuse", type=int, default=0)
-    ap.add_argument("--tol", type=float, default=1e-5)
+    ap.add_argument("--tol", type=float, default=1e-4)      # fast-math exp / division on the GPU vs libm in the emulator
     ap.add_argument("--token", type=int, default=17)
     args = ap.parse_args()
     os.environ["NT_B200_MEGA_FUSE"] = str(args.fuse)
