@@ -50,7 +50,8 @@ enum MegaEpilogue : int { MEP_STORE = 0, MEP_SWIGLU = 2, MEP_SLOT = 3 };
 enum MegaFuse : int { MEGA_FUSE_QUANT = 1, MEGA_FUSE_COMBINE = 2, MEGA_FUSE_NORM = 4 /* single rank only */,
                       MEGA_DEFER_RMS = 8 /* always on under tensor parallelism */,
                       MEGA_OVERLAP_ATTN = 16 /* needs MEGA_FUSE_COMBINE: stream the o-projection's weights during attention */,
-                      MEGA_SPLIT_TAIL = 32 /* cut a partly filled last round into 1- or 2-row stages spread over all warp slots */ };
+                      MEGA_SPLIT_TAIL = 32 /* cut a partly filled last round into 1- or 2-row stages spread over all warp slots */,
+                      MEGA_L2_PREFETCH = 64 /* experiment for wide tensor parallelism: pull the NEXT GEMV phase's rows into L2 */ };
 
 struct MegaMat {
     const uint8_t* W;
@@ -99,6 +100,10 @@ struct MegaPhase {
     //                      h * norm_w (the NEXT norm's weights, without the 1/rms factor) into xq_out; the consuming GEMV
     //                      (ssq_in != null) multiplies its results by rsqrt(sum(ssq_in) / hidden + eps)
     //                      => no MPH_NORM_XQ phase, two barriers less per layer.
+    // MEGA_L2_PREFETCH: the matrices of the GEMV phase after this one (whole allocations, 16-byte multiples); every CTA prefetches
+    // its 1/grid slice into L2 while this phase computes
+    const uint8_t* pf_ptr[3];
+    unsigned long long pf_bytes[3];
     unsigned* cnt;
     float* ssq_out;
     const float* ssq_in;

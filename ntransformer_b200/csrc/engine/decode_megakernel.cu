@@ -53,6 +53,7 @@ inline unsigned long long global_timer_ns() { return (unsigned long long)(cusim:
 inline void fence_proxy_async_smem() {}
 inline void prefetch_l2(const void*) {}
 inline unsigned long long sm_clock() { return (unsigned long long)(cusim::now_s() * 1e9); }
+inline void bulk_prefetch_l2(const void*, unsigned) {}
 #else
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
@@ -89,6 +90,9 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ unsigned long long sm_clock() { return (unsigned long long)clock64(); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {    // src and bytes: multiples of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 #endif
 
@@ -327,6 +331,19 @@ __device__ void gemv_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
         X.s16[4] = u1.x; X.s16[5] = u1.y; X.s16[6] = u1.z; X.s16[7] = u1.w;
     }
 
+    if ((d.fuse & MEGA_L2_PREFETCH) && warp == d.warps - 1 && lane == 0) {
+        // experiment (wide tensor parallelism, where a layer's shard fits the L2): this CTA's 1/grid slice of the next GEMV
+        // phase's matrices -> L2, fire and forget, while this phase computes
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const unsigned long long total = d.pf_bytes[i];
+            if (!total) continue;
+            const unsigned long long per = ((total + gridDim.x - 1) / gridDim.x + 15ull) & ~15ull;
+            unsigned long long off = per * blockIdx.x;
+            const unsigned long long end = min(total, off + per);
+            for (; off < end; off += 32768ull) bulk_prefetch_l2(d.pf_ptr[i] + off, (unsigned)min(32768ull, end - off));
+        }
+    }
     int slot = 0;
     for (int round = 0; round < n_rounds; round++) {
         // this slot's work in the round (segment 1, when there is one, is the same rows of the second matrix)
@@ -1110,6 +1127,20 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
     }
     // ring priming: at the end of a phase, start the next GEMV phase's weight stream unless an attention phase (which
     // aliases the ring area) still lies in between; the attention phase itself primes the GEMV that follows it.
+    if (fuse & MEGA_L2_PREFETCH) {
+        int prev = -1;
+        for (int i = 0; i < (int)plan.size(); i++) {
+            if (plan[i].kind != MPH_GEMV) continue;
+            if (prev >= 0) {
+                plan[prev].fuse |= MEGA_L2_PREFETCH;
+                for (int m = 0; m < plan[i].n_mat; m++) {
+                    plan[prev].pf_ptr[m] = plan[i].mat[m].W;
+                    plan[prev].pf_bytes[m] = ((unsigned long long)plan[i].mat[m].out * (unsigned long long)plan[i].mat[m].pitch) & ~15ull;
+                }
+            }
+            prev = i;
+        }
+    }
     pl.first_gemv = -1;
     const bool overlap = (pl.fuse & MEGA_OVERLAP_ATTN) != 0;
     for (int i = 0; i < (int)plan.size(); i++) {

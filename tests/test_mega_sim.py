@@ -240,6 +240,11 @@ def test_weights_stream_through_the_attention_phase(sim, tmp_path, fuse):
     m.close()
 
 
+def test_l2_prefetch_flag_is_functionally_neutral(sim, tmp_path):
+    # MEGA_L2_PREFETCH (64) only adds prefetch hints (no-ops in the emulator): the plan must stay consistent and results equal
+    check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=2, tp=2, grid=3, fuse=64 | 3, tol=5e-4)
+
+
 @pytest.mark.parametrize("fuse", [32, 63])
 def test_split_tail_rounds(sim, tmp_path, fuse):
     """MEGA_SPLIT_TAIL (32): the partly filled last round of a GEMV phase is dealt out 1 or 2 rows at a time over all warp slots
