@@ -776,6 +776,29 @@ __device__ void attn_phase(const MegaParams& P, Shared& S, const MegaPhase& d, u
     }
 }
 
+// Before the barrier that precedes an attention phase: the K/V cache rows of the units this CTA is about to process do not
+// depend on the token being computed, so start pulling them from HBM into L2 while the grid waits (hints only).
+__device__ void attn_prefetch(const MegaParams& P, const MegaPhase& next) {
+    const int pos = P.step[1], ctx = pos + 1;
+    const int n_groups = P.nh / P.gc, ratio = P.nh / P.nkv;
+    const SplitRule sr = split_rule(P, ctx, n_groups);
+    const int units = n_groups * sr.used;
+    const size_t row_bytes = (size_t)P.nkv * P.hd * sizeof(__half), head_bytes = (size_t)P.hd * sizeof(__half);
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int split = u / n_groups, grp = u - split * n_groups;
+        const int kv_head = (grp * P.gc) / ratio;
+        const int k_begin = split * sr.split_len, k_end = min(pos, k_begin + sr.split_len);      // the token's own row is not in the cache yet
+        const char* kb = static_cast<const char*>(next.kc) + (size_t)kv_head * head_bytes;
+        const char* vb = static_cast<const char*>(next.vc) + (size_t)kv_head * head_bytes;
+        const int lines = (int)((head_bytes + 127) / 128);
+        for (int t = threadIdx.x; t < (k_end - k_begin) * lines; t += NTHREADS) {
+            const size_t off = (size_t)(k_begin + t / lines) * row_bytes + (size_t)(t % lines) * 128;
+            prefetch_l2(kb + off);
+            prefetch_l2(vb + off);
+        }
+    }
+}
+
 // Merge the split partials of head h and emit its slice of the o-projection's xq (decode_combine_kernel with xq_out).
 // Called by threads 0..127 of a CTA (hd % 32 == 0: whole warps stay together in the quantiser).
 __device__ __forceinline__ void combine_head(const MegaParams& P, int h, int used) {
@@ -889,6 +912,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_step_kernel(const __grid_c
             __syncthreads();                                 // every warp is done with the ring area; descriptor i + 2 is visible
             prime_rings(S.ph[prime & 3], pr, smem, S.bars, warp, lane);
         }
+        if (i + 1 < P.n_phases && S.ph[(i + 1) & 3].kind == MPH_ATTN) attn_prefetch(P, S.ph[(i + 1) & 3]);
         if (tracing) trace[3 * i + 1] = sm_clock();
         mega_barrier(P, d.barrier, st);
         if (tracing) trace[3 * i + 2] = sm_clock();
