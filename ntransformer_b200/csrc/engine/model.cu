@@ -432,7 +432,10 @@ void Model::run_step_mega(bool with_head) {
 }
 
 void Model::run_step(bool with_head) {
-    if ((use_mega_ || env_on("NT_B200_MEGAKERNEL")) && ensure_mega()) { run_step_mega(with_head); return; }
+    // NT_B200_MEGAKERNEL: unset -> the model's own setting (set_use_megakernel, off by default), "0" -> off, anything else -> on
+    const char* mk = getenv("NT_B200_MEGAKERNEL");
+    const bool want_mega = mk ? env_on("NT_B200_MEGAKERNEL") : use_mega_;
+    if (want_mega && ensure_mega()) { run_step_mega(with_head); return; }
     if (!use_graph_ || getenv("NT_B200_NO_GRAPH")) {
         step_body(stream_);
         if (with_head) step_head(stream_);
