@@ -51,7 +51,8 @@ enum MegaFuse : int { MEGA_FUSE_QUANT = 1, MEGA_FUSE_COMBINE = 2, MEGA_FUSE_NORM
                       MEGA_DEFER_RMS = 8 /* always on under tensor parallelism */,
                       MEGA_OVERLAP_ATTN = 16 /* needs MEGA_FUSE_COMBINE: stream the o-projection's weights during attention */,
                       MEGA_SPLIT_TAIL = 32 /* cut a partly filled last round into 1- or 2-row stages spread over all warp slots */,
-                      MEGA_L2_PREFETCH = 64 /* experiment for wide tensor parallelism: pull the NEXT GEMV phase's rows into L2 */ };
+                      MEGA_L2_PREFETCH = 64 /* experiment for wide tensor parallelism: pull the NEXT GEMV phase's rows into L2 */,
+                      MEGA_XCHG_DIRECT = 128 /* experiment: every CTA signals every rank's arrival counter itself (no master hop) */ };
 
 struct MegaMat {
     const uint8_t* W;
@@ -124,7 +125,7 @@ struct MegaParams {
     int split_fixed;            // > 0: the graph path's rule (ctx cut into this many splits); 0: adaptive
     int min_split, max_split;   // adaptive rule: keys per split; max_split also sizes the score area in shared memory
     int attn_smem_off;          // byte offset of the attention phase's scratch inside the dynamic shared memory (0 = aliases the rings)
-    int pad3_;
+    int xchg_direct;            // MEGA_XCHG_DIRECT: the exchange is one remote atomic per CTA and rank instead of a master round trip
     unsigned* sync;             // MEGA_SYNC_WORDS words
     unsigned long long timeout_ns;
     int tp_rank, tp_size;
@@ -134,7 +135,7 @@ struct MegaParams {
     int trace_stride;               // values per CTA (3 x phases of the full program + 4)
     int pad2_;
     float* slots[MEGA_MAX_TP];      // rank r's slot buffer [2][tp_size][hidden] as mapped into this process
-    unsigned* flags[MEGA_MAX_TP];   // rank r's flag words (one 128-byte line per source rank)
+    unsigned* flags[MEGA_MAX_TP];   // rank r's flag words: one 128-byte line per source rank, then one line with its arrival counter
 };
 
 // What the plan builder needs to know about the model (device pointers owned by Model).

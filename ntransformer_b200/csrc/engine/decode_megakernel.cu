@@ -46,6 +46,7 @@ inline void red_release_gpu_add(unsigned* p, unsigned v) { __atomic_fetch_add(p,
 inline void red_relaxed_gpu_add(unsigned* p, unsigned v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
 inline void st_release_gpu(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline void st_relaxed_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline void red_relaxed_sys_add(unsigned* p, unsigned v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
 inline unsigned long long global_timer_ns() { return (unsigned long long)(cusim::now_s() * 1e9); }
 inline void fence_proxy_async_smem() {}
 inline void prefetch_l2(const void*) {}
@@ -75,6 +76,9 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_relaxed_sys_add(unsigned* p, unsigned v) {
+    asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void red_relaxed_gpu_add(unsigned* p, unsigned v) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -141,7 +145,15 @@ __device__ void mega_barrier(const MegaParams& P, int kind, SyncState& st) {
         // system fence followed by a relaxed arrive (the system fence subsumes the GPU-scope release).
         if (xchg) { __threadfence_system(); red_relaxed_gpu_add(counter, 1u); }
         else red_release_gpu_add(counter, 1u);
-        if (xchg) {
+        if (xchg && P.xchg_direct) {
+            // Experiment: no master hop.  Every CTA adds 1 to every rank's arrival counter (remote atomics over NVLink, posted) and
+            // waits until its own rank's counter has seen all tp_size * grid CTAs of this exchange.  The counter is never reset:
+            // the target grows with the exchange sequence number (a peer can be at most one exchange ahead).
+            for (int r = 0; r < P.tp_size; r++) red_relaxed_sys_add(P.flags[r] + 32 * P.tp_size, 1u);
+            const unsigned all = (st.xchg_base + st.xchg_idx) * (unsigned)P.tp_size * gridDim.x;
+            spin_until<true>(P.flags[P.tp_rank] + 32 * P.tp_size, all, abort_word, P.timeout_ns, st.bar_idx);
+            __threadfence_system();                                                 // acquire side: the peers' rows are visible
+        } else if (xchg) {
             const unsigned seq = st.xchg_base + st.xchg_idx;
             if (blockIdx.x == 0) {
                 spin_until<false>(counter, target, abort_word, P.timeout_ns, st.bar_idx);       // every local CTA has pushed its rows
@@ -902,8 +914,8 @@ bool DecodeMega::build(const MegaModelView& mv) {
     xq_h_ = dalloc<int8_t>(xq_bytes(hidden_)); xq_a_ = dalloc<int8_t>(xq_bytes(qdim)); xq_i_ = dalloc<int8_t>(xq_bytes(inter_));
     sync_ = dalloc<unsigned>(MEGA_SYNC_WORDS);
     const size_t slot_floats = (size_t)2 * tp_size_ * hidden_;
-    NT_CUDA_CHECK(cudaMalloc(&xchg_, slot_floats * sizeof(float) + (size_t)tp_size_ * 32 * sizeof(unsigned)));
-    NT_CUDA_CHECK(cudaMemset(xchg_, 0, slot_floats * sizeof(float) + (size_t)tp_size_ * 32 * sizeof(unsigned)));
+    NT_CUDA_CHECK(cudaMalloc(&xchg_, slot_floats * sizeof(float) + (size_t)(tp_size_ + 1) * 32 * sizeof(unsigned)));
+    NT_CUDA_CHECK(cudaMemset(xchg_, 0, slot_floats * sizeof(float) + (size_t)(tp_size_ + 1) * 32 * sizeof(unsigned)));
 
     cnt_quant_ = dalloc<unsigned>((size_t)inter_ / 32 + 1);
     cnt_attn_ = dalloc<unsigned>((size_t)mv.nh + 1);
@@ -929,6 +941,7 @@ bool DecodeMega::build(const MegaModelView& mv) {
     p_.q = q_; p_.k = k_; p_.v = v_; p_.attn_out = attn_; p_.attn_scratch = scratch_; p_.xq_a = xq_a_;
     p_.n_splits_max = plan_.n_splits_max; p_.split_fixed = plan_.split_fixed; p_.min_split = plan_.min_split; p_.max_split = plan_.max_split;
     p_.attn_smem_off = plan_.attn_smem_off;
+    p_.xchg_direct = (plan_.fuse & MEGA_XCHG_DIRECT) ? 1 : 0;
     p_.sync = sync_;
     p_.timeout_ns = 2000000000ull;
     if (const char* t = getenv("NT_B200_MEGA_TIMEOUT_MS")) p_.timeout_ns = (unsigned long long)atoll(t) * 1000000ull;

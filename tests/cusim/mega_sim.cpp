@@ -132,7 +132,7 @@ void* mega_sim_create(const char* gguf_path, int max_seq, int tp_size, int grid,
         R.xq_h.alloc(xq_bytes(c.hidden_size)); R.xq_a.alloc(xq_bytes(qdim)); R.xq_i.alloc(xq_bytes(inter));
         R.sync.alloc(MEGA_SYNC_WORDS * 4);
         const size_t slot_floats = (size_t)2 * tp_size * c.hidden_size;
-        R.xchg.alloc(slot_floats * 4 + (size_t)tp_size * 32 * 4);
+        R.xchg.alloc(slot_floats * 4 + (size_t)(tp_size + 1) * 32 * 4);
         MegaBuffers& B = R.B;
         B.hid[0] = R.hid[0].as<float>(); B.hid[1] = R.hid[1].as<float>(); B.q = R.q.as<float>(); B.k = R.k.as<float>();
         B.v = R.v.as<float>(); B.act = R.act.as<float>(); B.xq_h = R.xq_h.as<int8_t>(); B.xq_a = R.xq_a.as<int8_t>();
@@ -155,6 +155,7 @@ void* mega_sim_create(const char* gguf_path, int max_seq, int tp_size, int grid,
         P.q = B.q; P.k = B.k; P.v = B.v; P.attn_out = R.attn.as<float>(); P.attn_scratch = R.scratch.as<float>(); P.xq_a = B.xq_a;
         P.n_splits_max = R.plan.n_splits_max; P.split_fixed = R.plan.split_fixed; P.min_split = R.plan.min_split; P.max_split = R.plan.max_split;
         P.attn_smem_off = R.plan.attn_smem_off;
+        P.xchg_direct = (R.plan.fuse & MEGA_XCHG_DIRECT) ? 1 : 0;
         P.sync = R.sync.as<unsigned>();
         P.timeout_ns = 60ull * 1000000000ull;
         P.tp_rank = r; P.tp_size = tp_size;

@@ -240,6 +240,16 @@ def test_weights_stream_through_the_attention_phase(sim, tmp_path, fuse):
     m.close()
 
 
+def test_direct_exchange_protocol(sim, tmp_path):
+    """MEGA_XCHG_DIRECT (128): every CTA adds itself to every rank's never-reset arrival counter and waits for
+    sequence * tp * grid arrivals on its own — no master CTA, no second hop."""
+    check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=6, tp=2, grid=3, copy_delay=3, fuse=128 | 3, tol=5e-4)
+    check_against_oracle(sim, tmp_path, TP_CFG, "Q4_K", steps=3, tp=4, grid=4, fuse=128 | 51, tol=5e-4)
+    cfg = LlamaConfig(vocab_size=512, hidden_size=2048, intermediate_size=2048, n_layers=1, n_heads=32, n_kv_heads=8, head_dim=64,
+                      max_seq_len=64, bos_token_id=1, eos_token_id=2)
+    check_against_oracle(sim, tmp_path, cfg, "Q4_K", steps=2, tp=8, grid=8, fuse=128, tol=5e-4)
+
+
 def test_l2_prefetch_flag_is_functionally_neutral(sim, tmp_path):
     # MEGA_L2_PREFETCH (64) only adds prefetch hints (no-ops in the emulator): the plan must stay consistent and results equal
     check_against_oracle(sim, tmp_path, TINY, "Q4_K", steps=2, tp=2, grid=3, fuse=64 | 3, tol=5e-4)
