@@ -277,11 +277,8 @@ void launch_decode(float* out, const float* q, const __half* kc, const __half* v
     int split_len = (seq_len + n_splits - 1) / n_splits;
     n_splits = (seq_len + split_len - 1) / split_len;
     size_t smem = ((size_t)GC * split_len + (size_t)AW * GC * HD + (size_t)GC * HD + 2 * GC) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        NT_CUDA_CHECK(cudaFuncSetAttribute(decode_kernel<DPL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_MAX_DYN_SMEM));
-        configured = true;
-    }
+    static unsigned long long configured = 0;      // bit per device id
+    opt_in_dynamic_smem(decode_kernel<DPL, GC>, (int)(ATTN_MAX_DYN_SMEM), configured);
     NT_CHECK(smem <= (size_t)ATTN_MAX_DYN_SMEM, "attention_decode: context slice does not fit shared memory");
     float* scratch = nullptr;
     if (n_splits > 1) scratch = attn_scratch((size_t)n_heads * n_splits * (HD + 2));
@@ -304,11 +301,8 @@ void launch_decode_dyn(float* out, const float* q, const __half* kc, const __hal
     const int max_split_len = (max_seq + n_splits - 1) / n_splits;
     size_t smem = ((size_t)GC * max_split_len + (size_t)AW * GC * HD + (size_t)GC * HD + 2 * GC) * sizeof(float);
     NT_CHECK(smem <= (size_t)ATTN_MAX_DYN_SMEM, "attention_decode_dyn: context slice does not fit shared memory");
-    static bool configured = false;
-    if (!configured) {
-        NT_CUDA_CHECK(cudaFuncSetAttribute(decode_kernel<DPL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_MAX_DYN_SMEM));
-        configured = true;
-    }
+    static unsigned long long configured = 0;      // bit per device id
+    opt_in_dynamic_smem(decode_kernel<DPL, GC>, (int)(ATTN_MAX_DYN_SMEM), configured);
     launch_k(decode_kernel<DPL, GC>, dim3(groups, n_splits), dim3(AW * 32), smem, s, out, q, kc, vc, 0, n_heads, n_kv, scale,
              n_splits, 0, scratch, pos_dev);
     launch_k(decode_combine_kernel, dim3(n_heads), dim3(128), 0, s, out, (const float*)scratch, n_heads, HD, n_splits, 0, 0, pos_dev, xq_out);
@@ -321,11 +315,8 @@ void launch_prefill(float* out, const float* Q, const __half* kc, const __half* 
     constexpr int HD = DPL * 32;
     size_t smem = ((size_t)GC * (start_pos + seq_len) + (size_t)AW * GC * HD) * sizeof(float);
     NT_CHECK(smem <= (size_t)ATTN_MAX_DYN_SMEM, "attention_prefill: context does not fit shared memory");
-    static bool configured = false;
-    if (!configured) {
-        NT_CUDA_CHECK(cudaFuncSetAttribute(prefill_kernel<DPL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_MAX_DYN_SMEM));
-        configured = true;
-    }
+    static unsigned long long configured = 0;      // bit per device id
+    opt_in_dynamic_smem(prefill_kernel<DPL, GC>, (int)(ATTN_MAX_DYN_SMEM), configured);
     prefill_kernel<DPL, GC><<<dim3(n_heads / GC, seq_len), AW * 32, smem, s>>>(out, Q, kc, vc, start_pos, n_heads, n_kv, scale);
     count_launch();
 }

@@ -175,11 +175,8 @@ template <int HD>
 void launch(float* out, const float* Q, const __half* kc, const __half* vc, int seq_len, int start_pos, int n_heads, int n_kv,
             int max_seq, float scale, cudaStream_t s) {
     const int smem = 2 * 2 * BKV * (HD + PAD) * (int)sizeof(__half);
-    static bool configured = false;
-    if (!configured) {
-        NT_CUDA_CHECK(cudaFuncSetAttribute(prefill_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static unsigned long long configured = 0;      // bit per device id
+    opt_in_dynamic_smem(prefill_mma_kernel<HD>, (int)(smem), configured);
     prefill_mma_kernel<HD><<<dim3((seq_len + BQ - 1) / BQ, n_heads), 128, smem, s>>>(out, Q, kc, vc, seq_len, start_pos, n_heads, n_kv,
                                                                                     max_seq, scale);
     count_launch();

@@ -29,9 +29,11 @@ std::string Engine::generate(const std::string& prompt, const GenerateConfig& cf
     std::vector<float> logits((size_t)vocab);
     // Greedy without a repeat penalty needs no logits on the host: argmax runs on the GPU (4 B D2H instead of 513 KB).
     const bool gpu_greedy = cfg.temperature <= 0.0f && cfg.repeat_penalty <= 1.0f;
-    // Opt-in: penalty + top-k/top-p sampling on the GPU with the host's mt19937 stream (4 B D2H per token, csrc/sample.cu).
+    // Default: penalty + top-k/top-p sampling on the GPU with the host's mt19937 stream (4 B D2H per token, csrc/sample.cu);
+    // settings the kernel does not cover, --host-sampler and NT_B200_GPU_SAMPLER=0 take the host path (sampler.cpp:47-117).
     const char* gs_env = getenv("NT_B200_GPU_SAMPLER");
-    const bool gpu_sample = (cfg.gpu_sampler || (gs_env && *gs_env && std::string(gs_env) != "0")) && sample_topk_supported(vocab, cfg.temperature, cfg.top_k);
+    const bool gs_off = gs_env && std::string(gs_env) == "0";
+    const bool gpu_sample = cfg.gpu_sampler && !gs_off && sample_topk_supported(vocab, cfg.temperature, cfg.top_k);
     auto next_from = [&](float* dev_logits) {
         if (gpu_greedy) return model_.argmax_last();
         if (gpu_sample) {

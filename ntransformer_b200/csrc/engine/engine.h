@@ -18,7 +18,7 @@ struct GenerateConfig {             // defaults of engine.h:17-26
     int repeat_window = 64;
     uint64_t seed = 42;
     bool verbose = true;
-    bool gpu_sampler = false;          // sample on the GPU when the settings allow it (csrc/sample.cu); also NT_B200_GPU_SAMPLER=1
+    bool gpu_sampler = true;           // sample on the GPU when the settings allow it (csrc/sample.cu); --host-sampler / NT_B200_GPU_SAMPLER=0 turn it off
 };
 using TokenCallback = std::function<bool(const std::string& token, int token_id)>;
 

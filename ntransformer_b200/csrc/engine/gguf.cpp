@@ -1,4 +1,5 @@
-// gguf.cpp — see gguf.h. Bounds-checked cursor over the mmap (the reference trusts the file).
+// gguf.cpp — see gguf.h. Bounds-checked cursor over the mmap (the reference trusts the file): every count, shape and
+// offset read from the file is checked against the bytes that remain before anything is allocated or dereferenced.
 #include "gguf.h"
 
 #include <cinttypes>
@@ -17,7 +18,7 @@ struct Cursor {
     bool ok = true;
     template <typename T> T get() {
         T v{};
-        if (p + sizeof(T) > end) { ok = false; return v; }
+        if (!ok || (size_t)(end - p) < sizeof(T)) { ok = false; return v; }
         memcpy(&v, p, sizeof(T));
         p += sizeof(T);
         return v;
@@ -29,7 +30,10 @@ struct Cursor {
         p += n;
         return s;
     }
-    void skip(size_t n) { if (n > (size_t)(end - p)) ok = false; else p += n; }
+    void skip(size_t n) { if (!ok || n > (size_t)(end - p)) ok = false; else p += n; }
+    size_t left() const { return (size_t)(end - p); }
+    // n elements of es bytes each, without overflow
+    void skip_n(uint64_t n, size_t es) { if (!ok || es == 0 || n > left() / es) ok = false; else p += (size_t)n * es; }
 };
 
 enum : uint32_t { T_U8, T_I8, T_U16, T_I16, T_U32, T_I32, T_F32, T_BOOL, T_STR, T_ARR, T_U64, T_I64, T_F64 };
@@ -68,7 +72,9 @@ void skip_value(Cursor& c, uint32_t t) {
     if (t == T_ARR) {
         uint32_t et = c.get<uint32_t>();
         uint64_t n = c.get<uint64_t>();
-        if (size_t es = scalar_size(et)) { c.skip((size_t)n * es); return; }
+        if (size_t es = scalar_size(et)) { c.skip_n(n, es); return; }
+        if (et == T_ARR) { c.ok = false; return; }           // nested arrays: not produced by any writer we load; bounds the recursion
+        if (n > c.left()) { c.ok = false; return; }          // every element takes >= 1 byte
         for (uint64_t i = 0; i < n && c.ok; i++) skip_value(c, et);
         return;
     }
@@ -125,6 +131,8 @@ bool GGUFFile::parse() {
     if (version < 2 || version > 3) { fprintf(stderr, "Unsupported GGUF version: %u\n", version); return false; }
     uint64_t n_tensors = c.get<uint64_t>(), n_kv = c.get<uint64_t>();
     if (!c.ok) return false;
+    // a key needs >= 12 bytes (length + type), a tensor record >= 24 (name length, nd, type, offset): cap the counts by the file
+    if (n_kv > c.left() / 12 || n_tensors > c.left() / 24) { fprintf(stderr, "GGUF: header counts exceed the file size\n"); return false; }
     fprintf(stderr, "GGUF v%u: %" PRIu64 " tensors, %" PRIu64 " metadata entries\n", version, n_tensors, n_kv);
 
     for (uint64_t i = 0; i < n_kv && c.ok; i++) {
@@ -133,18 +141,23 @@ bool GGUFFile::parse() {
         if (type == T_ARR) {
             uint32_t et = c.get<uint32_t>();
             uint64_t n = c.get<uint64_t>();
+            if (!c.ok) break;
             if (key == "tokenizer.ggml.tokens" && et == T_STR) {
+                if (n > c.left() / 8) { c.ok = false; break; }          // a string takes >= 8 bytes
                 vocab_.tokens.reserve((size_t)n);
                 for (uint64_t j = 0; j < n && c.ok; j++) vocab_.tokens.push_back(c.str());
             } else if (key == "tokenizer.ggml.scores" && et == T_F32) {
+                if (n > c.left() / 4) { c.ok = false; break; }
                 vocab_.scores.reserve((size_t)n);
                 for (uint64_t j = 0; j < n && c.ok; j++) vocab_.scores.push_back(c.get<float>());
             } else if (key == "tokenizer.ggml.token_type" && et == T_I32) {
+                if (n > c.left() / 4) { c.ok = false; break; }
                 vocab_.token_types.reserve((size_t)n);
                 for (uint64_t j = 0; j < n && c.ok; j++) vocab_.token_types.push_back(c.get<int32_t>());
             } else if (size_t es = scalar_size(et)) {
-                c.skip((size_t)n * es);
+                c.skip_n(n, es);
             } else {
+                if (et == T_ARR || n > c.left()) { c.ok = false; break; }
                 for (uint64_t j = 0; j < n && c.ok; j++) skip_value(c, et);
             }
         } else {
@@ -177,12 +190,24 @@ bool GGUFFile::parse() {
         GGUFTensorInfo& t = tensors_[(size_t)i];
         t.name = c.str();
         uint32_t nd = c.get<uint32_t>();
-        if (nd > 8) { c.ok = false; break; }
-        int64_t n = 1;
-        for (uint32_t d = 0; d < nd; d++) { t.shape.push_back((int64_t)c.get<uint64_t>()); n *= t.shape.back(); }
+        if (nd < 1 || nd > 4) { c.ok = false; break; }        // GGML_MAX_DIMS = 4; a tensor has at least one dimension
+        uint64_t n = 1;
+        for (uint32_t d = 0; d < nd && c.ok; d++) {
+            const uint64_t e = c.get<uint64_t>();
+            // element counts stay far below 2^40 (a 70B embedding is 2^30): rejects zero, negative-as-int64 and overflowing shapes
+            if (e == 0 || e > ((uint64_t)1 << 40) || n > ((uint64_t)1 << 40) / e) { c.ok = false; break; }
+            t.shape.push_back((int64_t)e);
+            n *= e;
+        }
+        if (!c.ok) break;
         t.ggml_type = c.get<uint32_t>();
         t.dtype = ggml_to_dtype(t.ggml_type);
         t.offset = c.get<uint64_t>();
+        const size_t blk = dtype_block_size(t.dtype);
+        if (blk == 0 || (uint64_t)t.shape[0] % blk != 0) {       // quant blocks run along dimension 0 (the row)
+            fprintf(stderr, "GGUF: tensor '%s': row length %lld is not a multiple of the %zu-element block\n", t.name.c_str(), (long long)t.shape[0], blk);
+            return false;
+        }
         t.nbytes = dtype_row_size(t.dtype, (size_t)n);
         index_[t.name] = (size_t)i;
     }
@@ -191,6 +216,19 @@ bool GGUFFile::parse() {
     if (alignment <= 0 || (alignment & (alignment - 1))) alignment = 32;
     size_t header = (size_t)(c.p - base);
     data_offset_ = (header + (size_t)alignment - 1) & ~((size_t)alignment - 1);
+    // every tensor must lie inside the mapping (overflow-safe): checked here once, so data() can never hand out a wild pointer
+    if (data_offset_ > size_) {
+        if (!tensors_.empty()) { fprintf(stderr, "GGUF: tensor data starts beyond the end of the file\n"); return false; }
+        data_offset_ = size_;
+    }
+    const size_t avail = size_ - data_offset_;
+    for (const GGUFTensorInfo& t : tensors_) {
+        if (t.offset > avail || t.nbytes > avail - (size_t)t.offset) {
+            fprintf(stderr, "GGUF: tensor '%s' extends beyond the file (offset %" PRIu64 ", %zu bytes, %zu available)\n", t.name.c_str(),
+                    (uint64_t)t.offset, t.nbytes, avail);
+            return false;
+        }
+    }
     return true;
 }
 
@@ -200,8 +238,8 @@ const GGUFTensorInfo* GGUFFile::find(const std::string& name) const {
 }
 
 const void* GGUFFile::data(const GGUFTensorInfo& t) const {
-    size_t end = data_offset_ + (size_t)t.offset + t.nbytes;
-    if (end > size_) {      // same fatal condition as loader.cpp:247-255
+    const size_t avail = size_ - data_offset_;
+    if (t.offset > avail || t.nbytes > avail - (size_t)t.offset) {      // same fatal condition as loader.cpp:247-255; parse() already rejects such files
         fprintf(stderr, "\nERROR: Tensor '%s' extends beyond file! data_offset=%zu, tensor_offset=%zu, nbytes=%zu, file_size=%zu\n",
                 t.name.c_str(), data_offset_, (size_t)t.offset, t.nbytes, size_);
         abort();

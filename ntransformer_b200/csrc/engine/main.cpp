@@ -19,7 +19,7 @@ static void usage(const char* prog) {
     fprintf(stderr, "  --repeat-penalty <float> Repeat penalty (default: 1.1)\n");
     fprintf(stderr, "  -c, --ctx-size <int>     Context size (default: 4096)\n");
     fprintf(stderr, "  --seed <int>             Random seed (default: 42)\n");
-    fprintf(stderr, "  --gpu-sampler            Sample (penalty, top-k, top-p) on the GPU instead of the host [opt-in]\n");
+    fprintf(stderr, "  --host-sampler           Sample (penalty, top-k, top-p) on the host like the reference (default: on the GPU)\n");
     fprintf(stderr, "  --megakernel             Decode each token with one persistent kernel [opt-in]\n");
     fprintf(stderr, "  --benchmark              Run benchmark mode\n");
     fprintf(stderr, "  --chat                   Interactive chat mode\n");
@@ -49,6 +49,7 @@ int main(int argc, char** argv) {
         else if (a == "--seed") { if (auto v = val()) cfg.seed = std::stoull(v); }
         else if (a == "-c" || a == "--ctx-size") { if (auto v = val()) max_context = std::stoi(v); }
         else if (a == "--gpu-sampler") cfg.gpu_sampler = true;
+        else if (a == "--host-sampler") cfg.gpu_sampler = false;
         else if (a == "--megakernel") setenv("NT_B200_MEGAKERNEL", "1", 1);
         else if (a == "--benchmark") bench = true;
         else if (a == "--chat") chat = true;

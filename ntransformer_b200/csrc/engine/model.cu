@@ -521,8 +521,13 @@ void Model::prefill_batched(const int* tokens, int seq_len, int start_pos) {
     const size_t kv_stride = (size_t)max_seq * nkv_l_ * hd;
     ensure_prefill_buffers(std::min(seq_len, PREFILL_CHUNK));
     int last_rows = 0;
-    for (int c0 = 0; c0 < seq_len; c0 += PREFILL_CHUNK) {
-        const int T = std::min(PREFILL_CHUNK, seq_len - c0), p0 = start_pos + c0;
+    for (int c0 = 0, T = 0; c0 < seq_len; c0 += T) {
+        // A ragged tail of 1..15 tokens would miss the tiled attention kernel's 16-token minimum (and the per-query kernel it
+        // falls back to needs shared memory proportional to the whole context): shorten this chunk by 16 so the tail has >= 17.
+        T = std::min(PREFILL_CHUNK, seq_len - c0);
+        const int tail = seq_len - c0 - T;
+        if (tail > 0 && tail < 16) T -= 16;
+        const int p0 = start_pos + c0;
         last_rows = T;
         NT_CUDA_CHECK(cudaMemcpyAsync(pf_.tok, tokens + c0, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, s));
         iota_kernel<<<(T + 255) / 256, 256, 0, s>>>(pf_.pos, p0, T);

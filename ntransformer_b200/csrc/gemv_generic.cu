@@ -259,11 +259,8 @@ void gemv_generic(float* y, const void* W, const float* x, int out, int in, DTyp
     const uint8_t* w = static_cast<const uint8_t*>(W);
     if (dt == DType::F16 && in % 8 == 0 && pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (size_t)in * 4 <= (size_t)F16_MAX_SMEM && ep != GEMV_SWIGLU) {
-        static bool configured = false;
-        if (!configured) {
-            NT_CUDA_CHECK(cudaFuncSetAttribute(gemv_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_MAX_SMEM));
-            configured = true;
-        }
+        static unsigned long long configured = 0;      // bit per device id
+        opt_in_dynamic_smem(gemv_f16_kernel, (int)(F16_MAX_SMEM), configured);
         const int pairs = (out + 1) / 2;
         int grid16 = (pairs + F16_WARPS - 1) / F16_WARPS;
         const int resident = (int)std::min<size_t>(8, (size_t)(220 * 1024) / ((size_t)in * 4 + 1024)) * 148;   // CTAs the chip holds

@@ -127,6 +127,20 @@ void rmsnorm_split(void* workspace, const float* x, const float* w, int rows, in
 bool dequant_split_supported(DType dt);
 void dequant_split(void* w_hi, void* w_lo, const void* W, DType dt, size_t row_pitch, int rows, int cols, cudaStream_t s);
 
+// Opt-in to > 48 KB of dynamic shared memory.  The attribute is per DEVICE, so the "already done" state is a bit per device
+// id (a process that drives a second GPU must opt in there too).  `done` is the call site's static mask.
+template <typename K>
+inline void opt_in_dynamic_smem(K* kernel, int bytes, unsigned long long& done) {
+    int dev = 0;
+    NT_CUDA_CHECK(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done & bit) return;
+    NT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done |= bit;
+}
+// After a raw <<<>>> launch: a rejected configuration must not pass silently.
+#define NT_LAUNCH_CHECK() NT_CUDA_CHECK(cudaPeekAtLastError())
+
 // Number of kernels launched by this library since load (bench.py's gpu_launches claim).
 unsigned long long launch_count();
 void count_launch(int n = 1);

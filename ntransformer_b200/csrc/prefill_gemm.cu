@@ -349,11 +349,8 @@ bool launch_gemm(float* C, __half* split_out, const void* workspace, const void*
     if (!make_map(&map_a, workspace, 2 * Mp, (uint64_t)K, BM) || !make_map(&map_b, W, (uint64_t)N, (uint64_t)K, TN) ||
         !make_map(&map_b2, W2 ? W2 : W, (uint64_t)N, (uint64_t)K, TN))
         return false;
-    static bool configured = false;
-    if (!configured) {
-        NT_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
-        configured = true;
-    }
+    static unsigned long long configured = 0;      // bit per device id
+    opt_in_dynamic_smem(gemm_f16_tc_kernel<BN, MODE>, (int)(Cfg<BN>::SMEM), configured);
     const int tiles_m = (int)(Mp / BM), tiles_n = N / TN, n_tiles = tiles_n * tiles_m;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     // Tile order: concurrently running CTAs share the operand that is walked in the inner loop, the other one should stay

@@ -1,8 +1,5 @@
-"""Q4_0 on the TMA/dp4a GEMV path (NT_B200_Q4_0_TMA=1; process_stage<4> in csrc/gemv_kq_device.cuh) against the oracle.
-
-GATED (NT_B200_TEST_UNVERIFIED=1 or NT_B200_TEST_MEGA=1): written after round 1's GPU budget was spent; its arithmetic is
-verified through the CPU emulation of the persistent kernel (tests/test_mega_sim.py::test_q4_0_blocks_on_the_dp4a_path).  The
-switch is read once per process, hence the subprocess."""
+"""Q4_0 on the TMA/dp4a GEMV path (the default since round 2; process_stage<4> in csrc/gemv_kq_device.cuh) against the oracle,
+and the generic kernel (NT_B200_Q4_0_TMA=0) as the A/B twin.  The switch is read once per process, hence the subprocesses."""
 import os
 import subprocess
 import sys
@@ -10,9 +7,7 @@ from pathlib import Path
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("NT_B200_TEST_MEGA") != "1" and os.environ.get("NT_B200_TEST_UNVERIFIED") != "1",
-                                 reason="Q4_0 TMA path: opt-in until verified on hardware (NT_B200_TEST_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
 ROOT = Path(__file__).resolve().parent.parent
 
 SCRIPT = r'''
@@ -37,7 +32,8 @@ print("ok")
 ''' % str(ROOT)
 
 
-def test_q4_0_gemv_on_the_tma_path_matches_the_oracle():
-    env = dict(os.environ, NT_B200_Q4_0_TMA="1")
+@pytest.mark.parametrize("tma", ["1", "0"])
+def test_q4_0_gemv_matches_the_oracle(tma):
+    env = dict(os.environ, NT_B200_Q4_0_TMA=tma)
     r = subprocess.run([sys.executable, "-c", SCRIPT], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]
