@@ -256,23 +256,48 @@ def run_prefill(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+def workload_config(workload, prompt_len, ctx_first, steps, world):
+    """The workload's description: the same keys and values for both arms (ours / --impl reference) of one run."""
+    shape, mix, _, max_seq = WORKLOADS[workload]
+    return {"workload": workload, "quant_mix": mix, "batch": 1, "prompt_tokens": prompt_len,
+            "ctx_during_timing": [ctx_first, ctx_first + steps], "max_seq": max_seq,
+            "l2_policy": "weights read per step exceed the 126 MB L2 on every GPU; no flush needed"}
+
+
 def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
-    from ntransformer_b200 import kernels as K
-    from ntransformer_b200._lib import lib
-    from ntransformer_b200.dtypes import DType
-    from ntransformer_b200.engine import Model
-    from ntransformer_b200.model_spec import bytes_per_token, tensor_table
 
-    shape, mix, prompt_len, max_seq = WORKLOADS[args.workload]
-    if args.prompt_tokens is not None:
-        prompt_len = args.prompt_tokens
-    cfg = shape_cfg(shape, max_seq)
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure_decode(args, rank, world, args.workload, with_cpu=not args.no_cpu_baseline)
+    # BASELINE.json configs[3] (70B Q6_K, 8-way tensor parallel) rides along with the 8-GPU run of the metric's own config
+    # (Q4_K_M at every N, so that the 1/2/4/8 series stays one workload): reported under "configs3".
+    if world == 8 and args.workload == "llama3-70b-q4_k_m-decode" and not args.no_configs3:
+        extra = measure_decode(args, rank, world, "llama3-70b-q6_k-decode", with_cpu=False)
+        if rank == 0:
+            line["configs3"] = {k: extra[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "gpu_launches", "roofline", "tp")}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_decode(args, rank, world, workload, with_cpu):
+    import torch
+    import torch.distributed as dist
+    from ntransformer_b200 import kernels as K
+    from ntransformer_b200.dtypes import DType
+    from ntransformer_b200.engine import Model
+
+    shape, mix, prompt_len, max_seq = WORKLOADS[workload]
+    if args.prompt_tokens is not None:
+        prompt_len = args.prompt_tokens
+    cfg = shape_cfg(shape, max_seq)
+    local = int(os.environ.get("LOCAL_RANK", 0))
     model = Model.synthetic(cfg, mix, seed=1234, tp_rank=rank, tp_size=world)
     if world > 1:
         model.init_tp()
@@ -341,6 +366,16 @@ def run_ours(args, rank, world):
         e2e_ms = float(t.item())
     e2e_tok_s = args.steps / (e2e_ms / 1e3)
     assert np.isfinite(logits).all(), "non-finite logits"
+    tp_info = None
+    if world > 1:
+        # tensor-parallel lock-step: every rank must hold bit-identical logits (the replicas sample the same token)
+        mine = torch.from_numpy(np.ascontiguousarray(logits)).cuda()
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([1.0 if torch.equal(mine, ref) else 0.0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        assert float(same.item()) == 1.0, "tensor-parallel ranks diverged (logits differ between ranks)"
+        tp_info = {"ranks_bit_identical": True, "exchange": model.tp_exchange}
 
     # ---- roofline of the dominant kernel (fused gate+up K-quant GEMV), measured live ----
     peak, peak_src = measured_peak_hbm()
@@ -372,7 +407,7 @@ def run_ours(args, rank, world):
             kbytes = 2 * model._keep[names[0][0]][0].numel()
             ach = kbytes / (dur_ms / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": "gemv_kq_kernel (ffn gate+up fused, SwiGLU epilogue)", "achieved": round(ach, 1),
-                    "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": ncu_traffic(args.workload, world),
+                    "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": ncu_traffic(workload, world),
                     "bytes_per_launch": kbytes, "avg_launch_us": round(dur_ms * 1e3, 2), "launches_timed": len(evs),
                     "peak_source": peak_src}
         step_ach = b_tok * tok_s / 1e9
@@ -389,19 +424,18 @@ def run_ours(args, rank, world):
         roof["step_frac"] = round(step_ach / peak, 4)
         roof["step_bytes_per_gpu"] = b_tok
 
-    cpu = cpu_baseline(model, cfg, mix, world) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    cpu = cpu_baseline(model, cfg, mix, world) if (rank == 0 and world == 1 and with_cpu) else None
 
+    line = None
     if rank == 0:
         line = {
             "metric": "decode_tok_s", "value": round(tok_s, 2), "unit": "tok/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": DTYPE_NOTE, "data": "synthetic (seeded random valid GGUF blocks generated on the GPU)",
-            "config": {"workload": args.workload, "quant_mix": mix, "batch": 1, "prompt_tokens": prompt_len,
-                       "ctx_during_timing": [ctx_first, ctx_first + args.steps], "max_seq": max_seq,
-                       "parallelism": f"tp{world}" if world > 1 else "single",
-                       "l2_policy": "weights per step (%.1f GB/GPU) exceed the 126 MB L2; no flush needed" % (b_tok / 1e9),
-                       "cuda_graph": not model.megakernel_active,
-                       "decode_path": "persistent kernel (NT_B200_MEGAKERNEL)" if model.megakernel_active else "cuda graph of fused launches"},
+            "config": workload_config(workload, prompt_len, ctx_first, args.steps, world),
+            "path": {"parallelism": f"tp{world}" if world > 1 else "single", "cuda_graph": not model.megakernel_active,
+                     "decode_path": "persistent kernel (NT_B200_MEGAKERNEL)" if model.megakernel_active else "cuda graph of fused launches",
+                     "launches_per_step": round(launches / max(1, args.steps), 1), "weights_gb_per_gpu": round(b_tok / 1e9, 2)},
             "clocks": clocks,
             "e2e": {"value": round(e2e_tok_s, 2), "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": vocab * 4,
                     "ms_per_step": round(e2e_ms / args.steps, 4)},
@@ -410,13 +444,15 @@ def run_ours(args, rank, world):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        if tp_info:
+            line["tp"] = tp_info
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     model.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del model
+    torch.cuda.empty_cache()
+    return line
 
 
 def cpu_baseline(model, cfg, mix, world):
@@ -583,15 +619,124 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 activations x dequantised codes (reference CUDA-core kernels, sm_100 build)",
         "data": "synthetic (same seeded blocks as the B200 arm, written to a GGUF in /dev/shm)",
-        "config": {"workload": args.workload, "quant_mix": mix, "batch": 1, "prompt_tokens": p_len, "max_seq": max_seq,
-                   "parallelism": "single (the reference is single-GPU)", "device": "cuda:0",
-                   "note": "reference has no CPU path; this is its own CUDA path rebuilt for sm_100 (oracle/Makefile ref)"},
+        "config": workload_config(args.workload, p_len, p_len + args.warmup, args.steps, 1),
+        "path": {"parallelism": "single (the reference is single-GPU)", "cuda_graph": False, "device": "cuda:0",
+                 "decode_path": "the reference's own CUDA path rebuilt for sm_100 (oracle/Makefile ref); it has no CPU path"},
         "clocks": clocks,
         "cpu_baseline": {"value": round(tok_s, 2), "unit": "tok/s", "cores": 1, "kind": "reference",
                          "sample": f"{args.steps} decode steps through nt::Transformer::forward (1 host thread drives the GPU)"},
         "e2e": {"value": round(tok_s, 2), "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "setup_s": round(t_gen, 1),
     }), flush=True)
+
+
+def run_check(args, rank, world):
+    """Parity at the benchmarked configuration (not a timing): the workload's seeded model is written to a GGUF once, loaded by
+    the reference (oracle/_ref: its own loader + CUDA kernels, sm_100 build) and by our engine, and both decode greedily from the
+    same prompt.  Asserts logits <= 1e-3 relative (max |a - b| / max |b|) at every step where the histories agree and identical
+    greedy ids for --steps tokens.  One GPU (the reference is single-GPU); prints one JSON line."""
+    if rank != 0:
+        return
+    so = ROOT / "oracle" / "_ref" / "libnt_ref.so"
+    if not so.exists():
+        print(json.dumps({"check": args.workload, "unavailable": "oracle/_ref/libnt_ref.so was not built"}))
+        return
+    import torch
+    from ntransformer_b200.engine import Model
+    from ntransformer_b200.gguf_write import write_gguf_streaming
+    from ntransformer_b200.synth import random_blocks_cuda
+    from ntransformer_b200.model_spec import tensor_table
+
+    shape, mix, prompt_len, max_seq = WORKLOADS[args.workload]
+    cfg = shape_cfg(shape, max_seq)
+    if args.layers:                                   # a slice of the stack with full-width tensors (70B shapes in seconds)
+        from dataclasses import replace
+        cfg = replace(cfg, n_layers=args.layers)
+    torch.cuda.set_device(0)
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(tmpdir, f"nt_check_{args.workload}_{os.getpid()}.gguf")
+
+    def gen():
+        for idx, (name, dt, rows, cols) in enumerate(tensor_table(cfg, mix)):
+            s = 1234 + idx * 16
+            if name.endswith("norm.weight"):
+                g = torch.Generator(device="cuda")
+                g.manual_seed(s)
+                t = 1.0 + 0.1 * torch.randn(cols, generator=g, device="cuda", dtype=torch.float32)
+            else:
+                t = random_blocks_cuda(dt, rows, cols, s)
+            yield name, t.cpu().numpy(), dt, rows, cols
+    write_gguf_streaming(path, cfg, gen(), tensor_table(cfg, mix))
+    try:
+        ref = C.CDLL(str(so))
+        ref.ref_model_load.restype = C.c_void_p
+        ref.ref_model_load.argtypes = [C.c_char_p, C.c_int]
+        ref.ref_model_forward.restype = C.c_float
+        ref.ref_model_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        ref.ref_model_free.argtypes = [C.c_void_p]
+        devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(2)
+        os.dup2(devnull, 2)
+        try:
+            h = ref.ref_model_load(path.encode(), max_seq)
+            ours = Model.load(path, max_seq)
+        finally:
+            os.dup2(saved, 2)
+            os.close(devnull)
+        assert h, "reference failed to load the GGUF"
+        vocab = cfg.vocab_size
+        p_len = min(prompt_len, 16)                    # the reference prefills token by token
+        toks = np.array([token_at(i, vocab) for i in range(p_len)], np.int32)
+        lr = np.empty(vocab, np.float32)
+        ref.ref_model_forward(h, toks.ctypes.data_as(C.c_void_p), p_len, 0, lr.ctypes.data_as(C.c_void_p))
+        if args.per_token_prompt:
+            ours.set_prefill_min_tokens(0)
+        lo = ours.forward([int(t) for t in toks], 0).copy()          # 16 tokens: the batched tensor-core prefill, as a user gets it
+        rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+        errs = [rel(lo, lr)]
+        # conditioning of the synthetic model: the F64-accumulating CPU oracle on the same weights tells how far two correct F32
+        # implementations may drift apart (random weights make a deep stack chaotic; a trained checkpoint is far better behaved)
+        cond = None
+        if args.oracle_steps > 0:
+            from oracle import oracle as O
+            host = {name: (arr, int(dt)) for name, arr, dt, rows, cols in gen()}
+            c = cfg.dict()
+            c["max_seq_len"] = p_len + args.oracle_steps + 4
+            om = O.Model(c, host)
+            lq = om.forward([int(t) for t in toks], 0)
+            cond = {"ref_vs_f64": [rel(lr, lq)], "ours_vs_f64": [rel(lo, lq)]}
+        ids_o, ids_r, to, tr, pos, agree, first_bad = [], [], int(np.argmax(lo)), int(np.argmax(lr)), p_len, True, None
+        for step in range(args.steps):
+            ids_o.append(to)
+            ids_r.append(tr)
+            t = np.array([tr], np.int32)
+            ref.ref_model_forward(h, t.ctypes.data_as(C.c_void_p), 1, pos, lr.ctypes.data_as(C.c_void_p))
+            lo = ours.forward([to], pos).copy()
+            if agree and to != tr:
+                agree, first_bad = False, step
+            if agree:
+                errs.append(rel(lo, lr))
+                if cond is not None and step < args.oracle_steps:
+                    lq = om.forward([tr], pos)
+                    cond["ref_vs_f64"].append(rel(lr, lq))
+                    cond["ours_vs_f64"].append(rel(lo, lq))
+            to, tr, pos = int(np.argmax(lo)), int(np.argmax(lr)), pos + 1
+        worst = max(errs)
+        ref.ref_model_free(h)
+        ours.close()
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
+    ok = ids_o == ids_r and worst <= 1e-3
+    if cond is not None:
+        cond = {k: [float("%.3g" % v) for v in vs] for k, vs in cond.items()}
+    print(json.dumps({"check": args.workload, "layers": cfg.n_layers, "steps": args.steps, "prompt_tokens": p_len,
+                      "max_rel_logit_err": worst, "err_after_prompt": errs[0], "err_first_steps": [float("%.3g" % e) for e in errs[1:9]],
+                      "first_id_mismatch_step": first_bad, "conditioning": cond,
+                      "tolerance": 1e-3, "greedy_ids_identical": ids_o == ids_r, "ok": ok,
+                      "against": "oracle/_ref (the reference's loader + CUDA kernels + Transformer::forward, sm_100 build), same GGUF"}),
+          flush=True)
+    if not ok:
+        sys.exit(1)
 
 
 def main():
@@ -602,14 +747,23 @@ def main():
     ap.add_argument("--workload", default="llama3-70b-q4_k_m-decode", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs3", action="store_true", help="8 GPUs: skip the extra 70B Q6_K run reported under configs3")
+    ap.add_argument("--check", action="store_true",
+                    help="parity instead of timing: the same seeded GGUF through the reference's CUDA path (oracle/_ref) and ours; "
+                         "logits <= 1e-3 relative and --steps greedy ids identical")
     ap.add_argument("--prompt-tokens", type=int, default=None, help="override the workload's prompt length (profiling)")
+    ap.add_argument("--layers", type=int, default=0, help="--check only: keep this many layers of the workload's shape (0 = all)")
+    ap.add_argument("--oracle-steps", type=int, default=0, help="--check only: also run the F64-accumulating CPU oracle for the prompt and this many steps")
+    ap.add_argument("--per-token-prompt", action="store_true", help="--check only: our engine replays the prompt token by token like the reference")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if world != args.gpus and world == 1 and args.gpus > 1:
         sys.exit("bench.py --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
-    if args.impl == "reference":
+    if args.check:
+        run_check(args, rank, world)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     elif "prefill" in args.workload:
         run_prefill(args, rank, world)

@@ -82,6 +82,26 @@ void   nt_b200_quantize_x(const float* x, void* xq, int K, void* stream);
  * epilogue: 0 store, 1 y += W.x, 2 y0 = silu(W0.x) * (W1.x) */
 int    nt_b200_gemv_fused(int n_mat, float* const* y, const void* const* W, const int* out_features,
                           const int* dtypes, int in_features, const void* xq, int epilogue, void* stream);
+/* nt_b200_gemv_fused fed with the F32 activation vector itself: the kernel quantises x in its prologue (one pass, staged over
+ * the part of its TMA ring that is primed afterwards), so no separate quantise launch is needed.  norm_w (may be NULL): the
+ * GEMV of RMSNorm(x) * norm_w (src/cuda/rmsnorm.cu:17-70 followed by launch_gemv): the prologue quantises x * norm_w, sums x^2
+ * in the same pass and scales the results by rsqrt(mean(x^2) + eps) — equal to normalise-then-multiply up to round-off.
+ * Replaces the launch pairs launch_rmsnorm + launch_gemv of src/model/attention.cpp:144-162 and src/model/ffn.cpp:96-133.
+ * Returns 0, or < 0 when rejected (nothing launched). */
+int    nt_b200_gemv_fused_f32(int n_mat, float* const* y, const void* const* W, const int* out_features,
+                              const int* dtypes, int in_features, const float* x, const float* norm_w, float eps,
+                              int epilogue, void* stream);
+/* The decode step's attention sub-block in ONE launch: launch_rope (src/cuda/rotary.cu:113-140; q and k are read, not
+ * modified) + launch_copy_to_kv_cache at row *pos_dev (src/cuda/attention.cu:405-425) + launch_attention_decode over
+ * *pos_dev + 1 keys (src/cuda/attention.cu:348-375), context split over CTAs, merged by the last CTA of each head group.
+ * scratch: nt_b200_attention_decode_scratch_floats() floats; tickets: nt_b200_attention_decode_tickets() zeroed words (left
+ * zeroed); xq_out (may be NULL): the output also in xq form.  head_dim 64 / 128 / 256. */
+size_t nt_b200_attention_decode_scratch_floats(int max_seq, int n_heads, int n_kv_heads, int head_dim);
+int    nt_b200_attention_decode_tickets(int n_heads, int n_kv_heads);
+void   nt_b200_attention_decode_fused(float* out, const float* q, const float* k, const float* v, void* k_cache,
+                                      void* v_cache, const int* pos_dev, int max_seq, int n_heads, int n_kv_heads,
+                                      int head_dim, float theta_base, float freq_scale, float scale, float* scratch,
+                                      unsigned* tickets, void* xq_out, void* stream);
 void   nt_b200_embed_rows(float* out, const void* table, int dtype, const int* tokens_dev,
                           int n_tokens, int hidden, void* stream);
 /* Prefill GEMM on the tcgen05 tensor cores: C[M,N] (F32, row-major) = A[M,K] (F32) . W[N,K]^T (F16 weights, GGUF F16

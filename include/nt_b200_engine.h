@@ -63,6 +63,13 @@ float nt_sampler_uniform(uint64_t seed, int n_draws_before);
  * cache.  Models whose shapes/dtypes the kernel does not cover keep the graph path (a note goes to stderr).
  * Also enabled by the environment variable NT_B200_MEGAKERNEL=1.  Call before the first forward. */
 void nt_model_use_megakernel(nt_model_t m, int on);
+/* wall-clock seconds nt_model_load_gguf took for this model (header parse + shard plan + pipelined pread -> pinned staging ->
+ * cudaMemcpyAsync upload + buffer allocation); 0 for models built from device tensors.  Reference behaviour it replaces: one
+ * synchronous cudaMemcpy per tensor from the pageable mmap (src/model/transformer.cpp:286-328, src/core/tensor.cpp:224-225). */
+double nt_model_load_seconds(nt_model_t m);
+/* how a tensor-parallel model sums the o-projection / down-projection partials: 0 not tensor parallel (or no step run yet),
+ * 1 ncclAllReduce, 2 NVLink peer-memory exchange fused into the GEMV epilogue (default; NT_B200_TP_NCCL=1 selects 1) */
+int  nt_model_tp_exchange(nt_model_t m);
 int  nt_model_megakernel_active(nt_model_t m);      /* 1 once the persistent kernel has been built and is in use */
 /* phase kinds of the persistent kernel's per-token program (0 norm+quantise, 1 quantise, 2 GEMV, 3 attention,
  * 4 combine); returns the number of phases (may exceed cap), 0 when the kernel is not active */

@@ -40,6 +40,8 @@ ENGINE_SIGNATURES = {
     "nt_model_sample": (_i, [_vp, _f, _i, _f, _f, _vp, _i, _f]),
     "nt_sampler_uniform": (_f, [C.c_uint64, _i]),
     "nt_model_use_megakernel": (None, [_vp, _i]),
+    "nt_model_tp_exchange": (_i, [_vp]),
+    "nt_model_load_seconds": (C.c_double, [_vp]),
     "nt_model_megakernel_active": (_i, [_vp]),
     "nt_model_megakernel_plan": (_i, [_vp, _vp, _i]),
     "nt_model_megakernel_trace": (None, [_vp, _i]),

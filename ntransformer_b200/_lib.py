@@ -42,6 +42,10 @@ SIGNATURES = {
     "nt_b200_xq_bytes": (_sz, [_i]),
     "nt_b200_quantize_x": (None, [_vp, _vp, _i, _vp]),
     "nt_b200_gemv_fused": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _i, _vp]),
+    "nt_b200_gemv_fused_f32": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _vp, _f, _i, _vp]),
+    "nt_b200_attention_decode_scratch_floats": (_sz, [_i, _i, _i, _i]),
+    "nt_b200_attention_decode_tickets": (_i, [_i, _i]),
+    "nt_b200_attention_decode_fused": (None, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "nt_b200_embed_rows": (None, [_vp, _vp, _i, _vp, _i, _i, _vp]),
     "nt_b200_gemm_f16_tc_workspace_bytes": (_sz, [_i, _i]),
     "nt_b200_gemm_f16_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -24,6 +24,8 @@ namespace {
 
 constexpr int AW = 8;                    // warps per CTA
 constexpr int MAX_SPLITS = 64;
+constexpr int FUSED_MIN_SPLIT = 64;      // decode_fused_kernel: at least this many keys per context slice (one slice = no merge step)
+constexpr int KU = 8;                    // cache rows a warp keeps in flight in the score and P.V loops
 constexpr int ATTN_MAX_DYN_SMEM = 227 * 1024 - 1024;   // static __shared__ (s_max/s_sum) counts against the 227 KB cap
 
 template <int N> struct HalfVec;         // N halfs loaded as one vector
@@ -61,13 +63,60 @@ __device__ __forceinline__ float transpose_reduce(float (&v)[GC], int lane) {
     return r;
 }
 
+// Decode-step fusion (decode_fused_kernel): the token at cache row `pos` is not in the cache yet.  Its key arrives unrotated
+// in F32 from the q/k/v GEMV; the warp that reaches row `pos` rotates it (reference rotary.cu:16-62, pairs (i, i + hd/2)), rounds
+// key and value to F16 exactly as the cache write does (attention.cu:338-339) and — in the one CTA per KV head that owns the
+// write — stores the row.  pos < 0: plain attention over the cache, queries used as given.
+struct NewToken {
+    const float* k = nullptr;      // [n_kv][HD]
+    const float* v = nullptr;
+    int pos = -1;
+    float theta = 0.f, freq_scale = 1.f;
+    __half* kc_w = nullptr;        // cache base pointers, non-null only in the CTA that stores the row
+    __half* vc_w = nullptr;
+};
+
+// cos / sin of this lane's DPL rotation pairs.  Lane L holds dims [L*DPL, L*DPL + DPL): lanes 0-15 the first half of the
+// head, lanes 16-31 the second, so a pair (i, i + hd/2) lives in lanes (L, L ^ 16) at the same register index.
+// Same expression as rope_kv_decode_kernel / the reference (fast-math powf, cosf, sinf).
+template <int DPL>
+__device__ __forceinline__ void rope_angles(float (&c)[DPL], float (&sn)[DPL], int lane, int pos, float theta_base, float freq_scale) {
+    constexpr int head_dim = DPL * 32;
+#pragma unroll
+    for (int i = 0; i < DPL; i++) {
+        const int pair = (lane & 15) * DPL + i;
+        float freq = 1.0f / powf(theta_base, (2.0f * pair) / head_dim);
+        float angle = pos * freq * freq_scale;
+        c[i] = cosf(angle); sn[i] = sinf(angle);
+    }
+}
+template <int DPL>
+__device__ __forceinline__ void rope_rotate(float (&x)[DPL], const float (&c)[DPL], const float (&sn)[DPL], int lane) {
+#pragma unroll
+    for (int i = 0; i < DPL; i++) {
+        const float other = __shfl_xor_sync(0xFFFFFFFFu, x[i], 16);
+        const bool lo = lane < 16;
+        const float x0 = lo ? x[i] : other, x1 = lo ? other : x[i];
+        const float r0 = x0 * c[i] - x1 * sn[i], r1 = x1 * c[i] + x0 * sn[i];
+        x[i] = lo ? r0 : r1;
+    }
+}
+template <int DPL>
+__device__ __forceinline__ void store_row_f16(__half* p, const __half (&h)[DPL]) {
+    typename HalfVec<DPL>::T raw;
+    __half* d = reinterpret_cast<__half*>(&raw);
+#pragma unroll
+    for (int i = 0; i < DPL; i++) d[i] = h[i];
+    *reinterpret_cast<typename HalfVec<DPL>::T*>(p) = raw;
+}
+
 // One CTA: GC query heads of one KV head, keys [k_begin, k_end).
 // q_base: first of the GC heads' query vectors (contiguous [GC][hd]); out likewise.
 // If part_* != nullptr writes unnormalised partials, else the normalised output.
 template <int DPL, int GC>
 __device__ void attend_group(float* __restrict__ out, const float* __restrict__ q_base, const __half* __restrict__ kc,
                              const __half* __restrict__ vc, int kv_head, int n_kv, int k_begin, int k_end, float scale,
-                             float* __restrict__ part_o, float* __restrict__ part_ml, float* smem) {
+                             float* __restrict__ part_o, float* __restrict__ part_ml, float* smem, const NewToken nt = NewToken{}) {
     constexpr int HD = DPL * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_keys = k_end - k_begin;
@@ -83,21 +132,58 @@ __device__ void attend_group(float* __restrict__ out, const float* __restrict__ 
     for (int g = 0; g < GC; g++)
 #pragma unroll
         for (int i = 0; i < DPL; i++) qr[g][i] = q_base[(size_t)g * HD + lane * DPL + i];
+    float rc[DPL], rs[DPL];
+    if (nt.pos >= 0) {                                   // fused decode step: the queries arrive unrotated
+        rope_angles<DPL>(rc, rs, lane, nt.pos, nt.theta, nt.freq_scale);
+#pragma unroll
+        for (int g = 0; g < GC; g++) rope_rotate<DPL>(qr[g], rc, rs, lane);
+    }
 
-    // ---- phase 1: scores ----
-    for (int p = warp; p < n_keys; p += AW) {
-        float kf[DPL];
-        load_row<DPL>(kbase + (size_t)(k_begin + p) * row_stride, kf);
-        float part[GC];
+    // ---- phase 1: scores (KU cache rows in flight per warp: one memory round trip per KU keys).  A slice of at most AW * KU
+    // keys is one batch: its V rows are fetched in the same round trip and wait in registers for phase 3. ----
+    const bool single = n_keys <= AW * KU;
+    float vpre[KU][DPL];
+    for (int p0 = warp; p0 < n_keys; p0 += AW * KU) {
+        float kf[KU][DPL];
+        if (single) {
 #pragma unroll
-        for (int g = 0; g < GC; g++) {
-            float a = 0.f;
-#pragma unroll
-            for (int i = 0; i < DPL; i++) a = fmaf(qr[g][i], kf[i], a);
-            part[g] = a;
+            for (int u = 0; u < KU; u++) {
+                const int p = p0 + u * AW;
+                if (p >= n_keys) break;
+                if (k_begin + p != nt.pos) load_row<DPL>(vbase + (size_t)(k_begin + p) * row_stride, vpre[u]);
+            }
         }
-        float tot = transpose_reduce<GC>(part, lane);
-        if ((lane & (32 / GC - 1)) == 0) sc[(size_t)(lane / (32 / GC)) * n_keys + p] = tot * scale;
+#pragma unroll
+        for (int u = 0; u < KU; u++) {
+            const int p = p0 + u * AW;
+            if (p >= n_keys) break;                          // warp-uniform
+            if (k_begin + p == nt.pos) {                     // warp-uniform: the new token's key, not in the cache yet
+#pragma unroll
+                for (int i = 0; i < DPL; i++) kf[u][i] = nt.k[(size_t)kv_head * HD + lane * DPL + i];
+                rope_rotate<DPL>(kf[u], rc, rs, lane);
+                __half kh[DPL];
+#pragma unroll
+                for (int i = 0; i < DPL; i++) { kh[i] = __float2half(kf[u][i]); kf[u][i] = __half2float(kh[i]); }
+                if (nt.kc_w) store_row_f16<DPL>(nt.kc_w + (size_t)nt.pos * row_stride + (size_t)kv_head * HD + (size_t)lane * DPL, kh);
+            } else {
+                load_row<DPL>(kbase + (size_t)(k_begin + p) * row_stride, kf[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < KU; u++) {
+            const int p = p0 + u * AW;
+            if (p >= n_keys) break;
+            float part[GC];
+#pragma unroll
+            for (int g = 0; g < GC; g++) {
+                float a = 0.f;
+#pragma unroll
+                for (int i = 0; i < DPL; i++) a = fmaf(qr[g][i], kf[u][i], a);
+                part[g] = a;
+            }
+            float tot = transpose_reduce<GC>(part, lane);
+            if ((lane & (32 / GC - 1)) == 0) sc[(size_t)(lane / (32 / GC)) * n_keys + p] = tot * scale;
+        }
     }
     __syncthreads();
     // ---- phase 2: per-head max / exp / sum (warp g <-> head g) ----
@@ -120,14 +206,34 @@ __device__ void attend_group(float* __restrict__ out, const float* __restrict__ 
     for (int g = 0; g < GC; g++)
 #pragma unroll
         for (int i = 0; i < DPL; i++) acc[g][i] = 0.f;
-    for (int p = warp; p < n_keys; p += AW) {
-        float vf[DPL];
-        load_row<DPL>(vbase + (size_t)(k_begin + p) * row_stride, vf);
+    for (int p0 = warp; p0 < n_keys; p0 += AW * KU) {
+        float vf[KU][DPL];
 #pragma unroll
-        for (int g = 0; g < GC; g++) {
-            float w = sc[(size_t)g * n_keys + p];
+        for (int u = 0; u < KU; u++) {
+            const int p = p0 + u * AW;
+            if (p >= n_keys) break;
+            if (k_begin + p == nt.pos) {                     // the new token's value: F16-rounded like the cache row it becomes
+                __half vh[DPL];
 #pragma unroll
-            for (int i = 0; i < DPL; i++) acc[g][i] = fmaf(w, vf[i], acc[g][i]);
+                for (int i = 0; i < DPL; i++) { vh[i] = __float2half(nt.v[(size_t)kv_head * HD + lane * DPL + i]); vf[u][i] = __half2float(vh[i]); }
+                if (nt.vc_w) store_row_f16<DPL>(nt.vc_w + (size_t)nt.pos * row_stride + (size_t)kv_head * HD + (size_t)lane * DPL, vh);
+            } else if (single) {
+#pragma unroll
+                for (int i = 0; i < DPL; i++) vf[u][i] = vpre[u][i];
+            } else {
+                load_row<DPL>(vbase + (size_t)(k_begin + p) * row_stride, vf[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < KU; u++) {
+            const int p = p0 + u * AW;
+            if (p >= n_keys) break;
+#pragma unroll
+            for (int g = 0; g < GC; g++) {
+                float w = sc[(size_t)g * n_keys + p];
+#pragma unroll
+                for (int i = 0; i < DPL; i++) acc[g][i] = fmaf(w, vf[u][i], acc[g][i]);
+            }
         }
     }
 #pragma unroll
@@ -232,6 +338,96 @@ __global__ void decode_combine_kernel(float* __restrict__ out, const float* __re
     }
 }
 
+// The decode step's whole attention sub-block in ONE launch: RoPE of the queries and of the new key, the F16 KV-cache write
+// at row *pos_dev, split-context GQA attention, and — by the CTA that finishes a head group's last split ("last arriver", one
+// ticket per head group) — the merge of the splits and the xq form of the result for the o-projection.  Replaces
+// rope_kv_decode_kernel + decode_kernel + decode_combine_kernel (reference K14 rotary.cu:16-62, K15 attention.cu:316-342,
+// K16 attention.cu:108-202); the merge keeps decode_combine_kernel's arithmetic and order, so both paths agree bit for bit
+// whenever they cut the context at the same places.
+template <int DPL, int GC>
+__global__ void __launch_bounds__(AW * 32) decode_fused_kernel(float* __restrict__ out, const float* __restrict__ q,
+                                                               const float* __restrict__ k_new, const float* __restrict__ v_new,
+                                                               __half* __restrict__ kc, __half* __restrict__ vc,
+                                                               const int* __restrict__ pos_dev, int n_heads, int n_kv, float scale,
+                                                               float theta, float freq_scale, int n_splits, int min_split,
+                                                               float* __restrict__ scratch, unsigned* __restrict__ tickets,
+                                                               int8_t* __restrict__ xq_out) {
+    constexpr int HD = DPL * 32;
+    extern __shared__ float smem_dyn[];
+    __shared__ int s_last;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int pos = *pos_dev, seq_len = pos + 1;
+    int split_len = (seq_len + n_splits - 1) / n_splits;
+    if (split_len < min_split) split_len = min_split;      // short contexts: few, reasonably long slices
+    const int used = (seq_len + split_len - 1) / split_len;
+    const int head0 = blockIdx.x * GC, split = blockIdx.y;
+    const int per_kv = n_heads / n_kv, kv_head = head0 / per_kv;
+    const int k_begin = split * split_len, k_end = min(seq_len, k_begin + split_len);
+    if (k_begin >= k_end) return;
+    NewToken nt;
+    nt.k = k_new; nt.v = v_new; nt.pos = pos; nt.theta = theta; nt.freq_scale = freq_scale;
+    if (head0 % per_kv == 0) { nt.kc_w = kc; nt.vc_w = vc; }      // one CTA per KV head stores the new row (the split that holds pos)
+    if (used == 1 && !xq_out) {                            // short context: one slice per head group, normalised output, no merge
+        attend_group<DPL, GC>(out + (size_t)head0 * HD, q + (size_t)head0 * HD, kc, vc, kv_head, n_kv, k_begin, k_end, scale, nullptr, nullptr,
+                              smem_dyn, nt);
+        return;
+    }
+    float* stage = smem_dyn + (size_t)GC * (k_end - k_begin) + (size_t)AW * GC * HD;   // [GC][HD] + [GC][2]
+    attend_group<DPL, GC>(nullptr, q + (size_t)head0 * HD, kc, vc, kv_head, n_kv, k_begin, k_end, scale, stage, stage + GC * HD,
+                          smem_dyn, nt);
+    __syncthreads();
+    float* ml_all = scratch + (size_t)n_heads * n_splits * HD;
+    for (int idx = threadIdx.x; idx < GC * HD; idx += AW * 32) {
+        const int g = idx / HD, d = idx - g * HD;
+        scratch[((size_t)(head0 + g) * n_splits + split) * HD + d] = stage[idx];
+    }
+    if (threadIdx.x < 2 * GC) {
+        const int g = threadIdx.x >> 1;
+        ml_all[((size_t)(head0 + g) * n_splits + split) * 2 + (threadIdx.x & 1)] = stage[GC * HD + threadIdx.x];
+    }
+    // ---- last arriver of the head group merges the splits ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(tickets + blockIdx.x, 1u);
+        s_last = ((int)prev + 1 == used);
+        if (s_last) tickets[blockIdx.x] = 0;                   // ready for the next launch (all arrivals are in)
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < GC; g += AW) {
+        const int h = head0 + g;
+        const float* ml = ml_all + (size_t)h * n_splits * 2;
+        float m = -FLT_MAX;
+        for (int i = 0; i < used; i++) m = fmaxf(m, __ldcg(ml + 2 * i));
+        float l = 0.f;
+        for (int i = 0; i < used; i++) l += __ldcg(ml + 2 * i + 1) * expf(__ldcg(ml + 2 * i) - m);
+        const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+        for (int d = lane; d < HD; d += 32) {
+            float o = 0.f;
+            for (int i = 0; i < used; i++) o += __ldcg(scratch + ((size_t)h * n_splits + i) * HD + d) * expf(__ldcg(ml + 2 * i) - m);
+            const float v = o * inv;
+            out[(size_t)h * HD + d] = v;
+            if (xq_out) {
+                const int K = n_heads * HD, e = h * HD + d;
+                int q1, q2, q3;
+                float sc, s16;
+                quantize_lane32(v, q1, q2, q3, sc, s16);
+                const int se = (int)xq_swizzle((uint32_t)e);
+                xq_out[se] = (int8_t)q1;
+                xq_out[K + se] = (int8_t)q2;
+                xq_out[2 * K + se] = (int8_t)q3;
+                float* xscale = reinterpret_cast<float*>(xq_out + 3 * (size_t)K);
+                if (lane == 0) xscale[e >> 5] = sc;
+                if ((lane & 15) == 0) xscale[K / 32 + (e >> 4)] = s16;
+            }
+        }
+    }
+}
+
 template <int DPL, int GC>
 __global__ void __launch_bounds__(AW * 32) prefill_kernel(float* __restrict__ out, const float* __restrict__ Q,
                                                           const __half* __restrict__ kc, const __half* __restrict__ vc,
@@ -310,6 +506,23 @@ void launch_decode_dyn(float* out, const float* q, const __half* kc, const __hal
 }
 
 template <int DPL, int GC>
+void launch_decode_fused(float* out, const float* q, const float* k_new, const float* v_new, __half* kc, __half* vc, const int* pos_dev,
+                         int max_seq, int n_heads, int n_kv, float theta, float freq_scale, float scale, float* scratch, int n_splits,
+                         unsigned* tickets, int8_t* xq_out, cudaStream_t s) {
+    constexpr int HD = DPL * 32;
+    const int groups = n_heads / GC;
+    int max_split_len = (max_seq + n_splits - 1) / n_splits;
+    if (max_split_len < FUSED_MIN_SPLIT) max_split_len = FUSED_MIN_SPLIT;
+    size_t smem = ((size_t)GC * max_split_len + (size_t)AW * GC * HD + (size_t)GC * HD + 2 * GC) * sizeof(float);
+    NT_CHECK(smem <= (size_t)ATTN_MAX_DYN_SMEM, "attention_decode_fused: context slice does not fit shared memory");
+    static unsigned long long configured = 0;      // bit per device id
+    opt_in_dynamic_smem(decode_fused_kernel<DPL, GC>, (int)(ATTN_MAX_DYN_SMEM), configured);
+    launch_k(decode_fused_kernel<DPL, GC>, dim3(groups, n_splits), dim3(AW * 32), smem, s, out, q, k_new, v_new, kc, vc, pos_dev, n_heads,
+             n_kv, scale, theta, freq_scale, n_splits, FUSED_MIN_SPLIT, scratch, tickets, xq_out);
+    count_launch();
+}
+
+template <int DPL, int GC>
 void launch_prefill(float* out, const float* Q, const __half* kc, const __half* vc, int seq_len, int start_pos, int n_heads,
                     int n_kv, float scale, cudaStream_t s) {
     constexpr int HD = DPL * 32;
@@ -368,6 +581,18 @@ void attention_decode_dyn(float* out, const float* q, const void* kc, const void
     const int n_splits = attention_decode_dyn_splits(max_seq, n_heads, n_kv);
     if (xq_out) NT_CHECK((n_heads * hd) % 128 == 0, "attention_decode_dyn: n_heads * head_dim must be a multiple of 128 for the fused quantiser");
     NT_DISPATCH_ATTN(launch_decode_dyn, out, q, k, v, pos_dev, max_seq, n_heads, n_kv, scale, scratch, n_splits, static_cast<int8_t*>(xq_out), s);
+}
+
+int attention_decode_fused_tickets(int n_heads, int n_kv) { return n_heads / pick_gc(n_heads / n_kv); }
+void attention_decode_fused(float* out, const float* q, const float* k, const float* v, void* kc, void* vc, const int* pos_dev,
+                            int max_seq, int n_heads, int n_kv, int hd, float theta, float freq_scale, float scale, float* scratch,
+                            unsigned* tickets, void* xq_out, cudaStream_t s) {
+    __half* kh = static_cast<__half*>(kc);
+    __half* vh = static_cast<__half*>(vc);
+    const int n_splits = attention_decode_dyn_splits(max_seq, n_heads, n_kv);
+    if (xq_out) NT_CHECK((n_heads * hd) % 128 == 0, "attention_decode_fused: n_heads * head_dim must be a multiple of 128 for the fused quantiser");
+    NT_DISPATCH_ATTN(launch_decode_fused, out, q, k, v, kh, vh, pos_dev, max_seq, n_heads, n_kv, theta, freq_scale, scale, scratch, n_splits,
+                     tickets, static_cast<int8_t*>(xq_out), s);
 }
 
 void attention_prefill(float* out, const float* Q, const void* kc, const void* vc, int seq_len, int start_pos, int n_heads,

@@ -100,6 +100,8 @@ float nt_sampler_uniform(uint64_t seed, int n_draws_before) {
     return s.draw();
 }
 void nt_model_use_megakernel(nt_model_t m, int on) { if (m) H(m)->model.set_use_megakernel(on != 0); }
+double nt_model_load_seconds(nt_model_t m) { return m ? H(m)->model.load_seconds() : 0.0; }
+int nt_model_tp_exchange(nt_model_t m) { return m ? H(m)->model.tp_exchange_kind() : 0; }
 int nt_model_megakernel_active(nt_model_t m) { return (m && H(m)->model.megakernel_active()) ? 1 : 0; }
 int nt_model_megakernel_plan(nt_model_t m, int* kinds, int cap) {
     if (!m) return -1;

@@ -57,6 +57,7 @@ public:
     const std::unordered_map<std::string, Value>& metadata() const { return meta_; }
     size_t file_size() const { return size_; }
     size_t data_offset() const { return data_offset_; }
+    int fd() const { return fd_; }          // for pread: tensor t lives at file offset data_offset() + t.offset
     void print_info() const;
 
 private:

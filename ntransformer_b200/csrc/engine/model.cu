@@ -1,12 +1,17 @@
 // model.cu — see model.h.
 #include "model.h"
 #include "tp_comm.h"
+#include "peer_xchg.h"
 
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <unistd.h>
 
 namespace nt { namespace b200 {
 
@@ -63,6 +68,7 @@ Model::~Model() {
     for (void* p : owned_) cudaFree(p);
     for (void* p : {(void*)hidden_, (void*)xnorm_, (void*)q_, (void*)k_, (void*)v_, (void*)attn_, (void*)act_, (void*)up_, (void*)part_,
                     (void*)logits_, (void*)logits_l_, (void*)attn_scratch_, xq_h_, xq_a_, xq_i_, kc_, vc_, (void*)step_dev_,
+                    (void*)attn_tickets_,
                     (void*)argmax_dev_, (void*)recent_dev_})
         if (p) cudaFree(p);
     for (void* p : {(void*)pf_.x, (void*)pf_.q, (void*)pf_.k, (void*)pf_.v, (void*)pf_.attn, pf_.ws, pf_.ws2, (void*)pf_.tok, (void*)pf_.pos,
@@ -122,46 +128,35 @@ bool Model::set_tensor(const std::string& name, const void* ptr, DType dt, size_
     return false;
 }
 
-// Uploads tensor `name` (sharded) and fills *w. split: 0 replicate, 1 rows, 2 columns (quant-block aligned).
-const void* Model::upload(const GGUFFile& f, const std::string& name, Weight* w, int split) {
-    const GGUFTensorInfo* ti = f.find(name);
-    NT_CHECK(ti != nullptr, ("Tensor not found: " + name).c_str());
-    const uint8_t* src = static_cast<const uint8_t*>(f.data(*ti));
-    const DType dt = ti->dtype;
-    const int cols = (int)ti->shape[0];
-    const int rows = ti->shape.size() > 1 ? (int)ti->shape[1] : 1;
-    const size_t row_bytes = dtype_row_size(dt, (size_t)cols);
-    void* dst = nullptr;
-    if (split == 0 || tp_size_ == 1) {
-        NT_CUDA_CHECK(cudaMalloc(&dst, std::max<size_t>(ti->nbytes, 16)));
-        NT_CUDA_CHECK(cudaMemcpy(dst, src, ti->nbytes, cudaMemcpyHostToDevice));
-        if (w) { w->rows = rows; w->cols = cols; w->pitch = row_bytes; }
-    } else if (split == 1) {
-        int per = (rows + tp_size_ - 1) / tp_size_;
-        int r0 = std::min(rows, tp_rank_ * per), r1 = std::min(rows, r0 + per);
-        size_t bytes = (size_t)(r1 - r0) * row_bytes;
-        NT_CUDA_CHECK(cudaMalloc(&dst, std::max<size_t>(bytes, 16)));
-        if (bytes) NT_CUDA_CHECK(cudaMemcpy(dst, src + (size_t)r0 * row_bytes, bytes, cudaMemcpyHostToDevice));
-        if (w) { w->rows = r1 - r0; w->cols = cols; w->pitch = row_bytes; }
-    } else {
-        const int bs = (int)dtype_block_size(dt);
-        NT_CHECK(cols % tp_size_ == 0 && (cols / tp_size_) % bs == 0, "column shard is not quant-block aligned");
-        const int c_l = cols / tp_size_;
-        const size_t shard_row = dtype_row_size(dt, (size_t)c_l);
-        const size_t pitch = round16(shard_row);                // rows start 16 B aligned for the TMA path
-        NT_CUDA_CHECK(cudaMalloc(&dst, std::max<size_t>(pitch * rows, 16)));
-        NT_CUDA_CHECK(cudaMemset(dst, 0, pitch * rows));
-        NT_CUDA_CHECK(cudaMemcpy2D(dst, pitch, src + (size_t)tp_rank_ * shard_row, row_bytes, shard_row, (size_t)rows,
-                                   cudaMemcpyHostToDevice));
-        if (w) { w->rows = rows; w->cols = c_l; w->pitch = pitch; }
-    }
-    owned_.push_back(dst);
-    if (w) { w->ptr = dst; w->dtype = dt; w->owned = true; }
-    return dst;
-}
+// ---- GGUF -> HBM ----------------------------------------------------------------------------------------------------------------
+// The reference copies one tensor at a time with a synchronous cudaMemcpy straight from the pageable mmap
+// (transformer.cpp:286-328 via tensor.cpp:224-225): the driver stages every page through its own bounce buffer on one thread.
+// Here: every tensor's shard is planned first (shapes validated against the config — a mismatching file is rejected, not
+// trusted), all weights live in ONE device allocation, and NT_LOAD_THREADS reader threads each cycle
+//     pread(chunk of whole rows) -> pinned staging buffer -> cudaMemcpyAsync / cudaMemcpy2DAsync on the thread's own stream
+// so page-cache reads, PCIe copies and the other threads' reads overlap.  Under tensor parallelism a rank uploads only its
+// shard: row shards are one contiguous file range, column shards (attn_output, ffn_down) read whole rows and copy the rank's
+// byte slice of each row (block-aligned, padded to a 16-byte pitch for TMA).
+namespace {
+
+struct UploadJob {
+    const GGUFTensorInfo* ti = nullptr;
+    size_t file_off = 0;        // first byte of the first row this rank needs
+    size_t src_pitch = 0;       // bytes between rows in the file
+    size_t col_off = 0;         // byte offset of the rank's slice inside a row
+    size_t width = 0;           // bytes of a row this rank keeps
+    size_t rows = 0;
+    size_t dst_pitch = 0;
+    size_t dst_off = 0;         // inside the arena
+};
+
+struct Chunk { int job; size_t row0, nrows; };
+
+}  // namespace
 
 bool Model::load_gguf(const std::string& path, int max_context, int tp_rank, int tp_size) {
     fprintf(stderr, "Loading model: %s\n", path.c_str());
+    const auto t_start = std::chrono::steady_clock::now();
     GGUFFile f;
     if (!f.open(path)) return false;
     ModelConfig cfg = f.config();
@@ -171,36 +166,169 @@ bool Model::load_gguf(const std::string& path, int max_context, int tp_rank, int
     }
     cfg.print();
     f.print_info();
+    if (cfg.hidden_size <= 0 || cfg.n_layers <= 0 || cfg.n_heads <= 0 || cfg.n_kv_heads <= 0 || cfg.vocab_size <= 0 ||
+        cfg.intermediate_size <= 0 || cfg.n_heads % tp_size || cfg.n_kv_heads % tp_size || cfg.intermediate_size % tp_size) {
+        fprintf(stderr, "GGUF: model dimensions are invalid (or do not divide by the tensor-parallel size %d)\n", tp_size);
+        return false;
+    }
     vocab_ = f.vocab();
     init(cfg, tp_rank, tp_size);
 
-    upload(f, "token_embd.weight", &embd_, 0);
-    if (embd_.dtype == DType::Q5_K)
-        fprintf(stderr, "Error: Unsupported embedding dtype: Q5_K (rows read as zeros, like the reference)\n");
-    if (f.find("output.weight")) {
-        upload(f, "output.weight", &head_, 1);
-    } else if (tp_size_ == 1) {
-        head_ = embd_;                               // tied embeddings (transformer.cpp:96-99)
-        head_.owned = false;
-    } else {
-        upload(f, "token_embd.weight", &head_, 1);
-    }
-    out_norm_ = static_cast<const float*>(upload(f, "output_norm.weight", nullptr, 0));
-    for (int i = 0; i < cfg_.n_layers; i++) {
+    // ---- plan: one job per tensor, shapes checked against the config ----
+    const int hidden = cfg_.hidden_size, hd = cfg_.head_dim;
+    std::vector<UploadJob> jobs;
+    std::vector<Weight*> job_w;
+    std::vector<const float**> job_f;
+    size_t arena = 0;
+    bool ok = true;
+    auto plan = [&](const std::string& name, int rows, int cols, int split, Weight* w, const float** fptr) {
+        const GGUFTensorInfo* ti = f.find(name);
+        if (!ti) { fprintf(stderr, "GGUF: tensor not found: %s\n", name.c_str()); ok = false; return; }
+        const long long frows = ti->shape.size() > 1 ? ti->shape[1] : 1, fcols = ti->shape[0];
+        long long extra = 1;
+        for (size_t d = 2; d < ti->shape.size(); d++) extra *= ti->shape[d];
+        if (fcols != cols || frows != rows || extra != 1) {
+            fprintf(stderr, "GGUF: tensor %s has shape [%lld x %lld], the config needs [%d x %d]\n", name.c_str(), frows, fcols, rows, cols);
+            ok = false; return;
+        }
+        if (fptr && ti->dtype != DType::F32) { fprintf(stderr, "GGUF: %s must be F32\n", name.c_str()); ok = false; return; }
+        UploadJob j;
+        j.ti = ti;
+        const DType dt = ti->dtype;
+        const size_t row_bytes = dtype_row_size(dt, (size_t)cols);
+        j.src_pitch = row_bytes;
+        size_t r0 = 0, nrows = (size_t)rows;
+        j.width = row_bytes; j.dst_pitch = row_bytes;
+        int w_rows = rows, w_cols = cols;
+        if (tp_size_ > 1 && split == 1) {
+            const int per = (rows + tp_size_ - 1) / tp_size_;
+            r0 = (size_t)std::min(rows, tp_rank_ * per);
+            nrows = (size_t)std::min(rows, (int)r0 + per) - r0;
+            w_rows = (int)nrows;
+        } else if (tp_size_ > 1 && split == 2) {
+            const int bs = (int)dtype_block_size(dt);
+            if (cols % tp_size_ != 0 || (cols / tp_size_) % bs != 0) {
+                fprintf(stderr, "GGUF: %s: a %d-way column shard is not quantisation-block aligned\n", name.c_str(), tp_size_);
+                ok = false; return;
+            }
+            w_cols = cols / tp_size_;
+            j.width = dtype_row_size(dt, (size_t)w_cols);
+            j.col_off = (size_t)tp_rank_ * j.width;
+            j.dst_pitch = round16(j.width);                     // rows start 16 B aligned for the TMA path
+        }
+        j.rows = nrows;
+        j.file_off = f.data_offset() + (size_t)ti->offset + r0 * row_bytes;
+        j.dst_off = arena;
+        arena += (std::max<size_t>(j.dst_pitch * nrows, 16) + 255) & ~(size_t)255;
+        if (w) { w->dtype = dt; w->rows = w_rows; w->cols = w_cols; w->pitch = j.dst_pitch; w->owned = true; }
+        jobs.push_back(j); job_w.push_back(w); job_f.push_back(fptr);
+    };
+    plan("token_embd.weight", cfg_.vocab_size, hidden, 0, &embd_, nullptr);
+    const bool has_head = f.find("output.weight") != nullptr;
+    if (has_head) plan("output.weight", cfg_.vocab_size, hidden, 1, &head_, nullptr);
+    else if (tp_size_ > 1) plan("token_embd.weight", cfg_.vocab_size, hidden, 1, &head_, nullptr);   // tied embeddings, sharded head
+    plan("output_norm.weight", 1, hidden, 0, nullptr, &out_norm_);
+    for (int i = 0; i < cfg_.n_layers && ok; i++) {
         const std::string p = "blk." + std::to_string(i) + ".";
         LayerWeights& L = layers_[(size_t)i];
-        L.attn_norm = static_cast<const float*>(upload(f, p + "attn_norm.weight", nullptr, 0));
-        upload(f, p + "attn_q.weight", &L.wq, 1);
-        upload(f, p + "attn_k.weight", &L.wk, 1);
-        upload(f, p + "attn_v.weight", &L.wv, 1);
-        upload(f, p + "attn_output.weight", &L.wo, 2);
-        L.ffn_norm = static_cast<const float*>(upload(f, p + "ffn_norm.weight", nullptr, 0));
-        upload(f, p + "ffn_gate.weight", &L.gate, 1);
-        upload(f, p + "ffn_up.weight", &L.up, 1);
-        upload(f, p + "ffn_down.weight", &L.down, 2);
-        if ((i & 7) == 7 || i + 1 == cfg_.n_layers) fprintf(stderr, "  Loaded layer %d/%d\n", i + 1, cfg_.n_layers);
+        plan(p + "attn_norm.weight", 1, hidden, 0, nullptr, &L.attn_norm);
+        plan(p + "attn_q.weight", cfg_.n_heads * hd, hidden, 1, &L.wq, nullptr);
+        plan(p + "attn_k.weight", cfg_.n_kv_heads * hd, hidden, 1, &L.wk, nullptr);
+        plan(p + "attn_v.weight", cfg_.n_kv_heads * hd, hidden, 1, &L.wv, nullptr);
+        plan(p + "attn_output.weight", hidden, cfg_.n_heads * hd, 2, &L.wo, nullptr);
+        plan(p + "ffn_norm.weight", 1, hidden, 0, nullptr, &L.ffn_norm);
+        plan(p + "ffn_gate.weight", cfg_.intermediate_size, hidden, 1, &L.gate, nullptr);
+        plan(p + "ffn_up.weight", cfg_.intermediate_size, hidden, 1, &L.up, nullptr);
+        plan(p + "ffn_down.weight", hidden, cfg_.intermediate_size, 2, &L.down, nullptr);
     }
+    if (!ok) return false;
+    if (embd_.dtype == DType::Q5_K)
+        fprintf(stderr, "Error: Unsupported embedding dtype: Q5_K (rows read as zeros, like the reference)\n");
+
+    uint8_t* base = nullptr;
+    if (cudaMalloc(&base, std::max<size_t>(arena, 256)) != cudaSuccess) {
+        cudaGetLastError();
+        fprintf(stderr, "model: cannot allocate %.2f GB of device memory for the weights\n", arena / 1e9);
+        return false;
+    }
+    owned_.push_back(base);
+    size_t padded = 0;
+    for (size_t k = 0; k < jobs.size(); k++) {
+        if (job_w[k]) job_w[k]->ptr = base + jobs[k].dst_off;
+        if (job_f[k]) *job_f[k] = reinterpret_cast<const float*>(base + jobs[k].dst_off);
+        if (jobs[k].dst_pitch != jobs[k].width) padded += jobs[k].dst_pitch * jobs[k].rows;
+    }
+    if (padded) NT_CUDA_CHECK(cudaMemset(base, 0, arena));          // pitch padding of column shards must be finite bytes
+    if (!has_head && tp_size_ == 1) { head_ = embd_; head_.owned = false; }   // tied embeddings (transformer.cpp:96-99)
+
+    // ---- chunks of whole rows, at most CHUNK bytes of file each ----
+    constexpr size_t CHUNK = (size_t)32 << 20;
+    std::vector<Chunk> chunks;
+    size_t file_bytes = 0;
+    for (size_t k = 0; k < jobs.size(); k++) {
+        const UploadJob& j = jobs[k];
+        if (j.src_pitch > CHUNK) { fprintf(stderr, "model: a tensor row exceeds the staging chunk\n"); return false; }
+        const size_t per = std::max<size_t>(1, CHUNK / j.src_pitch);
+        for (size_t r = 0; r < j.rows; r += per) chunks.push_back({(int)k, r, std::min(per, j.rows - r)});
+        file_bytes += j.rows * j.src_pitch;
+    }
+    int n_threads = 8;
+    if (const char* e = getenv("NT_LOAD_THREADS")) n_threads = std::max(1, std::min(32, atoi(e)));
+    n_threads = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, chunks.size()));
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    const int fd = f.fd();
+    int dev = 0;
+    NT_CUDA_CHECK(cudaGetDevice(&dev));
+    auto reader = [&]() {
+        cudaSetDevice(dev);
+        uint8_t* stage[2] = {nullptr, nullptr};
+        cudaEvent_t done[2];
+        cudaStream_t st = nullptr;
+        bool up = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+        for (int b = 0; b < 2 && up; b++)
+            up = cudaHostAlloc((void**)&stage[b], CHUNK, cudaHostAllocDefault) == cudaSuccess && cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming) == cudaSuccess;
+        if (!up) { failed = 1; return; }
+        int b = 0;
+        for (size_t c = next.fetch_add(1); c < chunks.size() && !failed; c = next.fetch_add(1)) {
+            const Chunk& ch = chunks[c];
+            const UploadJob& j = jobs[(size_t)ch.job];
+            if (cudaEventSynchronize(done[b]) != cudaSuccess) { failed = 1; break; }      // the copy that last used this buffer
+            const size_t bytes = ch.nrows * j.src_pitch;
+            size_t got = 0;
+            while (got < bytes) {
+                const ssize_t n = pread(fd, stage[b] + got, bytes - got, (off_t)(j.file_off + ch.row0 * j.src_pitch + got));
+                if (n <= 0) { failed = 2; break; }
+                got += (size_t)n;
+            }
+            if (failed) break;
+            uint8_t* dst = base + j.dst_off + ch.row0 * j.dst_pitch;
+            cudaError_t e;
+            if (j.width == j.src_pitch && j.dst_pitch == j.src_pitch) e = cudaMemcpyAsync(dst, stage[b], bytes, cudaMemcpyHostToDevice, st);
+            else e = cudaMemcpy2DAsync(dst, j.dst_pitch, stage[b] + j.col_off, j.src_pitch, j.width, ch.nrows, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess || cudaEventRecord(done[b], st) != cudaSuccess) { failed = 1; break; }
+            b ^= 1;
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) failed = 1;
+        for (int k = 0; k < 2; k++) { if (stage[k]) cudaFreeHost(stage[k]); cudaEventDestroy(done[k]); }
+        cudaStreamDestroy(st);
+    };
+    const auto t_copy = std::chrono::steady_clock::now();
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_threads; t++) pool.emplace_back(reader);
+        for (std::thread& t : pool) t.join();
+    }
+    if (failed) {
+        cudaGetLastError();
+        fprintf(stderr, failed == 2 ? "model: short read from %s\n" : "model: staging / copy failure while loading %s\n", path.c_str());
+        return false;
+    }
+    const double copy_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_copy).count();
+    fprintf(stderr, "  Loaded %d layers: %.2f GB read, %.2f GB resident on this GPU, %.2f s (%.1f GB/s, %d reader threads)\n", cfg_.n_layers,
+            file_bytes / 1e9, arena / 1e9, copy_s, file_bytes / 1e9 / std::max(copy_s, 1e-9), n_threads);
     if (!finalize()) return false;
+    load_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     fprintf(stderr, "Model loaded successfully!\n");
     return true;
 }
@@ -237,6 +365,9 @@ bool Model::finalize() {
     xq_h_ = dmalloc<uint8_t>(xq_bytes(hidden));
     xq_a_ = dmalloc<uint8_t>(xq_bytes(nh_l_ * hd));
     xq_i_ = dmalloc<uint8_t>(xq_bytes(inter_l_));
+    attn_tickets_ = dmalloc<unsigned>((size_t)std::max(1, nh_l_));
+    NT_CUDA_CHECK(cudaMemset(attn_tickets_, 0, (size_t)std::max(1, nh_l_) * sizeof(unsigned)));
+    if (const char* fz = getenv("NT_B200_FUSE")) fuse_mask_ = atoi(fz);
     const size_t kv_elems = (size_t)cfg_.n_layers * max_seq * nkv_l_ * hd;     // F16 [L, max_seq, n_kv, hd], transformer.cpp:340-346
     kc_ = dmalloc<uint16_t>(kv_elems);
     vc_ = dmalloc<uint16_t>(kv_elems);
@@ -307,36 +438,113 @@ bool Model::o_xq_fusable(const Weight& wo) const {
 // hidden += all_reduce(partial)   (one exchange per sub-block)
 void Model::reduce_residual(float* partial, cudaStream_t s) {
     NT_CHECK(comm_ != nullptr, "tensor-parallel model without a communicator");
+    // (the unfused path; with the peer exchange mapped the short chain sums through NVLink stores instead, see step_body)
     comm_->all_reduce_sum(partial, (size_t)cfg_.hidden_size, s);
     add_inplace(hidden_, partial, cfg_.hidden_size, s);
 }
 
+// The short launch chain needs every projection on the TMA/dp4a GEMV (its prologue carries the norm + quantiser).
+// Collective (every rank takes the same branch): map the peers' exchange buffers once, before any graph is captured.
+void Model::ensure_xchg() {
+    if (tp_size_ == 1 || xchg_tried_) return;
+    xchg_tried_ = true;
+    NT_CHECK(comm_ != nullptr, "tensor-parallel model without a communicator");
+    if (env_on("NT_B200_TP_NCCL")) return;
+    auto x = std::make_unique<PeerXchg>();
+    float ok = x->init(comm_, tp_rank_, tp_size_, cfg_.hidden_size, stream_) ? 0.f : 1.f;
+    float* flag = dmalloc<float>(1);                       // all ranks agree: any failure anywhere keeps NCCL everywhere
+    NT_CUDA_CHECK(cudaMemcpyAsync(flag, &ok, sizeof(float), cudaMemcpyHostToDevice, stream_));
+    comm_->all_reduce_sum(flag, 1, stream_);
+    NT_CUDA_CHECK(cudaMemcpyAsync(&ok, flag, sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    NT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    NT_CUDA_CHECK(cudaFree(flag));
+    if (ok == 0.f) xchg_ = std::move(x);
+    else if (tp_rank_ == 0) fprintf(stderr, "Note: NVLink peer exchange unavailable; tensor-parallel sums go through ncclAllReduce\n");
+}
+
+bool Model::chain_ok() const {
+    if ((tp_size_ != 1 && !xchg_) || !(fuse_mask_ & 1)) return false;
+    if (cfg_.hidden_size % 128 != 0 || inter_l_ % 128 != 0 || (nh_l_ * cfg_.head_dim) % 128 != 0) return false;
+    auto kq = [&](const Weight& w, int K) {
+        GemvMat m; m.W = w.ptr; m.y = nullptr; m.out = w.rows; m.dtype = w.dtype; m.row_pitch = w.pitch;
+        return w.cols == K && gemv_kq_supported(&m, 1, K);
+    };
+    for (const LayerWeights& L : layers_) {
+        GemvMat qkv[3];
+        const Weight* ws[3] = {&L.wq, &L.wk, &L.wv};
+        for (int i = 0; i < 3; i++) { qkv[i].W = ws[i]->ptr; qkv[i].out = ws[i]->rows; qkv[i].dtype = ws[i]->dtype; qkv[i].row_pitch = ws[i]->pitch; }
+        if (!gemv_kq_supported(qkv, 3, cfg_.hidden_size)) return false;
+        if (!kq(L.wo, nh_l_ * cfg_.head_dim) || !kq(L.gate, cfg_.hidden_size) || !kq(L.up, cfg_.hidden_size) || !kq(L.down, inter_l_)) return false;
+        if (L.gate.dtype != L.up.dtype) return false;
+    }
+    return kq(head_, cfg_.hidden_size) || head_.rows == 0;
+}
+
+// One decoded token, all layers.  Two forms of the reference's launch sequence (Attention::forward attention.cpp:120-211,
+// FFN::forward ffn.cpp:85-134, 15 launches per layer there):
+//   short chain (one GPU, all projections on the TMA/dp4a GEMV) — 6 launches per layer:
+//     [RMSNorm + quantise + q/k/v GEMV] [RoPE + KV write + attention + merge] [quantise + o GEMV += residual]
+//     [RMSNorm + quantise + gate/up GEMV + SwiGLU] [quantise] [down GEMV += residual]
+//     The norms and the quantisers of hidden-sized vectors run in the consuming GEMV's prologue while its first weights are
+//     already in flight (gemv_kquant.cu); only the intermediate-sized activation vector keeps its own quantise launch;
+//   unfused — 8-10 launches per layer (tensor parallel, mixed dtypes, NT_B200_FUSE=0).
 void Model::step_body(cudaStream_t s) {
     const int hidden = cfg_.hidden_size, hd = cfg_.head_dim, max_seq = cfg_.max_seq_len;
     const float scale = 1.0f / sqrtf((float)hd);                         // attention.cpp:21
     const size_t kv_stride = (size_t)max_seq * nkv_l_ * hd;               // transformer.cpp:629
     const int* pos_dev = step_dev_ + 1;
+    const bool chain = chain_ok();
+    const bool attn1 = (fuse_mask_ & 2) != 0;
     embed_rows(hidden_, embd_.ptr, embd_.dtype, step_dev_, 1, hidden, s);
+    auto mat = [](const Weight& w, float* y) { GemvMat m; m.W = w.ptr; m.y = y; m.out = w.rows; m.dtype = w.dtype; m.row_pitch = w.pitch; return m; };
     for (int i = 0; i < cfg_.n_layers; i++) {
         const LayerWeights& L = layers_[(size_t)i];
         uint16_t* kc = static_cast<uint16_t*>(kc_) + (size_t)i * kv_stride;
         uint16_t* vc = static_cast<uint16_t*>(vc_) + (size_t)i * kv_stride;
         // --- attention sub-block ---
-        { const Weight* ws[3] = {&L.wq, &L.wk, &L.wv}; float* ys[3] = {q_, k_, v_}; matvec(ws, ys, 3, hidden_, L.attn_norm, GEMV_STORE, s); }
-        rope_kv_decode(q_, k_, v_, kc, vc, pos_dev, nh_l_, nkv_l_, hd, cfg_.rope_theta, cfg_.rope_freq_scale, max_seq, s);
-        const bool o_fused = o_xq_fusable(L.wo);          // attention emits xq for the o-projection directly
-        attention_decode_dyn(attn_, q_, kc, vc, pos_dev, max_seq, nh_l_, nkv_l_, hd, scale, attn_scratch_, o_fused ? xq_a_ : nullptr, s);
-        { const Weight* ws[1] = {&L.wo};
-          float* ys[1] = {tp_size_ == 1 ? hidden_ : part_};
-          const GemvEpilogue ep = tp_size_ == 1 ? GEMV_ADD : GEMV_STORE;
-          if (o_fused) {
-              GemvMat m; m.W = L.wo.ptr; m.y = ys[0]; m.out = L.wo.rows; m.dtype = L.wo.dtype; m.row_pitch = L.wo.pitch;
-              gemv_kq(&m, 1, L.wo.cols, xq_a_, ep, s);
-          } else {
-              matvec(ws, ys, 1, attn_, nullptr, ep, s);
-          }
-          if (tp_size_ > 1) reduce_residual(part_, s); }
+        if (chain) {
+            GemvMat m3[3] = {mat(L.wq, q_), mat(L.wk, k_), mat(L.wv, v_)};
+            GemvInput in; in.x = hidden_; in.norm_w = L.attn_norm; in.eps = cfg_.norm_eps;
+            gemv_kq(m3, 3, hidden, in, GEMV_STORE, s);
+        } else {
+            const Weight* ws[3] = {&L.wq, &L.wk, &L.wv}; float* ys[3] = {q_, k_, v_}; matvec(ws, ys, 3, hidden_, L.attn_norm, GEMV_STORE, s);
+        }
+        const bool o_xq = !chain && o_xq_fusable(L.wo);            // unfused path: attention emits xq for the o-projection
+        if (attn1) {
+            attention_decode_fused(attn_, q_, k_, v_, kc, vc, pos_dev, max_seq, nh_l_, nkv_l_, hd, cfg_.rope_theta, cfg_.rope_freq_scale, scale,
+                                   attn_scratch_, attn_tickets_, o_xq ? xq_a_ : nullptr, s);
+        } else {
+            rope_kv_decode(q_, k_, v_, kc, vc, pos_dev, nh_l_, nkv_l_, hd, cfg_.rope_theta, cfg_.rope_freq_scale, max_seq, s);
+            attention_decode_dyn(attn_, q_, kc, vc, pos_dev, max_seq, nh_l_, nkv_l_, hd, scale, attn_scratch_, o_xq ? xq_a_ : nullptr, s);
+        }
+        if (chain) {
+            GemvMat m = mat(L.wo, hidden_);
+            GemvInput in; in.x = attn_;
+            if (tp_size_ == 1) gemv_kq(&m, 1, L.wo.cols, in, GEMV_ADD, s);
+            else { gemv_kq_peer(m, L.wo.cols, in, xchg_->out(), s); xchg_->reduce_residual(hidden_, s); }
+        } else {
+            const Weight* ws[1] = {&L.wo};
+            float* ys[1] = {tp_size_ == 1 ? hidden_ : part_};
+            const GemvEpilogue ep = tp_size_ == 1 ? GEMV_ADD : GEMV_STORE;
+            if (o_xq) {
+                GemvMat m = mat(L.wo, ys[0]);
+                gemv_kq(&m, 1, L.wo.cols, xq_a_, ep, s);
+            } else {
+                matvec(ws, ys, 1, attn_, nullptr, ep, s);
+            }
+            if (tp_size_ > 1) reduce_residual(part_, s);
+        }
         // --- FFN sub-block ---
+        if (chain) {
+            GemvMat m2[2] = {mat(L.gate, act_), mat(L.up, up_)};
+            GemvInput in; in.x = hidden_; in.norm_w = L.ffn_norm; in.eps = cfg_.norm_eps;
+            gemv_kq(m2, 2, hidden, in, GEMV_SWIGLU, s);
+            quantize_x(act_, xq_i_, inter_l_, s);           // 3.4 x inter bytes of staging: too long for the down GEMV's prologue
+            GemvMat md = mat(L.down, hidden_);
+            if (tp_size_ == 1) gemv_kq(&md, 1, inter_l_, xq_i_, GEMV_ADD, s);
+            else { GemvInput ind; ind.xq = xq_i_; gemv_kq_peer(md, inter_l_, ind, xchg_->out(), s); xchg_->reduce_residual(hidden_, s); }
+            continue;
+        }
         { const Weight* ws[2] = {&L.gate, &L.up}; float* ys[2] = {act_, up_}; matvec(ws, ys, 2, hidden_, L.ffn_norm, GEMV_SWIGLU, s); }
         { const Weight* ws[1] = {&L.down};
           if (tp_size_ == 1) { float* ys[1] = {hidden_}; matvec(ws, ys, 1, act_, nullptr, GEMV_ADD, s); }
@@ -344,8 +552,15 @@ void Model::step_body(cudaStream_t s) {
     }
 }
 
-void Model::step_head(cudaStream_t s) {
+void Model::step_head(cudaStream_t s, bool from_chain) {
     const Weight* ws[1] = {&head_};                                               // final norm fused: transformer.cpp:657-665
+    if (from_chain) {
+        GemvMat m; m.W = head_.ptr; m.y = tp_size_ == 1 ? logits_ : logits_l_; m.out = head_.rows; m.dtype = head_.dtype; m.row_pitch = head_.pitch;
+        GemvInput in; in.x = hidden_; in.norm_w = out_norm_; in.eps = cfg_.norm_eps;
+        if (head_.rows > 0) gemv_kq(&m, 1, cfg_.hidden_size, in, GEMV_STORE, s);
+        if (tp_size_ > 1) comm_->all_gather(logits_l_, logits_, (size_t)vocab_l_, s);
+        return;
+    }
     if (tp_size_ == 1) {
         float* ys[1] = {logits_};
         matvec(ws, ys, 1, hidden_, out_norm_, GEMV_STORE, s);
@@ -436,9 +651,10 @@ void Model::run_step(bool with_head) {
     const char* mk = getenv("NT_B200_MEGAKERNEL");
     const bool want_mega = mk ? env_on("NT_B200_MEGAKERNEL") : use_mega_;
     if (want_mega && ensure_mega()) { run_step_mega(with_head); return; }
+    ensure_xchg();
     if (!use_graph_ || getenv("NT_B200_NO_GRAPH")) {
         step_body(stream_);
-        if (with_head) step_head(stream_);
+        if (with_head) step_head(stream_, chain_ok());
         return;
     }
     cudaGraphExec_t& g = with_head ? g_full_ : g_body_;
@@ -449,7 +665,7 @@ void Model::run_step(bool with_head) {
         NT_CUDA_CHECK(cudaStreamBeginCapture(stream_, tp_size_ > 1 ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
         set_pdl(use_pdl_ && !getenv("NT_B200_NO_PDL"));   // programmatic edges between the step's kernels
         step_body(stream_);
-        if (with_head) step_head(stream_);
+        if (with_head) step_head(stream_, chain_ok());
         set_pdl(false);
         NT_CUDA_CHECK(cudaStreamEndCapture(stream_, &graph));
         NT_CUDA_CHECK(cudaGraphInstantiate(&g, graph, 0));
@@ -581,8 +797,10 @@ void Model::forward_async(const int* tokens, int seq_len, int start_pos) {
 
 int Model::sync() {
     if (mega_) mega_->enqueue_abort_read(stream_);
+    if (xchg_) xchg_->enqueue_abort_read(stream_);
     const cudaError_t e = cudaStreamSynchronize(stream_);
     if (e == cudaSuccess && mega_) mega_->check_abort();
+    if (e == cudaSuccess && xchg_) NT_CHECK(!xchg_->aborted(), "tensor-parallel peer exchange timed out (a rank never published its partial rows)");
     return (int)e;
 }
 

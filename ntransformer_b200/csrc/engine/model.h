@@ -15,6 +15,7 @@
 #include "../kernels_internal.h"
 #include "gguf.h"
 #include "decode_mega.h"
+#include "peer_xchg.h"
 
 namespace nt { namespace b200 {
 
@@ -73,6 +74,7 @@ public:
     // Algorithmic bytes this rank reads per decoded token at context length ctx (SURVEY §8d B_tok).
     size_t bytes_per_token(int ctx) const;
     size_t weight_bytes() const;
+    double load_seconds() const { return load_seconds_; }     // wall time of load_gguf (parse + plan + pipelined upload + buffers)
     void set_use_graph(bool on) { use_graph_ = on; }
     void set_use_pdl(bool on) { use_pdl_ = on; }
     // Prompts of at least n tokens go through the batched tensor-core prefill when the weights allow it (0 = never).
@@ -82,6 +84,7 @@ public:
     // Opt-in (also NT_B200_MEGAKERNEL=1): run the decode step as one persistent kernel (engine/decode_mega.h) instead of
     // the graph of fused launches.  Falls back to the graph path, with a note on stderr, when a shape is not covered.
     void set_use_megakernel(bool on) { use_mega_ = on; }
+    int tp_exchange_kind() const { return tp_size_ == 1 || !xchg_tried_ ? 0 : (xchg_ ? 2 : 1); }
     bool megakernel_active();                 // true once the persistent kernel has been built for this model
     // Debug read-back of the persistent kernel's working buffers ("hid0", "hid1", "q", "attn", "act", "slots"): device pointer.
     const float* mega_debug_buffer(const char* name, size_t* count);
@@ -93,7 +96,8 @@ private:
     bool ensure_mega();
     void run_step_mega(bool with_head);
     void step_body(cudaStream_t s);      // embedding + all layers for the token/position in step_dev_
-    void step_head(cudaStream_t s);      // final norm + LM head (+ all-gather under TP)
+    void step_head(cudaStream_t s, bool from_chain = false);   // final norm + LM head (+ all-gather under TP); from_chain: norm + quantiser in the GEMV prologue
+    bool chain_ok() const;               // every projection on the TMA/dp4a GEMV: the fused launch chain applies
     void run_step(bool with_head);
     void matvec(const Weight* const* ws, float* const* ys, int n, const float* x, const float* norm_w, GemvEpilogue ep,
                 cudaStream_t s);
@@ -106,7 +110,6 @@ private:
     // C[T, w.rows] (+)= split(A)[T, w.cols] . W^T for a weight of any GGUF dtype (quantised: dequantise to hi/lo, two GEMMs)
     void prefill_gemm(float* C, const void* ws, const Weight& w, int T, bool add, cudaStream_t s);
     bool o_xq_fusable(const Weight& wo) const;
-    const void* upload(const GGUFFile& f, const std::string& name, Weight* w, int split /*0 none,1 rows,2 cols*/);
     void release_graphs();
 
     ModelConfig cfg_;
@@ -126,6 +129,8 @@ private:
     float *hidden_ = nullptr, *xnorm_ = nullptr, *q_ = nullptr, *k_ = nullptr, *v_ = nullptr, *attn_ = nullptr;
     float *act_ = nullptr, *up_ = nullptr, *part_ = nullptr, *logits_ = nullptr, *logits_l_ = nullptr, *attn_scratch_ = nullptr;
     void *xq_h_ = nullptr, *xq_a_ = nullptr, *xq_i_ = nullptr;
+    unsigned* attn_tickets_ = nullptr;   // last-arriver tickets of the one-launch attention (zero between launches)
+    int fuse_mask_ = 1;                  // bit 0: norm + quantiser in the GEMV prologues (default), bit 1: one-launch attention (opt-in: measured slower, profiles/r02_*) (NT_B200_FUSE)
     void *kc_ = nullptr, *vc_ = nullptr;
     int* step_dev_ = nullptr;            // [0] token, [1] position
     int* argmax_dev_ = nullptr;
@@ -148,6 +153,13 @@ private:
     cudaGraphExec_t g_full_ = nullptr, g_body_ = nullptr;
     int n_full_ = 0, n_body_ = 0;        // kernels per graph replay
     bool finalized_ = false;
+    double load_seconds_ = 0.0;
+
+    // Tensor parallel: the o-projection / down-projection partials are summed through NVLink peer memory (engine/peer_xchg.h);
+    // NT_B200_TP_NCCL=1 (or a failed peer mapping) keeps ncclAllReduce + add.
+    std::unique_ptr<PeerXchg> xchg_;
+    bool xchg_tried_ = false;
+    void ensure_xchg();
 
     bool use_mega_ = false;
     bool mega_tried_ = false;

@@ -49,13 +49,15 @@ struct KqParams {
     int K, NB, NC;             // elements, super-blocks per row, chunks per row (NC <= warps)
     const int8_t* xq;          // pre-quantised activations, or null:
     const float* x_f32;        //   F32 activations quantised in the prologue,
-    const float* norm_w;       //   optionally RMS-normalised first (x * rsqrt(mean(x^2) + eps) * norm_w)
-    float eps;
+    const float* norm_w;       //   optionally as RMSNorm(x) * norm_w: the prologue quantises x * norm_w and sums x^2 in the same
+    float eps;                 //   pass; the scalar rsqrt(mean(x^2) + eps) is applied to the results (exact up to round-off)
+    int x_alias;               // the prologue's staging area aliases ring stages >= 1 (those are primed after the prologue)
     int total_groups;          // SWIGLU: groups of mat[0]
     int n_seg;                 // segments (matrices) per row-group: 2 for SWIGLU else 1
     int epilogue;
     int stages;                // ring depth per warp
     int gpc;                   // row-groups a CTA processes per round = warps / NC
+    PeerOut peer;              // epilogue GEMV_PEER
 };
 
 // MASK: bit f set <=> matrices of format f may appear in this launch (mixed Q4_K_M projections share one launch).
@@ -68,10 +70,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     const int K = p.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stages = p.stages, NC = p.NC, NB = p.NB, n_seg = p.n_seg, gpc = p.gpc;
-    // smem carve-up: [rings][mbarriers][only when x is F32: x planes 3K, scale K/32, sum16 K/16]
-    uint8_t* ring = smem + (size_t)warp * stages * SLOT;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * stages * SLOT) + warp * stages;
-    uint8_t* xs = smem + ((((size_t)WARPS * stages * (SLOT + 8)) + 127) & ~(size_t)127);
+    // smem carve-up: [ring stage 0: WARPS slots][stage 1: WARPS slots]...[mbarriers][x staging unless it aliases stages >= 1]
+    uint8_t* ring = smem + (size_t)warp * SLOT;                             // this warp's slot of stage s: ring + s * WARPS * SLOT
+    constexpr size_t STAGE_STRIDE = (size_t)WARPS * SLOT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_STRIDE) + warp * stages;
+    uint8_t* xs = p.x_alias ? smem + STAGE_STRIDE : smem + ((((size_t)WARPS * stages * (SLOT + 8)) + 127) & ~(size_t)127);
 
     const int chunk = warp % NC, gsub = warp / NC;        // this warp's chunk of every row, and its row-group slot
     const int n_rounds = (p.total_groups + gridDim.x * gpc - 1) / (gridDim.x * gpc);
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
             // copy size rounded up to 16 B (a 210-byte Q6_K tail may spill into row padding; checked on the host)
             const uint32_t bytes = ((uint32_t)(nbc * blkb) + 15u) & ~15u;
             mbar_expect_tx(bar, bytes * RG);
-            uint8_t* dst = ring + (size_t)slot * SLOT;
+            uint8_t* dst = ring + (size_t)slot * STAGE_STRIDE;
             const int row0 = gl * RG;
             const uint8_t* src = m.W + (long long)chunk * (BS * blkb) + (long long)row0 * m.row_pitch;
             if (row0 + RG <= m.out) {
@@ -121,9 +124,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     }
     __syncwarp();
     int issued = 0;
-    // Weights do not depend on the previous kernel: start streaming before touching x.
+    // Weights do not depend on the previous kernel: start streaming before touching x.  When the prologue's staging area
+    // aliases the ring, only stage 0 is primed here and the rest follows once x sits in registers.
+    const int prime_now = p.x_alias ? 1 : stages;
     if (lane == 0) {
-        for (; issued < stages && issued < n_stages_total; issued++) issue_next(issued);
+        for (; issued < prime_now && issued < n_stages_total; issued++) issue_next(issued);
     }
     pdl_wait();   // no-op unless launched with programmatic stream serialization
 
@@ -131,61 +136,105 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     const int blk = lane >> 1, h = lane & 1;
     const uint32_t hb = (uint32_t)((chunk * BS + min(blk, nbc - 1)) * 2 + h);   // global half-block index (clamped for idle lanes)
     XRegs X;
+    float rms_inv = 1.0f;
     if (p.x_f32) {
-        // fused prologue (stateless launch_gemv path): (RMSNorm +) quantisation into shared memory, then load the slice.
+        // Fused prologue (the stateless launch_gemv path and the decode chain): F32 vector -> xq form in shared memory, one pass.
+        // With norm_w the quantiser sees x * norm_w and the pass also sums x^2; block-scaled quantisation is scale invariant,
+        // so multiplying the RESULTS by rsqrt(mean(x^2) + eps) equals RMSNorm-then-GEMV up to round-off (rmsnorm.cu:17-70).
         float* xscale = reinterpret_cast<float*>(xs + 3 * (size_t)K);
         float* xsum16 = xscale + K / 32;
-        float rms_inv = 1.0f;
+        // One thread <-> 8 consecutive elements (4 threads share a 32-element block: 2 shuffles for its absmax, 1 for the
+        // 16-element sums), all loads of the pass issued up front: the whole CTA is busy and the pass costs one L2 round trip.
+        // Same representation as quantize_lane32 (x ~= scale * (q1 * 16384 + q2 * 128 + q3)), with x / s taken as x * (127 / amax).
+        constexpr int MAXV = 3;                             // thread-iterations held in registers at once (K <= 24 * threads)
+        const int nvec = K / 8, nthr = WARPS * 32;
+        float ss = 0.f;
+        for (int base = 0; base < nvec; base += MAXV * nthr) {
+            float4 hv[MAXV][2], wv[MAXV][2];
+#pragma unroll
+            for (int j = 0; j < MAXV; j++) {
+                const int t = base + j * nthr + (int)threadIdx.x;
+                if (t < nvec) {
+                    hv[j][0] = __ldcg(reinterpret_cast<const float4*>(p.x_f32) + 2 * t);
+                    hv[j][1] = __ldcg(reinterpret_cast<const float4*>(p.x_f32) + 2 * t + 1);
+                    if (p.norm_w) {
+                        wv[j][0] = __ldg(reinterpret_cast<const float4*>(p.norm_w) + 2 * t);
+                        wv[j][1] = __ldg(reinterpret_cast<const float4*>(p.norm_w) + 2 * t + 1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < MAXV; j++) {
+                const int t = base + j * nthr + (int)threadIdx.x;
+                if (t >= nvec) break;                       // nvec % 32 == 0: whole warps leave together
+                float x[8] = {hv[j][0].x, hv[j][0].y, hv[j][0].z, hv[j][0].w, hv[j][1].x, hv[j][1].y, hv[j][1].z, hv[j][1].w};
+                if (p.norm_w) {
+                    const float w[8] = {wv[j][0].x, wv[j][0].y, wv[j][0].z, wv[j][0].w, wv[j][1].x, wv[j][1].y, wv[j][1].z, wv[j][1].w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { ss = fmaf(x[i], x[i], ss); x[i] = __fmul_rn(x[i], w[i]); }
+                }
+                float amax = 0.f, s8 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) { amax = fmaxf(amax, fabsf(x[i])); s8 = __fadd_rn(s8, x[i]); }
+                amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 1));
+                amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 2));
+                const float s16 = __fadd_rn(s8, __shfl_xor_sync(0xFFFFFFFFu, s8, 1));
+                const float sc = __fdiv_rn(amax, 127.0f);
+                const float inv = (amax > 0.f) ? __fdiv_rn(127.0f, amax) : 0.f;
+                uint32_t w1[2] = {0, 0}, w2[2] = {0, 0}, w3[2] = {0, 0};
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float tq = __fmul_rn(x[i], inv);
+                    const float f1 = rintf(tq);
+                    const float r1 = __fmul_rn(__fsub_rn(tq, f1), 128.0f);
+                    const float f2 = rintf(r1);
+                    const float r2 = __fmul_rn(__fsub_rn(r1, f2), 128.0f);
+                    const float f3 = rintf(r2);
+                    w1[i >> 2] |= ((uint32_t)(int)f1 & 0xFFu) << (8 * (i & 3));
+                    w2[i >> 2] |= ((uint32_t)(int)f2 & 0xFFu) << (8 * (i & 3));
+                    w3[i >> 2] |= ((uint32_t)(int)f3 & 0xFFu) << (8 * (i & 3));
+                }
+                const uint32_t se = xq_swizzle((uint32_t)t * 8u);          // 8 bytes stay inside one swizzled 16-byte column
+                *reinterpret_cast<uint2*>(xs + se) = make_uint2(w1[0], w1[1]);
+                *reinterpret_cast<uint2*>(xs + K + se) = make_uint2(w2[0], w2[1]);
+                *reinterpret_cast<uint2*>(xs + 2 * (size_t)K + se) = make_uint2(w3[0], w3[1]);
+                if ((threadIdx.x & 3) == 0) xscale[t >> 2] = __fmul_rn(sc, 1.0f / 16384.0f);
+                if ((threadIdx.x & 1) == 0) xsum16[t >> 1] = s16;
+            }
+        }
         if (p.norm_w) {
-            float ss = 0.f;
-            for (int i = threadIdx.x; i < K; i += WARPS * 32) { const float v = p.x_f32[i]; ss += v * v; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
             if (lane == 0) red[warp] = ss;
-            __syncthreads();
-            float t = (lane < WARPS) ? red[lane] : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
-            rms_inv = rsqrtf(t / K + p.eps);
-        }
-        constexpr int PB = 8;                               // blocks per batch: PB loads in flight per L2 latency
-        const int nblk = K / 32;
-        for (int b0 = warp; b0 < nblk; b0 += WARPS * PB) {
-            float v[PB], w[PB];
-#pragma unroll
-            for (int j = 0; j < PB; j++) {
-                const int e = min(b0 + j * WARPS, nblk - 1) * 32 + lane;
-                v[j] = p.x_f32[e];
-                w[j] = p.norm_w ? p.norm_w[e] : 1.0f;
-            }
-#pragma unroll
-            for (int j = 0; j < PB; j++) {
-                const int b = b0 + j * WARPS;
-                if (b >= nblk) break;                       // warp-uniform
-                const int e = b * 32 + lane;
-                const float x = p.norm_w ? v[j] * rms_inv * w[j] : v[j];
-                int q1, q2, q3;
-                float sc, s16;
-                quantize_lane32(x, q1, q2, q3, sc, s16);
-                xs[e] = (uint8_t)q1;
-                xs[K + e] = (uint8_t)q2;
-                xs[2 * K + e] = (uint8_t)q3;
-                if (lane == 0) xscale[b] = sc;
-                if ((lane & 15) == 0) xsum16[2 * b + (lane >> 4)] = s16;
-            }
         }
         __syncthreads();
+        if (p.norm_w) {
+            float t = 0.f;
 #pragma unroll
-        for (int pl = 0; pl < 3; pl++)
+            for (int i = 0; i < WARPS; i++) t += red[i];    // fixed order: the same value in every warp and CTA
+            rms_inv = rsqrtf(t / K + p.eps);
+        }
+        {
+            const uint32_t sw = (hb & 7u) << 4;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int4 v = *reinterpret_cast<const int4*>(xs + pl * K + hb * 128u + 16u * i);
-                X.x[pl][4 * i] = v.x; X.x[pl][4 * i + 1] = v.y; X.x[pl][4 * i + 2] = v.z; X.x[pl][4 * i + 3] = v.w;
-            }
+            for (int pl = 0; pl < 3; pl++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int4 v = *reinterpret_cast<const int4*>(xs + (size_t)pl * K + ((hb * 128u + 16u * i) ^ sw));
+                    X.x[pl][4 * i] = v.x; X.x[pl][4 * i + 1] = v.y; X.x[pl][4 * i + 2] = v.z; X.x[pl][4 * i + 3] = v.w;
+                }
+        }
 #pragma unroll
         for (int j = 0; j < 4; j++) X.sx[j] = xscale[hb * 4 + j];
 #pragma unroll
         for (int j = 0; j < 8; j++) X.s16[j] = xsum16[hb * 8 + j];
+        if (p.x_alias) {
+            __syncthreads();                                 // every lane holds its slice: the staging area becomes ring again
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes before async-proxy (TMA) writes
+                for (; issued < stages && issued < n_stages_total; issued++) issue_next(issued);
+            }
+        }
     } else {
         // pre-quantised xq in global memory (planes stored with the 16-byte-column swizzle of xquant.cuh)
         const int8_t* xq = p.xq;
@@ -205,6 +254,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
         X.s16[0] = u0.x; X.s16[1] = u0.y; X.s16[2] = u0.z; X.s16[3] = u0.w;
         X.s16[4] = u1.x; X.s16[5] = u1.y; X.s16[6] = u1.z; X.s16[7] = u1.w;
     }
+    unsigned peer_seq = 0, peer_parity = 0;
+    if (p.epilogue == GEMV_PEER) { peer_seq = __ldcg(p.peer.seq) + 1u; peer_parity = peer_seq & 1u; }
     pdl_launch_dependents();
 
     int slot = 0;
@@ -219,7 +270,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
             if (live && blk < nbc) {
                 int mi, gl;
                 locate(g, seg, mi, gl);
-                const uint8_t* slot_base = ring + (size_t)slot * SLOT;
+                const uint8_t* slot_base = ring + (size_t)slot * STAGE_STRIDE;
                 const int fmt = (MASK == 1) ? 0 : (MASK == 2) ? 1 : (MASK == 4) ? 2 : (MASK == 8) ? 3 : (MASK == 16) ? 4 : p.mat[mi].fmt;
                 if ((MASK & 1) && fmt == 0) process_stage<0>(slot_base, blk, h, X, acc);
                 if ((MASK & 2) && fmt == 1) process_stage<1>(slot_base, blk, h, X, acc);
@@ -247,6 +298,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
                 v0 += partial[buf][gsub * NC + c][0][lane];
                 if (n_seg == 2) v1 += partial[buf][gsub * NC + c][1][lane];
             }
+            v0 *= rms_inv; v1 *= rms_inv;                   // 1.0 unless the prologue normalised (RMSNorm's scalar factor)
             int mi, gl;
             locate(g, 0, mi, gl);
             const KqMat& m = p.mat[mi];
@@ -257,9 +309,29 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
                     m.y[row] = __fdividef(v0, 1.0f + __expf(-v0)) * v1;
                 } else if (p.epilogue == GEMV_ADD) {
                     m.y[row] += v0;
+                } else if (p.epilogue == GEMV_PEER) {
+                    // this rank's partial row -> slot [parity][rank] on every rank (NVLink stores; lanes 0..3 write 16 contiguous bytes)
+                    const size_t off = ((size_t)peer_parity * p.peer.size + p.peer.rank) * (size_t)p.peer.hidden + (size_t)row;
+                    for (int r = 0; r < p.peer.size; r++) p.peer.slots[r][off] = v0;
                 } else {
                     m.y[row] = v0;
                 }
+            }
+        }
+    }
+    if (p.epilogue == GEMV_PEER) {
+        // One fence per CTA: the storing lanes make their peer stores visible system-wide, the CTA arrives, and the last CTA of
+        // the grid publishes the sequence number in every rank's flag line (posted NVLink writes).
+        if (chunk == 0 && lane < RG) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned prev = atomicAdd(p.peer.arrive, 1u);
+            if (prev == gridDim.x - 1) {
+                *p.peer.arrive = 0;
+                __threadfence_system();
+                for (int r = 0; r < p.peer.size; r++)
+                    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.peer.flags[r] + 32 * p.peer.rank), "r"(peer_seq) : "memory");
             }
         }
     }
@@ -319,15 +391,30 @@ template <int MASK>
 void launch_fmt(KqParams& p, cudaStream_t s) {
     constexpr int SLOT = RG * BS * max_blk(MASK);
     const size_t xq_sz = p.x_f32 ? (((size_t)3 * p.K + (size_t)(p.K / 32) * 4 + (size_t)(p.K / 16) * 4 + 127) & ~(size_t)127) + 128 : 0;
-    const size_t budget = SMEM_CAP - xq_sz - 256;
-    int w = pick_warps(p.NC, p.total_groups, SLOT, budget, 2);
-    if (!w) w = pick_warps(p.NC, p.total_groups, SLOT, budget, 1);   // long rows with in-kernel quantisation: single-stage ring
-    NT_CHECK(w != 0, "gemv_kq: shared memory budget exceeded");
+    // F32 input: first try to stage x over ring stages >= 1 (full ring depth and CTA width, the ring is primed in two steps);
+    // vectors too long for that get their own area behind a smaller ring.
+    int w = 0, stages = 0;
+    p.x_alias = 0;
+    if (p.x_f32) {
+        const size_t budget = SMEM_CAP - 256;
+        w = pick_warps(p.NC, p.total_groups, SLOT, budget, 2);
+        if (w) {
+            stages = (int)(budget / ((size_t)w * (SLOT + 8)));
+            if (stages > 4) stages = 4;
+            if (xq_sz <= (size_t)w * (stages - 1) * SLOT) p.x_alias = 1; else w = 0;
+        }
+    }
+    if (!w) {
+        const size_t budget = SMEM_CAP - xq_sz - 256;
+        w = pick_warps(p.NC, p.total_groups, SLOT, budget, 2);
+        if (!w) w = pick_warps(p.NC, p.total_groups, SLOT, budget, 1);   // long rows with in-kernel quantisation: single-stage ring
+        NT_CHECK(w != 0, "gemv_kq: shared memory budget exceeded");
+        stages = (int)(budget / ((size_t)w * (SLOT + 8)));
+        if (stages > 4) stages = 4;
+    }
     p.gpc = w / p.NC;
-    int stages = (int)(budget / ((size_t)w * (SLOT + 8)));
-    if (stages > 4) stages = 4;
     p.stages = stages;
-    const size_t smem = (size_t)w * stages * (SLOT + 8) + 128 + xq_sz;
+    const size_t smem = (size_t)w * stages * (SLOT + 8) + 128 + (p.x_alias ? 0 : xq_sz);
     switch (w) {
         case 12: launch_kq<MASK, 12>(p, smem, s); break;
         case 11: launch_kq<MASK, 11>(p, smem, s); break;
@@ -361,8 +448,11 @@ bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K) {
     return true;
 }
 
+namespace { const PeerOut* g_peer = nullptr; }      // set around the GEMV_PEER launch by gemv_kq_peer (single host thread, like the reference)
+
 void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpilogue ep, cudaStream_t s) {
     NT_CHECK(gemv_kq_supported(mats, n_mat, K), "gemv_kq: unsupported shape/dtype/alignment");
+    NT_CHECK(ep != GEMV_PEER || (g_peer && n_mat == 1), "gemv_kq: GEMV_PEER goes through gemv_kq_peer");
     NT_CHECK((in.xq != nullptr) != (in.x != nullptr), "gemv_kq: exactly one of xq / x must be given");
     if (ep == GEMV_SWIGLU)
         NT_CHECK(n_mat == 2 && mats[0].out == mats[1].out, "gemv_kq: SWIGLU needs gate and up of equal rows");
@@ -378,6 +468,7 @@ void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpi
     p.K = K; p.NB = K / 256; p.NC = (p.NB + BS - 1) / BS;
     p.xq = static_cast<const int8_t*>(in.xq);
     p.x_f32 = in.x; p.norm_w = in.norm_w; p.eps = in.eps;
+    if (ep == GEMV_PEER) p.peer = *g_peer;
     p.epilogue = (int)ep;
     p.n_mat = n_mat;
     int total = 0;
@@ -402,6 +493,13 @@ void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpi
         case 16: launch_fmt<16>(p, s); break;
         default: launch_fmt<5>(p, s); break;
     }
+}
+
+void gemv_kq_peer(const GemvMat& mat, int K, const GemvInput& in, const PeerOut& peer, cudaStream_t s) {
+    NT_CHECK(mat.out == peer.hidden && peer.size >= 2 && peer.size <= PeerOut::kMaxTP, "gemv_kq_peer: rows must equal the exchanged vector length");
+    g_peer = &peer;
+    gemv_kq(&mat, 1, K, in, GEMV_PEER, s);
+    g_peer = nullptr;
 }
 
 void gemv_kq(const GemvMat* mats, int n_mat, int K, const void* xq, GemvEpilogue ep, cudaStream_t s) {

@@ -29,12 +29,28 @@ struct GemvMat {
     DType dtype = DType::F32;
     size_t row_pitch = 0;      // bytes between rows (0 = dense GGUF rows)
 };
-enum GemvEpilogue { GEMV_STORE = 0, GEMV_ADD = 1 /* y += W.x (residual) */, GEMV_SWIGLU = 2 /* y0 = silu(W0.x) * (W1.x) */ };
+enum GemvEpilogue { GEMV_STORE = 0, GEMV_ADD = 1 /* y += W.x (residual) */, GEMV_SWIGLU = 2 /* y0 = silu(W0.x) * (W1.x) */,
+                    GEMV_PEER = 3 /* tensor parallel: rows go to every rank's slot over NVLink (PeerOut), y is not written */ };
+
+// Where a tensor-parallel GEMV (o-projection / down-projection shard) delivers its partial rows (engine/peer_xchg.h): the slot
+// [parity][rank][hidden] of every rank, then — from the last CTA — the exchange's sequence number *seq + 1 into every rank's
+// flag line.  Pointers index ranks; entry `rank` is this GPU's own buffer.
+struct PeerOut {
+    static constexpr int kMaxTP = 8;
+    float* slots[kMaxTP];
+    unsigned* flags[kMaxTP];       // flags[r] + 32 * source_rank: one 128-byte line per source
+    unsigned* arrive;              // CTA arrival counter of the producing kernel (zero between launches)
+    unsigned* seq;                 // exchanges completed on this rank
+    unsigned* abort_word;
+    int rank, size, hidden;
+};
 
 // Fused K-quant GEMV over up to 3 matrices sharing one activation vector (already in xq form).
 // All matrices must be Q4_K / Q5_K / Q6_K with 16-byte aligned W and row pitch.
 // Where the shared activation vector comes from: either pre-quantised `xq`, or an F32 vector `x` that the
-// kernel quantises in its prologue, optionally RMS-normalised first (x * rsqrt(mean(x^2) + eps) * norm_w).
+// kernel quantises in its prologue (staged over the not-yet-primed part of its TMA ring), optionally as
+// RMSNorm(x) * norm_w: the prologue quantises x * norm_w, sums x^2 in the same pass and the scalar
+// rsqrt(mean(x^2) + eps) is applied to the results.
 struct GemvInput {
     const void* xq = nullptr;
     const float* x = nullptr;
@@ -44,6 +60,8 @@ struct GemvInput {
 bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K);
 void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpilogue ep, cudaStream_t s);
 void gemv_kq(const GemvMat* mats, int n_mat, int K, const void* xq, GemvEpilogue ep, cudaStream_t s);
+// epilogue GEMV_PEER: one matrix, rows == peer.hidden
+void gemv_kq_peer(const GemvMat& mat, int K, const GemvInput& in, const PeerOut& peer, cudaStream_t s);
 
 // Generic GEMV for every dtype / any alignment, F32 activations (Q8_0, Q4_0, F16, F32 and
 // unaligned K-quant shards).
@@ -83,6 +101,13 @@ size_t attention_decode_dyn_scratch_floats(int max_seq, int n_heads, int n_kv, i
 // xq_out (optional): the merged output is also written in xq form for the o-projection GEMV.
 void attention_decode_dyn(float* out, const float* q, const void* kc, const void* vc, const int* pos_dev, int max_seq,
                           int n_heads, int n_kv, int hd, float scale, float* scratch, void* xq_out, cudaStream_t s);
+// The decode step's attention sub-block in one launch: RoPE (q and the new key; q, k are NOT modified in memory) + F16 KV-cache
+// write at row *pos_dev + split-context attention + merge of the splits + optional xq of the result.  scratch as for
+// attention_decode_dyn; tickets: attention_decode_fused_tickets() zeroed words (left zeroed).  hd 64 / 128 / 256.
+int attention_decode_fused_tickets(int n_heads, int n_kv);
+void attention_decode_fused(float* out, const float* q, const float* k, const float* v, void* kc, void* vc, const int* pos_dev,
+                            int max_seq, int n_heads, int n_kv, int hd, float theta, float freq_scale, float scale, float* scratch,
+                            unsigned* tickets, void* xq_out, cudaStream_t s);
 // Fused RoPE (q, k in place; reference rotary.cu:16-62, non-interleaved pairs) + F16 KV-cache write at *pos_dev.
 void rope_kv_decode(float* q, float* k, const float* v, void* kc, void* vc, const int* pos_dev, int n_heads, int n_kv,
                     int hd, float theta, float freq_scale, int max_seq, cudaStream_t s);

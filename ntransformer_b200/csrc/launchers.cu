@@ -125,6 +125,25 @@ int nt_b200_gemv_fused(int n_mat, float* const* y, const void* const* W, const i
     nt::b200::gemv_kq(m, n_mat, in_features, xq, (nt::b200::GemvEpilogue)epilogue, static_cast<cudaStream_t>(stream));
     return 0;
 }
+int nt_b200_gemv_fused_f32(int n_mat, float* const* y, const void* const* W, const int* out_features, const int* dtypes, int in_features,
+                           const float* x, const float* norm_w, float eps, int epilogue, void* stream) {
+    if (n_mat < 1 || n_mat > 3 || !x) return -1;
+    nt::b200::GemvMat m[3];
+    for (int i = 0; i < n_mat; i++) { m[i].W = W[i]; m[i].y = y[i]; m[i].out = out_features[i]; m[i].dtype = (DType)dtypes[i]; m[i].row_pitch = 0; }
+    if (!nt::b200::gemv_kq_supported(m, n_mat, in_features)) return -2;
+    if (epilogue == 2 && (n_mat != 2 || out_features[0] != out_features[1])) return -3;
+    nt::b200::GemvInput in; in.x = x; in.norm_w = norm_w; in.eps = eps;
+    nt::b200::gemv_kq(m, n_mat, in_features, in, (nt::b200::GemvEpilogue)epilogue, static_cast<cudaStream_t>(stream));
+    return 0;
+}
+size_t nt_b200_attention_decode_scratch_floats(int ms, int nh, int nkv, int hd) { return nt::b200::attention_decode_dyn_scratch_floats(ms, nh, nkv, hd); }
+int nt_b200_attention_decode_tickets(int nh, int nkv) { return nt::b200::attention_decode_fused_tickets(nh, nkv); }
+void nt_b200_attention_decode_fused(float* o, const float* q, const float* k, const float* v, void* kc, void* vc, const int* pos_dev, int ms,
+                                    int nh, int nkv, int hd, float theta, float fs, float sc, float* scratch, unsigned* tickets, void* xq_out,
+                                    void* s) {
+    nt::b200::attention_decode_fused(o, q, k, v, kc, vc, pos_dev, ms, nh, nkv, hd, theta, fs, sc, scratch, tickets, xq_out,
+                                     static_cast<cudaStream_t>(s));
+}
 void nt_b200_embed_rows(float* out, const void* table, int dt, const int* tokens_dev, int n, int hidden, void* s) {
     nt::b200::embed_rows(out, table, (DType)dt, tokens_dev, n, hidden, static_cast<cudaStream_t>(s));
 }

@@ -133,6 +133,14 @@ class Model:
         lib().nt_model_use_megakernel(self._h, int(on))
 
     @property
+    def load_seconds(self) -> float:
+        return float(lib().nt_model_load_seconds(self._h))
+
+    @property
+    def tp_exchange(self) -> str:
+        return {0: "none", 1: "ncclAllReduce", 2: "nvlink peer-memory exchange (GEMV epilogue)"}[int(lib().nt_model_tp_exchange(self._h))]
+
+    @property
     def megakernel_active(self) -> bool:
         return bool(lib().nt_model_megakernel_active(self._h))
 

@@ -126,6 +126,35 @@ def gemv_fused(ys, Ws, outs, dtypes, in_features, xq, epilogue=0, stream=None):
         raise ValueError(f"nt_b200_gemv_fused rejected the launch (code {rc})")
 
 
+def gemv_fused_f32(ys, Ws, outs, dtypes, in_features, x, epilogue=0, norm_w=None, eps=0.0, stream=None):
+    """gemv_fused fed with the F32 vector: quantised in the kernel's prologue, optionally as RMSNorm(x) * norm_w
+    (include/nt_b200.h nt_b200_gemv_fused_f32)."""
+    n = len(Ws)
+    yp = (C.c_void_p * n)(*[_p(y) for y in ys])
+    wp = (C.c_void_p * n)(*[_p(w) for w in Ws])
+    op = (C.c_int * n)(*outs)
+    dp = (C.c_int * n)(*[int(d) for d in dtypes])
+    rc = lib().nt_b200_gemv_fused_f32(n, yp, wp, op, dp, in_features, _p(x), _p(norm_w), eps, epilogue, _s(stream))
+    if rc != 0:
+        raise ValueError(f"nt_b200_gemv_fused_f32 rejected the launch (code {rc})")
+
+
+def attention_decode_scratch_floats(max_seq, n_heads, n_kv_heads, head_dim) -> int:
+    return int(lib().nt_b200_attention_decode_scratch_floats(max_seq, n_heads, n_kv_heads, head_dim))
+
+
+def attention_decode_tickets(n_heads, n_kv_heads) -> int:
+    return int(lib().nt_b200_attention_decode_tickets(n_heads, n_kv_heads))
+
+
+def attention_decode_fused(out, q, k, v, k_cache, v_cache, pos_dev, max_seq, n_heads, n_kv_heads, head_dim, theta_base, freq_scale,
+                           scale, scratch, tickets, xq_out=None, stream=None):
+    """RoPE + KV-cache write at row *pos_dev + attention over *pos_dev + 1 keys + split merge (+ xq) in one launch."""
+    lib().nt_b200_attention_decode_fused(_p(out), _p(q), _p(k), _p(v), _p(k_cache), _p(v_cache), _p(pos_dev), max_seq, n_heads,
+                                         n_kv_heads, head_dim, theta_base, freq_scale, scale, _p(scratch), _p(tickets), _p(xq_out),
+                                         _s(stream))
+
+
 def embed_rows(out, table, dtype, tokens_dev, n_tokens, hidden, stream=None):
     lib().nt_b200_embed_rows(_p(out), _p(table), int(dtype), _p(tokens_dev), n_tokens, hidden, _s(stream))
 

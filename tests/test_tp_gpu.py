@@ -1,6 +1,8 @@
-"""GPU tensor-parallel parity (needs >= 2 GPUs, run with `gpurun --gpus 2`): the TP engine over NCCL must reproduce the
-single-GPU engine's logits (<= 1e-3 relative; only the summation grouping of the o-proj / down-proj partials
-differs) and its greedy ids."""
+"""GPU tensor-parallel parity (needs >= 2 GPUs, run with `gpurun --gpus 2|4|8`): the TP engine must reproduce the single-GPU
+engine's logits (<= 1e-3 relative; only the summation grouping of the o-proj / down-proj partials differs) and its greedy
+ids, with the partial sums exchanged through NVLink peer memory (default, engine/peer_xchg.h) and through ncclAllReduce
+(NT_B200_TP_NCCL=1).  8 KV heads so that 8-way sharding (one KV head per GPU, BASELINE configs[3]) is covered."""
+import os
 import socket
 import subprocess
 import sys
@@ -16,12 +18,13 @@ from ntransformer_b200.model_spec import LlamaConfig
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
-CFG = LlamaConfig(vocab_size=2048, hidden_size=2048, intermediate_size=4096, n_layers=3, n_heads=16, n_kv_heads=4, head_dim=128,
+CFG = LlamaConfig(vocab_size=2048, hidden_size=2048, intermediate_size=4096, n_layers=3, n_heads=16, n_kv_heads=8, head_dim=128,
                   max_seq_len=128, bos_token_id=1, eos_token_id=2)
 
 
-@pytest.mark.parametrize("mix,world", [("Q4_K_M", 2), ("Q6_K", 2), ("Q8_0", 2), ("Q4_K_M", 4)])
-def test_tp_matches_single_gpu(tmp_path, mix, world):
+@pytest.mark.parametrize("mix,world,nccl", [("Q4_K_M", 2, 0), ("Q4_K_M", 2, 1), ("Q6_K", 2, 0), ("Q8_0", 2, 0), ("Q4_K_M", 4, 0), ("Q6_K", 8, 0),
+                                            ("Q4_K_M", 8, 0), ("Q6_K", 8, 1)])
+def test_tp_matches_single_gpu(tmp_path, mix, world, nccl):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     path = tmp_path / f"{mix}.gguf"
@@ -43,7 +46,8 @@ def test_tp_matches_single_gpu(tmp_path, mix, world):
     out = tmp_path / "tp.npz"
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
                         "127.0.0.1", "--master-port", str(port), str(ROOT / "tests" / "tp_worker.py"), str(path), str(out),
-                        str(CFG.max_seq_len)], capture_output=True, text=True, errors="replace", timeout=240)
+                        str(CFG.max_seq_len)], capture_output=True, text=True, errors="replace", timeout=240,
+                       env=dict(os.environ, NT_B200_TP_NCCL=str(nccl), NT_B200_XCHG_TIMEOUT_MS="5000"))
     assert r.returncode == 0, r.stderr[-3000:]
     got = np.load(out)
     assert list(got["ids"]) == ids
