@@ -14,6 +14,28 @@ bool Engine::load(const std::string& path, int max_context) {
     return true;
 }
 
+bool Engine::load_tp(const std::string& path, int max_context, int tp_rank, int tp_size, const void* nccl_id) {
+    tp_rank_ = tp_rank;
+    if (tp_size <= 1) return load(path, max_context);
+    if (!model_.load_gguf(path, max_context, tp_rank, tp_size)) return false;
+    auto c = std::make_unique<TPComm>();
+    if (!c->init(nccl_id, tp_rank, tp_size)) return false;
+    {   // NCCL builds its channels lazily on the first collective: do that here, not inside the decode step's graph capture
+        cudaStream_t st = model_.stream();
+        float* tmp = nullptr;
+        NT_CUDA_CHECK(cudaMalloc(&tmp, sizeof(float) * 1024 * (size_t)(tp_size + 1)));
+        NT_CUDA_CHECK(cudaMemsetAsync(tmp, 0, sizeof(float) * 1024 * (size_t)(tp_size + 1), st));
+        c->all_reduce_sum(tmp, 1024, st);
+        c->all_gather(tmp, tmp + 1024, 1024, st);
+        NT_CUDA_CHECK(cudaStreamSynchronize(st));
+        NT_CUDA_CHECK(cudaFree(tmp));
+    }
+    model_.set_comm(c.get());
+    comm_ = std::move(c);
+    tok_.init(model_.vocab(), model_.config().bos_token_id, model_.config().eos_token_id);
+    return true;
+}
+
 std::string Engine::generate(const std::string& prompt, const GenerateConfig& cfg, TokenCallback cb) {
     Stats st;
     Sampler sampler;

@@ -6,6 +6,7 @@
 #include <string>
 #include "model.h"
 #include "text.h"
+#include "tp_comm.h"
 
 namespace nt { namespace b200 {
 
@@ -25,6 +26,11 @@ using TokenCallback = std::function<bool(const std::string& token, int token_id)
 class Engine {
 public:
     bool load(const std::string& model_path, int max_context = 4096);
+    // Tensor-parallel rank of a one-process-per-GPU group (the CLI's --tp N forks the ranks): nccl_id is the 128-byte id made by
+    // rank 0 (TPComm::unique_id).  Every rank runs the same generate() with the same seed; logits are bit-identical on all ranks,
+    // so the replicas sample the same tokens without exchanging them.  Only rank 0 prints.
+    bool load_tp(const std::string& model_path, int max_context, int tp_rank, int tp_size, const void* nccl_id);
+    int tp_rank() const { return tp_rank_; }
     std::string generate(const std::string& prompt, const GenerateConfig& cfg, TokenCallback cb = nullptr);
     void chat(const GenerateConfig& cfg);
     void benchmark(const std::string& prompt, int n_tokens);
@@ -38,9 +44,11 @@ public:
     const Stats& last_stats() const { return stats_; }
 private:
     void print_stats(const Stats& s) const;
+    std::unique_ptr<TPComm> comm_;       // declared before the model: destroyed after it (its graphs reference the communicator)
     Model model_;
     Tokenizer tok_;
     Stats stats_;
+    int tp_rank_ = 0;
 };
 
 }}  // namespace nt::b200

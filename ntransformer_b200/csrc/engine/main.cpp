@@ -3,8 +3,13 @@
 // --delta-model) belongs to the PCIe/NVMe streaming subsystem that this resident engine drops: they are
 // rejected with an explanation instead of being silently ignored.
 #include "engine.h"
+#include <atomic>
 #include <cstring>
 #include <string>
+#include <vector>
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 using namespace nt::b200;
 
@@ -19,6 +24,9 @@ static void usage(const char* prog) {
     fprintf(stderr, "  --repeat-penalty <float> Repeat penalty (default: 1.1)\n");
     fprintf(stderr, "  -c, --ctx-size <int>     Context size (default: 4096)\n");
     fprintf(stderr, "  --seed <int>             Random seed (default: 42)\n");
+    fprintf(stderr, "  --device <int>           First CUDA device to use (default: 0)\n");
+    fprintf(stderr, "  --tp <int>               Tensor-parallel over this many GPUs (devices device..device+tp-1, one process each,\n"
+                    "                           attention heads and FFN columns sharded, partial sums exchanged over NVLink); 1, 2, 4 or 8\n");
     fprintf(stderr, "  --host-sampler           Sample (penalty, top-k, top-p) on the host like the reference (default: on the GPU)\n");
     fprintf(stderr, "  --megakernel             Decode each token with one persistent kernel [opt-in]\n");
     fprintf(stderr, "  --benchmark              Run benchmark mode\n");
@@ -31,7 +39,7 @@ static void usage(const char* prog) {
 
 int main(int argc, char** argv) {
     std::string model_path, prompt;
-    int max_context = 4096;
+    int max_context = 4096, tp = 1, device = 0;
     bool bench = false, chat = false;
     GenerateConfig cfg;
     cfg.verbose = true;
@@ -48,6 +56,8 @@ int main(int argc, char** argv) {
         else if (a == "--repeat-penalty") { if (auto v = val()) cfg.repeat_penalty = std::stof(v); }
         else if (a == "--seed") { if (auto v = val()) cfg.seed = std::stoull(v); }
         else if (a == "-c" || a == "--ctx-size") { if (auto v = val()) max_context = std::stoi(v); }
+        else if (a == "--tp") { if (auto v = val()) tp = std::stoi(v); }
+        else if (a == "--device") { if (auto v = val()) device = std::stoi(v); }
         else if (a == "--gpu-sampler") cfg.gpu_sampler = true;
         else if (a == "--host-sampler") cfg.gpu_sampler = false;
         else if (a == "--megakernel") setenv("NT_B200_MEGAKERNEL", "1", 1);
@@ -61,10 +71,50 @@ int main(int argc, char** argv) {
         } else { fprintf(stderr, "Unknown option: %s\n", a.c_str()); usage(argv[0]); return 1; }
     }
     if (model_path.empty()) { fprintf(stderr, "Error: model path required (-m)\n\n"); usage(argv[0]); return 1; }
-    Engine engine;
-    if (!engine.load(model_path, max_context)) { fprintf(stderr, "Failed to load model: %s\n", model_path.c_str()); return 1; }
-    if (bench) engine.benchmark(prompt.empty() ? "The meaning of life is" : prompt, cfg.max_tokens);
-    else if (chat || prompt.empty()) engine.chat(cfg);
-    else engine.generate(prompt, cfg);
-    return 0;
+    if (tp < 1 || tp > 8 || (tp & (tp - 1))) { fprintf(stderr, "Error: --tp must be 1, 2, 4 or 8\n"); return 1; }
+    // Tensor parallel: one process per GPU.  The ranks are forked here, BEFORE anything touches CUDA; rank 0 hands the NCCL id to
+    // the others through a shared page.  All ranks run the same generation with the same seed (bit-identical logits everywhere).
+    struct Shared { std::atomic<int> ready; unsigned char id[TPComm::kIdBytes]; };
+    Shared* sh = nullptr;
+    int rank = 0;
+    std::vector<pid_t> kids;
+    if (tp > 1) {
+        if (chat || (prompt.empty() && !bench)) { fprintf(stderr, "Error: --tp needs -p <prompt> or --benchmark (the ranks cannot share an interactive stdin)\n"); return 1; }
+        sh = static_cast<Shared*>(mmap(nullptr, sizeof(Shared), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0));
+        if (sh == MAP_FAILED) { perror("mmap"); return 1; }
+        new (&sh->ready) std::atomic<int>(0);
+        for (int r = 1; r < tp; r++) {
+            pid_t pid = fork();
+            if (pid < 0) { perror("fork"); return 1; }
+            if (pid == 0) { rank = r; kids.clear(); break; }
+            kids.push_back(pid);
+        }
+    }
+    if (cudaSetDevice(device + rank) != cudaSuccess) { fprintf(stderr, "Error: cannot select CUDA device %d\n", device + rank); return 1; }
+    int rc = 0;
+    {
+        Engine engine;
+        bool ok;
+        if (tp > 1) {
+            if (rank == 0) {
+                if (!TPComm::unique_id(sh->id)) { fprintf(stderr, "Error: ncclGetUniqueId failed\n"); sh->ready.store(-1); return 1; }
+                sh->ready.store(1);
+            } else {
+                while (sh->ready.load() == 0) usleep(200);
+                if (sh->ready.load() < 0) return 1;
+                cfg.verbose = false;                                  // only rank 0 talks
+                if (!freopen("/dev/null", "w", stdout)) return 1;
+                if (!getenv("NT_B200_TP_VERBOSE") && !freopen("/dev/null", "w", stderr)) return 1;   // loader / stats lines once, not tp times
+            }
+            ok = engine.load_tp(model_path, max_context, rank, tp, sh->id);
+        } else {
+            ok = engine.load(model_path, max_context);
+        }
+        if (!ok) { fprintf(stderr, "Failed to load model: %s\n", model_path.c_str()); rc = 1; }
+        else if (bench) engine.benchmark(prompt.empty() ? "The meaning of life is" : prompt, cfg.max_tokens);
+        else if (chat || prompt.empty()) engine.chat(cfg);
+        else engine.generate(prompt, cfg);
+    }
+    for (pid_t k : kids) { int st = 0; waitpid(k, &st, 0); if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) rc = 1; }
+    return rc;
 }

@@ -146,7 +146,10 @@ private:
         void *whi = nullptr, *wlo = nullptr;  // dequantised weight matrix as an F16 hi/lo pair (quantised models)
         int *tok = nullptr, *pos = nullptr;
     } pf_;
-    int prefill_min_tokens_ = 16;
+    // Prompts shorter than this replay token by token through the decode chain (exact-integer GEMVs); longer ones take the batched
+    // tensor-core prefill, whose F32 accumulation inside the tensor cores truncates once per 16-deep MMA step: ~1e-5..1e-4 per GEMM,
+    // ~3e-4 per layer on the random synthetic models (profiles/r02_parity_8b.txt) against ~1e-5 per layer for the GEMV path.
+    int prefill_min_tokens_ = 32;
 
     bool use_graph_ = true;
     bool use_pdl_ = true;

@@ -10,11 +10,11 @@ namespace nt { namespace b200 {
 
 namespace {
 
-constexpr int LINE = 32;                                 // words per 128-byte line: one flag / counter per line
+constexpr int LINE = 32;                                 // words per 128-byte line: one counter per line
 
-__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -23,40 +23,42 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-// hidden[e] += slot[parity][0][e] + ... + slot[parity][tp-1][e]  (rank order), once every rank has published sequence number s.
+// hidden[e] += slot[parity][0][e] + ... + slot[parity][tp-1][e]  (rank order).  Every slot element is {sequence : value}: the thread
+// that owns element e polls its tp elements (all loads in flight together) until each carries sequence number s — the peers'
+// GEMV epilogues deliver them with single 64-bit NVLink stores, so there is no fence and no flag round trip on the path.
 __global__ void __launch_bounds__(256) xchg_reduce_kernel(PeerOut P, float* __restrict__ hidden, unsigned* __restrict__ reduce_arrive,
                                                           unsigned long long timeout_ns) {
     pdl_launch_dependents();
     pdl_wait();
     const unsigned s = __ldcg(P.seq) + 1u;
-    if ((int)threadIdx.x < P.size) {
-        // peers write their flag into THIS rank's memory: local polls, relaxed at system scope, one fence once it has arrived
-        const unsigned* flag = P.flags[P.rank] + LINE * threadIdx.x;
-        if (!__ldcg(P.abort_word)) {
-            const unsigned long long t0 = global_timer_ns();
-            unsigned n = 0;
-            while ((int)(ld_relaxed_sys(flag) - s) < 0) {
-                if ((++n & 255u) == 0 && (__ldcg(P.abort_word) || global_timer_ns() - t0 > timeout_ns)) {
-                    atomicExch(P.abort_word, 1u + threadIdx.x);          // which peer never arrived (+1)
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < P.hidden) {
+        const unsigned long long* sl = P.slots[P.rank] + (size_t)(s & 1u) * P.size * (size_t)P.hidden + e;
+        unsigned long long pk[PeerOut::kMaxTP];
+        unsigned pending = (1u << P.size) - 1u;
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while (pending) {
+#pragma unroll
+            for (int r = 0; r < PeerOut::kMaxTP; r++)
+                if (pending & (1u << r)) pk[r] = ld_relaxed_sys_u64(sl + (size_t)r * P.hidden);
+#pragma unroll
+            for (int r = 0; r < PeerOut::kMaxTP; r++)
+                if ((pending & (1u << r)) && (unsigned)(pk[r] >> 32) == s) pending &= ~(1u << r);
+            if (pending && (++spins & 63u) == 0) {
+                if (!t0) t0 = global_timer_ns();
+                if (__ldcg(P.abort_word) || global_timer_ns() - t0 > timeout_ns) {
+                    atomicExch(P.abort_word, 1u + (unsigned)__ffs((int)pending) - 1u);     // which peer never arrived (+1)
                     break;
                 }
             }
         }
-        __threadfence_system();                                        // acquire side: the peers' rows are visible
-    }
-    __syncthreads();
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < P.hidden) {
-        const float* sl = P.slots[P.rank] + (size_t)(s & 1u) * P.size * (size_t)P.hidden + e;
-        float sv[PeerOut::kMaxTP];
+        float t = __uint_as_float((unsigned)pk[0]);
 #pragma unroll
-        for (int r = 0; r < PeerOut::kMaxTP; r++) sv[r] = (r < P.size) ? __ldcg(sl + (size_t)r * P.hidden) : 0.f;   // all loads in flight together
-        float t = sv[0];
-#pragma unroll
-        for (int r = 1; r < PeerOut::kMaxTP; r++) if (r < P.size) t += sv[r];
+        for (int r = 1; r < PeerOut::kMaxTP; r++) if (r < P.size) t += __uint_as_float((unsigned)pk[r]);
         hidden[e] += t;
     }
-    // the last CTA ends the exchange: the next producer publishes s + 1 (every CTA has read *seq above)
+    // the last CTA ends the exchange: the next producer sends s + 1 (every CTA has read *seq above)
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned prev = atomicAdd(reduce_arrive, 1u);
@@ -76,8 +78,8 @@ PeerXchg::~PeerXchg() {
 bool PeerXchg::init(TPComm* comm, int rank, int size, int hidden, cudaStream_t s) {
     if (!comm || size < 2 || size > PeerOut::kMaxTP) return false;
     if (const char* t = getenv("NT_B200_XCHG_TIMEOUT_MS")) timeout_ns_ = (unsigned long long)atoll(t) * 1000000ull;
-    const size_t slot_floats = (size_t)2 * size * hidden;
-    const size_t words = slot_floats + (size_t)(size + 3) * LINE;        // slots | flags[size] | arrive | seq | abort
+    const size_t slot_words = (size_t)2 * size * hidden * 2;              // 64-bit elements
+    const size_t words = slot_words + (size_t)2 * LINE;                   // slots | seq | abort
     NT_CUDA_CHECK(cudaMalloc(&local_, words * 4));
     NT_CUDA_CHECK(cudaMemset(local_, 0, words * 4));
     NT_CUDA_CHECK(cudaMalloc(&reduce_arrive_, 128));
@@ -113,13 +115,11 @@ bool PeerXchg::init(TPComm* comm, int rank, int size, int hidden, cudaStream_t s
             }
             peer_maps_[(size_t)r] = p;
         }
-        out_.slots[r] = static_cast<float*>(p);
-        out_.flags[r] = reinterpret_cast<unsigned*>(static_cast<float*>(p) + slot_floats);
+        out_.slots[r] = static_cast<unsigned long long*>(p);
     }
-    unsigned* base = reinterpret_cast<unsigned*>(static_cast<float*>(local_) + slot_floats);
-    out_.arrive = base + (size_t)size * LINE;
-    out_.seq = base + (size_t)(size + 1) * LINE;
-    out_.abort_word = base + (size_t)(size + 2) * LINE;
+    unsigned* base = static_cast<unsigned*>(local_) + slot_words;
+    out_.seq = base;
+    out_.abort_word = base + LINE;
     return true;
 }
 

@@ -2,11 +2,14 @@
 //
 // New relative to the single-GPU reference ("one all-reduce per sub-block").  One-shot all-reduce in two kernels:
 //   * the producing GEMV (gemv_kquant.cu, epilogue GEMV_PEER) stores each finished row of its partial result straight into the
-//     "slot" [parity][source rank][hidden] of EVERY rank (plain stores to cudaIpc-mapped peer memory, i.e. NVLink writes issued
-//     from the GEMV's epilogue while other CTAs are still streaming weights); the last CTA to finish publishes the exchange's
-//     sequence number in every rank's flag line;
-//   * xchg_reduce_kernel (this file) waits until all ranks' flags carry the sequence number, then hidden += sum_r slot[r] in
-//     rank order on every rank (deterministic, bit-identical everywhere: the replicas' greedy ids stay in lock-step).
+//     "slot" [parity][source rank][hidden] of EVERY rank (stores to cudaIpc-mapped peer memory, i.e. NVLink writes issued from
+//     the GEMV's epilogue while other CTAs are still streaming weights).  A slot element is one 64-bit word {sequence : value}
+//     written by a single store, so the value is its own arrival flag (the scheme of NCCL's LL protocol): no fence and no
+//     separate flag hop;
+//   * xchg_reduce_kernel (this file): the thread that owns element e polls its tp slot elements until they carry the sequence
+//     number, then hidden[e] += sum_r slot[r][e] in rank order on every rank (deterministic, bit-identical everywhere: the
+//     replicas' greedy ids stay in lock-step).  A first version with plain rows + system fence + flag line per rank measured
+//     10.87 ms/token at TP-2 against 9.38 with ncclAllReduce (profiles/r02_tp2_*): the fence and flag hop cost more than NCCL.
 // Slots are double-buffered by the sequence number's parity: a rank can run at most one exchange ahead of a peer.
 // Every spin has a time-out that raises an abort word instead of hanging the GPU.
 #pragma once

@@ -57,6 +57,10 @@ struct KqParams {
     int epilogue;
     int stages;                // ring depth per warp
     int gpc;                   // row-groups a CTA processes per round = warps / NC
+    // Lock-step rounds over grid * gpc warp slots.  A partly filled last round would cost a whole round (70B gate/up: 7168
+    // row-groups over 888 slots = 8.07 -> 9 rounds; o-projection 2.3 -> 3): its tail_groups row-groups are dealt out tail_nr (1 or 2)
+    // rows at a time over all slots instead, so the tail costs tail_nr / 4 of a round.  tail_nr == 4: no split.
+    int full_rounds, tail_groups, tail_nr;
     PeerOut peer;              // epilogue GEMV_PEER
 };
 
@@ -77,9 +81,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     uint8_t* xs = p.x_alias ? smem + STAGE_STRIDE : smem + ((((size_t)WARPS * stages * (SLOT + 8)) + 127) & ~(size_t)127);
 
     const int chunk = warp % NC, gsub = warp / NC;        // this warp's chunk of every row, and its row-group slot
-    const int n_rounds = (p.total_groups + gridDim.x * gpc - 1) / (gridDim.x * gpc);
+    const int n_rounds = p.full_rounds + (p.tail_groups > 0 ? 1 : 0);
     const int nbc = min(BS, NB - chunk * BS);              // super-blocks in this warp's chunk
-    auto group_of = [&](int round) { return (round * (int)gridDim.x + (int)blockIdx.x) * gpc + gsub; };
+    // what this warp slot holds in `round`: row-group g (global), the first row's offset inside it and the number of rows
+    auto slot_of = [&](int round, int& g, int& row_sub, int& nr) -> bool {
+        if (round < p.full_rounds || p.tail_nr >= RG) {
+            g = (round * (int)gridDim.x + (int)blockIdx.x) * gpc + gsub; row_sub = 0; nr = RG;
+            return g < p.total_groups;
+        }
+        nr = p.tail_nr;
+        const int per = RG / nr, u = (int)blockIdx.x * gpc + gsub;
+        g = p.full_rounds * (int)gridDim.x * gpc + u / per;
+        row_sub = (u % per) * nr;
+        return u < p.tail_groups * per;
+    };
     auto locate = [&](int g, int seg, int& mi, int& gl) {  // matrix and local row-group of global group g
         if (n_seg == 2) { mi = seg; gl = g; return; }
         mi = 0;
@@ -89,33 +104,35 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     const int n_stages_total = n_rounds * n_seg;           // flattened stage index s = round * n_seg + seg
     // Producer cursor (used by lane 0): global row-group and segment of the next stage to fetch.  Kept incremental:
     // the TMA issue path runs on one lane but costs whole-warp issue slots (profiles/r01: 0.30 instr/weight before).
-    int p_g = group_of(0), p_seg = 0;
-    const int g_stride = (int)gridDim.x * gpc;
+    int p_round = 0, p_seg = 0;
     auto issue_next = [&](int slot) {                      // lane 0: TMA copies of the next stage into ring slot
         uint64_t* bar = bars + slot;
-        if (p_g >= p.total_groups) {
+        int g, row_sub, nr, mi = 0, gl = 0;
+        bool have = slot_of(p_round, g, row_sub, nr);
+        if (have) {
+            locate(g, p_seg, mi, gl);
+            have = gl * RG + row_sub < p.mat[mi].out;        // a slice of a ragged last group may hold no row
+        }
+        if (!have) {
             mbar_expect_tx(bar, 0);                          // nothing to fetch: just complete the phase
         } else {
-            int mi, gl;
-            locate(p_g, p_seg, mi, gl);
             const KqMat& m = p.mat[mi];
             const int blkb = (MASK == 1) ? 144 : (MASK == 2) ? 176 : (MASK == 4) ? 210 : (MASK == 8) ? 272 : (MASK == 16) ? 144 : (m.fmt == 0 ? 144 : m.fmt == 1 ? 176 : 210);
             // copy size rounded up to 16 B (a 210-byte Q6_K tail may spill into row padding; checked on the host)
             const uint32_t bytes = ((uint32_t)(nbc * blkb) + 15u) & ~15u;
-            mbar_expect_tx(bar, bytes * RG);
+            mbar_expect_tx(bar, bytes * nr);
             uint8_t* dst = ring + (size_t)slot * STAGE_STRIDE;
-            const int row0 = gl * RG;
+            const int row0 = gl * RG + row_sub;
             const uint8_t* src = m.W + (long long)chunk * (BS * blkb) + (long long)row0 * m.row_pitch;
-            if (row0 + RG <= m.out) {
+            if (nr == RG && row0 + RG <= m.out) {
 #pragma unroll
                 for (int r = 0; r < RG; r++) bulk_g2s(dst + r * (BS * blkb), src + r * m.row_pitch, bytes, bar);
-            } else {                                         // ragged last group: re-read the last valid row
-#pragma unroll
-                for (int r = 0; r < RG; r++)
+            } else {                                         // tail stage / ragged last group: re-read the last valid row
+                for (int r = 0; r < nr; r++)
                     bulk_g2s(dst + r * (BS * blkb), src + (long long)min(r, m.out - 1 - row0) * m.row_pitch, bytes, bar);
             }
         }
-        if (++p_seg == n_seg) { p_seg = 0; p_g += g_stride; }
+        if (++p_seg == n_seg) { p_seg = 0; p_round++; }
     };
 
     if (lane == 0) {
@@ -261,8 +278,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     int slot = 0;
     uint32_t parity = 0;
     for (int round = 0; round < n_rounds; round++) {
-        const int g = group_of(round);
-        const bool live = g < p.total_groups;
+        int g, row_sub, nr;
+        const bool live = slot_of(round, g, row_sub, nr);
         float res[2] = {0.f, 0.f};
         for (int seg = 0; seg < n_seg; seg++) {
             float acc[RG] = {0.f, 0.f, 0.f, 0.f};
@@ -272,11 +289,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
                 locate(g, seg, mi, gl);
                 const uint8_t* slot_base = ring + (size_t)slot * STAGE_STRIDE;
                 const int fmt = (MASK == 1) ? 0 : (MASK == 2) ? 1 : (MASK == 4) ? 2 : (MASK == 8) ? 3 : (MASK == 16) ? 4 : p.mat[mi].fmt;
-                if ((MASK & 1) && fmt == 0) process_stage<0>(slot_base, blk, h, X, acc);
-                if ((MASK & 2) && fmt == 1) process_stage<1>(slot_base, blk, h, X, acc);
-                if ((MASK & 4) && fmt == 2) process_stage<2>(slot_base, blk, h, X, acc);
-                if ((MASK & 8) && fmt == 3) process_stage<3>(slot_base, blk, h, X, acc);
-                if ((MASK & 16) && fmt == 4) process_stage<4>(slot_base, blk, h, X, acc);
+                if (nr == RG) {
+                    if ((MASK & 1) && fmt == 0) process_stage<0>(slot_base, blk, h, X, acc);
+                    if ((MASK & 2) && fmt == 1) process_stage<1>(slot_base, blk, h, X, acc);
+                    if ((MASK & 4) && fmt == 2) process_stage<2>(slot_base, blk, h, X, acc);
+                    if ((MASK & 8) && fmt == 3) process_stage<3>(slot_base, blk, h, X, acc);
+                    if ((MASK & 16) && fmt == 4) process_stage<4>(slot_base, blk, h, X, acc);
+                } else {                                     // tail stage of 1 or 2 rows: one row at a time
+                    const int rowp = BS * ((fmt == 0 || fmt == 4) ? 144 : fmt == 1 ? 176 : fmt == 2 ? 210 : 272);
+#pragma unroll 1
+                    for (int r = 0; r < nr; r++) {
+                        float a1[RG] = {0.f, 0.f, 0.f, 0.f};
+                        const uint8_t* rb = slot_base + r * rowp;
+                        if ((MASK & 1) && fmt == 0) process_stage<0, 1>(rb, blk, h, X, a1);
+                        if ((MASK & 2) && fmt == 1) process_stage<1, 1>(rb, blk, h, X, a1);
+                        if ((MASK & 4) && fmt == 2) process_stage<2, 1>(rb, blk, h, X, a1);
+                        if ((MASK & 8) && fmt == 3) process_stage<3, 1>(rb, blk, h, X, a1);
+                        if ((MASK & 16) && fmt == 4) process_stage<4, 1>(rb, blk, h, X, a1);
+                        acc[0] = (r == 0) ? a1[0] : acc[0];       // no dynamic indexing: acc stays in registers
+                        acc[1] = (r == 1) ? a1[0] : acc[1];
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0 && issued < n_stages_total) issue_next(slot);
@@ -292,7 +325,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
             partial[buf][warp][1][r] = res[1];
         }
         __syncthreads();
-        if (live && chunk == 0 && lane < RG) {
+        if (live && chunk == 0 && lane < nr) {
             float v0 = 0.f, v1 = 0.f;
             for (int c = 0; c < NC; c++) {
                 v0 += partial[buf][gsub * NC + c][0][lane];
@@ -302,7 +335,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
             int mi, gl;
             locate(g, 0, mi, gl);
             const KqMat& m = p.mat[mi];
-            const int row = gl * RG + lane;
+            const int row = gl * RG + row_sub + lane;
             if (row < m.out) {
                 if (p.epilogue == GEMV_SWIGLU) {
                     // silu(g) * u with the reference's fast-math expression (gemm.cu:713-725)
@@ -310,28 +343,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
                 } else if (p.epilogue == GEMV_ADD) {
                     m.y[row] += v0;
                 } else if (p.epilogue == GEMV_PEER) {
-                    // this rank's partial row -> slot [parity][rank] on every rank (NVLink stores; lanes 0..3 write 16 contiguous bytes)
+                    // this rank's partial row -> slot [parity][rank] on every rank: one 64-bit NVLink store {sequence : value} per peer
+                    // (lanes 0..3 write 32 contiguous bytes); the value is its own arrival flag
                     const size_t off = ((size_t)peer_parity * p.peer.size + p.peer.rank) * (size_t)p.peer.hidden + (size_t)row;
-                    for (int r = 0; r < p.peer.size; r++) p.peer.slots[r][off] = v0;
+                    const unsigned long long pkt = ((unsigned long long)peer_seq << 32) | (unsigned long long)__float_as_uint(v0);
+                    for (int r = 0; r < p.peer.size; r++)
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.peer.slots[r] + off), "l"(pkt) : "memory");
                 } else {
                     m.y[row] = v0;
                 }
-            }
-        }
-    }
-    if (p.epilogue == GEMV_PEER) {
-        // One fence per CTA: the storing lanes make their peer stores visible system-wide, the CTA arrives, and the last CTA of
-        // the grid publishes the sequence number in every rank's flag line (posted NVLink writes).
-        if (chunk == 0 && lane < RG) __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            const unsigned prev = atomicAdd(p.peer.arrive, 1u);
-            if (prev == gridDim.x - 1) {
-                *p.peer.arrive = 0;
-                __threadfence_system();
-                for (int r = 0; r < p.peer.size; r++)
-                    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.peer.flags[r] + 32 * p.peer.rank), "r"(peer_seq) : "memory");
             }
         }
     }
@@ -360,14 +380,31 @@ int num_sms() {
 
 constexpr size_t SMEM_CAP = 227 * 1024 - 1024;    // static __shared__ (red, partial) counts against the cap
 
+bool tail_split_enabled() {       // NT_B200_TAIL_SPLIT=0 keeps whole 4-row stages in the last round (A/B aid)
+    static const bool on = [] { const char* e = getenv("NT_B200_TAIL_SPLIT"); return !(e && e[0] == '0' && e[1] == 0); }();
+    return on;
+}
+
 template <int MASK, int WARPS>
 void launch_kq(const KqParams& p, size_t smem, cudaStream_t s) {
     static unsigned long long configured = 0;      // bit per device id
     opt_in_dynamic_smem(gemv_kq_kernel<MASK, WARPS>, (int)((int)SMEM_CAP), configured);
     int grid = num_sms();
-    const int need = (p.total_groups + p.gpc - 1) / p.gpc;
-    if (need < grid) grid = need;
-    launch_k(gemv_kq_kernel<MASK, WARPS>, dim3(grid), dim3(WARPS * 32), smem, s, p);
+    KqParams q = p;
+    const int slots = grid * q.gpc;
+    q.full_rounds = q.total_groups / slots;
+    q.tail_groups = q.total_groups % slots;
+    q.tail_nr = RG;
+    if (q.tail_groups > 0 && tail_split_enabled()) {          // also when the whole launch is less than one round (narrow shards)
+        if (4 * q.tail_groups <= slots) q.tail_nr = 1;
+        else if (2 * q.tail_groups <= slots) q.tail_nr = 2;
+    }
+    if (q.full_rounds == 0) {                                  // fewer units than warp slots: no more CTAs than there is work
+        const int units = q.tail_groups * (RG / q.tail_nr);
+        const int need = (units + q.gpc - 1) / q.gpc;
+        if (need < grid) grid = need;
+    }
+    launch_k(gemv_kq_kernel<MASK, WARPS>, dim3(grid), dim3(WARPS * 32), smem, s, q);
     count_launch();
 }
 

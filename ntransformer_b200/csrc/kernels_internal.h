@@ -33,14 +33,13 @@ enum GemvEpilogue { GEMV_STORE = 0, GEMV_ADD = 1 /* y += W.x (residual) */, GEMV
                     GEMV_PEER = 3 /* tensor parallel: rows go to every rank's slot over NVLink (PeerOut), y is not written */ };
 
 // Where a tensor-parallel GEMV (o-projection / down-projection shard) delivers its partial rows (engine/peer_xchg.h): the slot
-// [parity][rank][hidden] of every rank, then — from the last CTA — the exchange's sequence number *seq + 1 into every rank's
-// flag line.  Pointers index ranks; entry `rank` is this GPU's own buffer.
+// [parity][rank][hidden] of every rank.  A slot element is ONE 8-byte word {sequence number : value bits} written with a single
+// 64-bit store (single-copy atomic), so the data is its own arrival flag: no fence, no separate flag hop — the receiver polls
+// the element until it carries the sequence number it expects.  Pointers index ranks; entry `rank` is this GPU's own buffer.
 struct PeerOut {
     static constexpr int kMaxTP = 8;
-    float* slots[kMaxTP];
-    unsigned* flags[kMaxTP];       // flags[r] + 32 * source_rank: one 128-byte line per source
-    unsigned* arrive;              // CTA arrival counter of the producing kernel (zero between launches)
-    unsigned* seq;                 // exchanges completed on this rank
+    unsigned long long* slots[kMaxTP];
+    unsigned* seq;                 // exchanges completed on this rank; the exchange in flight carries *seq + 1
     unsigned* abort_word;
     int rank, size, hidden;
 };

@@ -104,6 +104,11 @@ enum : int { MODE_STORE = 0, MODE_ADD = 1, MODE_SWIGLU = 2 };
 // Persistent, warp-specialised GEMM: CTA b handles output tiles b, b + grid, ...; the shared-memory ring and the two TMEM
 // accumulators run across tile boundaries, so the epilogue of tile i overlaps the MMAs of tile i + 1.
 //   MODE_STORE  C = A.W^T              MODE_ADD  C += A.W^T (residual)
+//   K-chunked accumulation (STORE / ADD): the tensor cores truncate the F32 accumulator once per 16-deep MMA step, an error that
+//   grows with the number of steps summed into one accumulator (~K/16 * 2^-25 relative, twice that with the hi/lo activation
+//   split).  A tile's K range is therefore cut into chunks of kc_blocks k-blocks; each chunk gets a fresh TMEM accumulator and the
+//   epilogue adds the chunk's partial sum into C with an ordinary (round-to-nearest) F32 add.  The same CTA walks a tile's chunks
+//   back to back, so the read-modify-write of C is race-free and overlaps the next chunk's MMAs through the second accumulator.
 //   MODE_SWIGLU (BN = 256 as 128 gate + 128 up columns, W = gate via map_b, up via map_b2):
 //               split_out = F16 hi/lo split of silu(A.Wg^T) * (A.Wu^T), i.e. the down projection's GEMM input, so the
 //               F32 gate/up activations never touch HBM (ffn.cpp:96-133 computes them as three launches).
@@ -112,7 +117,8 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
                                                              const __grid_constant__ CUtensorMap map_b,
                                                              const __grid_constant__ CUtensorMap map_b2,
                                                              float* __restrict__ C, __half* __restrict__ split_out,
-                                                             int M, int Mp, int N, int K, int tiles_m, int tiles_n, int n_tiles, int n_outer) {
+                                                             int M, int Mp, int N, int K, int tiles_m, int tiles_n, int n_tiles, int n_outer,
+                                                             int kc_blocks) {
     constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TMEM_COLS = 2 * BN;
     constexpr int TN = MODE == MODE_SWIGLU ? 128 : BN;          // output columns per tile
     constexpr uint32_t IDESC = MODE == MODE_SWIGLU ? Cfg<128>::IDESC : Cfg<BN>::IDESC;
@@ -123,6 +129,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
     __shared__ uint32_t tmem_base_smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = K / BK;
+    const int n_kc = (MODE == MODE_SWIGLU) ? 1 : (num_kb + kc_blocks - 1) / kc_blocks;      // accumulation chunks per tile
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
             uint32_t it = 0;                           // k-block counter across all of this CTA's tiles
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int m0 = (n_outer ? tile % tiles_m : tile / tiles_n) * BM, n0 = (n_outer ? tile / tiles_m : tile % tiles_n) * TN;
-                for (int kb = 0; kb < num_kb; kb++, it++) {
+                for (int kb = 0; kb < num_kb; kb++, it++) {         // chunk boundaries do not matter to the producer
                     const uint32_t s = it % STAGES;
                     wait_or_trap(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
                     uint8_t* st = smem + (size_t)s * STAGE_BYTES;
@@ -158,12 +165,14 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
     } else if (warp == 1) {
         if (lane == 0) {                               // ---- MMA issuer ----
             uint32_t it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, lt++) {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (int kc = 0; kc < n_kc; kc++, lt++) {
                 const uint32_t acc = lt & 1, acc_phase = (lt >> 1) & 1;
                 wait_or_trap(&tmem_empty_bar[acc], acc_phase ^ 1);         // epilogue drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; kb++, it++) {
+                const int kb0 = (MODE == MODE_SWIGLU) ? 0 : kc * kc_blocks, kb1 = (MODE == MODE_SWIGLU) ? num_kb : min(num_kb, kb0 + kc_blocks);
+                for (int kb = kb0; kb < kb1; kb++, it++) {
                     const uint32_t s = it % STAGES;
                     wait_or_trap(&full_bar[s], (it / STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
                     const uint64_t db2 = make_desc(st + 2 * TILE_A + 128 * BK * 2);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {  // advance 32 bytes (>> 4 = 2) inside the 128-byte swizzle row
-                        umma_f16(d, da_hi + 2 * k, db + 2 * k, IDESC, (kb | k) ? 1u : 0u);
+                        umma_f16(d, da_hi + 2 * k, db + 2 * k, IDESC, ((kb - kb0) | k) ? 1u : 0u);
                         if (MODE == MODE_SWIGLU) umma_f16(d + 128, da_hi + 2 * k, db2 + 2 * k, IDESC, (kb | k) ? 1u : 0u);
                     }
 #pragma unroll
@@ -189,8 +198,10 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
         // ---- epilogue: TMEM -> registers -> global (warp w may only touch TMEM lanes [32 * (w % 4), +32)) ----
         const int quarter = warp & 3;
         uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, lt++) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int kc = 0; kc < n_kc; kc++, lt++) {
             const uint32_t acc = lt & 1, acc_phase = (lt >> 1) & 1;
+            const bool add_c = MODE == MODE_ADD || kc > 0;           // later chunks add their partial sums to what is in C
             const int m0 = (n_outer ? tile % tiles_m : tile / tiles_n) * BM, n0 = (n_outer ? tile / tiles_m : tile % tiles_n) * TN;
             const int row = m0 + quarter * 32 + lane;
             wait_or_trap(&tmem_full_bar[acc], acc_phase);
@@ -233,7 +244,7 @@ __global__ void __launch_bounds__(192, 1) gemm_f16_tc_kernel(const __grid_consta
                         for (int j = 0; j < 32; j += 4) {
                             float4* dst = reinterpret_cast<float4*>(crow + j);
                             float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                            if (MODE == MODE_ADD) { const float4 r = *dst; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }   // residual
+                            if (add_c) { const float4 r = *dst; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }   // residual / earlier chunks
                             *dst = o;
                         }
                     }
@@ -360,8 +371,11 @@ bool launch_gemm(float* C, __half* split_out, const void* workspace, const void*
     const size_t a_bytes = 4 * Mp * (size_t)K, w_bytes = (MODE == MODE_SWIGLU ? 4 : 2) * (size_t)N * K;
     static const bool force_m_outer = getenv("NT_B200_GEMM_M_OUTER") != nullptr;
     const int n_outer = (a_bytes < w_bytes && !force_m_outer) ? 1 : 0;
+    // accumulation chunk: 1024 elements of K (16 k-blocks) per fresh accumulator; NT_B200_GEMM_KC=<k-blocks> overrides (0: whole K)
+    static const int kc_env = [] { const char* e = getenv("NT_B200_GEMM_KC"); return e ? atoi(e) : 16; }();
+    const int kc_blocks = kc_env > 0 ? kc_env : K / BK;
     gemm_f16_tc_kernel<BN, MODE><<<grid, 192, Cfg<BN>::SMEM, s>>>(map_a, map_b, map_b2, C, split_out, M, (int)Mp, N, K, tiles_m, tiles_n,
-                                                                 n_tiles, n_outer);
+                                                                 n_tiles, n_outer, kc_blocks);
     count_launch();
     return true;
 }

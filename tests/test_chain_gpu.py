@@ -168,3 +168,35 @@ def test_fused_chain_matches_the_unfused_launch_sequence(mix, monkeypatch):
         want = om.forward([tok], pos)
         assert rel_err(la[i], want) <= 1e-3
         tok, pos = ia[i], pos + 1
+
+
+@pytest.mark.parametrize("dt", [DType.Q4_K_M, DType.Q6_K, DType.Q8_0, DType.Q5_K, DType.Q4_0])
+@pytest.mark.parametrize("out", [8192, 7507, 7106, 3680, 3557])
+def test_gemv_tail_round_split(dt, out):
+    """Row counts that leave a partly filled last round on 148 SMs (K = 8192: 888 warp slots of 4 rows): the tail is dealt out in
+    1- or 2-row stages over all slots (gemv_kquant.cu KqParams::tail_nr); ragged last groups included.  Store and residual."""
+    rng = np.random.default_rng(out + int(dt))
+    inn = 8192
+    W = random_blocks_np(dt, out, inn, rng)
+    x = rng.standard_normal(inn).astype(np.float32)
+    base = rng.standard_normal(out).astype(np.float32)
+    y, yb = torch.zeros(out, device=DEV), dev(base)
+    Wd, xd = dev(W), dev(x)
+    K.gemv_fused_f32([y], [Wd], [out], [dt], inn, xd, epilogue=0)
+    K.gemv_fused_f32([yb], [Wd], [out], [dt], inn, xd, epilogue=1)
+    sync()
+    want = O.gemv(W, x, out, inn, int(dt))
+    assert rel_err(y.cpu().numpy(), want) <= 3e-5
+    assert rel_err(yb.cpu().numpy(), base + want) <= 3e-5
+
+
+def test_swiglu_tail_round_split_70b_shape():
+    rng = np.random.default_rng(5)
+    inn, inter = 8192, 28672
+    g, u = random_blocks_np(DType.Q4_K_M, inter, inn, rng, std=0.05), random_blocks_np(DType.Q4_K_M, inter, inn, rng, std=0.05)
+    x = rng.standard_normal(inn).astype(np.float32)
+    act, dummy = torch.zeros(inter, device=DEV), torch.zeros(inter, device=DEV)
+    K.gemv_fused_f32([act, dummy], [dev(g), dev(u)], [inter, inter], [DType.Q4_K_M] * 2, inn, dev(x), epilogue=2)
+    sync()
+    want = O.silu_mul(O.gemv(g, x, inter, inn, O.Q4_K), O.gemv(u, x, inter, inn, O.Q4_K))
+    assert rel_err(act.cpu().numpy(), want) <= 5e-5

@@ -46,7 +46,8 @@ def main():
     size = os.path.getsize(path)
     out = {"workload": args.workload, "file_gb": round(size / 1e9, 2), "write_s": round(gen_s, 1), "reader_threads": args.threads}
     try:
-        devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(2)
+        log = f"/tmp/nt_load_{os.getpid()}.log"
+        devnull, saved = os.open(log, os.O_WRONLY | os.O_CREAT | os.O_TRUNC), os.dup(2)
         os.dup2(devnull, 2)
         try:
             for rep in range(2):                       # second pass: page cache certainly warm for both
@@ -73,6 +74,11 @@ def main():
             os.close(devnull)
     finally:
         os.unlink(path)
+    try:
+        out["ours_copy_phase"] = [l.strip() for l in open(log, errors="replace") if "reader threads" in l][-1]
+        os.unlink(log)
+    except Exception:
+        pass
     out.update({"ours_load_s": round(ours, 2), "ours_load_s_inner": round(inner, 2), "ours_gb_per_s": round(size / 1e9 / ours, 2),
                 "reference_load_s": None if ref_s is None else round(ref_s, 2),
                 "reference_gb_per_s": None if ref_s is None else round(size / 1e9 / ref_s, 2)})
