@@ -47,6 +47,12 @@ std::string Engine::generate(const std::string& prompt, const GenerateConfig& cf
     std::vector<int> tokens = tok_.encode(prompt, true);
     st.prompt_tokens = (int)tokens.size();
     if (cfg.verbose) fprintf(stderr, "Prompt tokens: %d\n", st.prompt_tokens);
+    if (st.prompt_tokens > model_.config().max_seq_len) {
+        // the reference writes past its KV cache here (transformer.cpp:629-640 has no check); an error return instead of an abort
+        fprintf(stderr, "Error: the prompt has %d tokens, the context holds %d (use --ctx-size)\n", st.prompt_tokens, model_.config().max_seq_len);
+        stats_ = st;
+        return std::string();
+    }
     const int vocab = model_.config().vocab_size;
     std::vector<float> logits((size_t)vocab);
     // Greedy without a repeat penalty needs no logits on the host: argmax runs on the GPU (4 B D2H instead of 513 KB).

@@ -539,10 +539,14 @@ void Model::step_body(cudaStream_t s) {
             GemvMat m2[2] = {mat(L.gate, act_), mat(L.up, up_)};
             GemvInput in; in.x = hidden_; in.norm_w = L.ffn_norm; in.eps = cfg_.norm_eps;
             gemv_kq(m2, 2, hidden, in, GEMV_SWIGLU, s);
-            quantize_x(act_, xq_i_, inter_l_, s);           // 3.4 x inter bytes of staging: too long for the down GEMV's prologue
+            // The activation vector's quantiser: in the down GEMV's prologue when its staging (3.4 x inter bytes) fits over the ring
+            // (tensor-parallel shards: inter / tp <= 8192), as a launch of its own for the full 28672-wide vector.
             GemvMat md = mat(L.down, hidden_);
-            if (tp_size_ == 1) gemv_kq(&md, 1, inter_l_, xq_i_, GEMV_ADD, s);
-            else { GemvInput ind; ind.xq = xq_i_; gemv_kq_peer(md, inter_l_, ind, xchg_->out(), s); xchg_->reduce_residual(hidden_, s); }
+            GemvInput ind;
+            if (inter_l_ <= 8192) ind.x = act_;
+            else { quantize_x(act_, xq_i_, inter_l_, s); ind.xq = xq_i_; }
+            if (tp_size_ == 1) gemv_kq(&md, 1, inter_l_, ind, GEMV_ADD, s);
+            else { gemv_kq_peer(md, inter_l_, ind, xchg_->out(), s); xchg_->reduce_residual(hidden_, s); }
             continue;
         }
         { const Weight* ws[2] = {&L.gate, &L.up}; float* ys[2] = {act_, up_}; matvec(ws, ys, 2, hidden_, L.ffn_norm, GEMV_SWIGLU, s); }

@@ -1,29 +1,13 @@
-// gemv_kquant.cu — dequant-fused GEMV over GGUF Q4_K / Q5_K / Q6_K super-blocks for sm_100a.
-//
-// Replaces reference kernels K3/K4/K5 (src/cuda/gemm.cu:158-470) behind launch_gemv (gemm.cu:748-805).
-// The reference walks one warp per row with per-lane byte loads, an F32 convert + 2 FMAs per weight and
-// x re-read from shared memory for every row.  On B200 (7.3 TB/s reads, ~48 Q4_K weights/clk/SM) that
-// instruction stream is ~2x over the issue budget, so this kernel is organised differently:
-//
-//   * chunk-stationary warps: a row is cut into chunks of 16 super-blocks (4096 weights); warp w of a CTA
-//     owns chunk (w % NC) for the whole kernel, lane <-> one 128-weight half super-block.  The lane's slice of
-//     the activation vector therefore never changes: it is loaded ONCE into registers (3 int8 planes x 128
-//     elements = 96 registers) and the streaming loop touches shared memory only for weights;
-//   * weights: each warp owns a private ring of TMA bulk copies (cp.async.bulk + mbarrier): one stage =
-//     4 rows x 16 super-blocks (>= 2304 B per copy), filled by the warp's lane 0 and consumed by the same
-//     warp, so HBM requests stay in flight across row-group boundaries with no CTA barrier on the data path;
-//   * the NC warps that hold the chunks of one row-group meet once per row-group (a CTA barrier) and one of
-//     them adds the NC partial sums in a fixed order (deterministic) and applies the epilogue.  All 148 CTAs
-//     advance over the row-groups in lock-step rounds, so the tail is one row-group, not one warp-task;
-//   * activations: block-scaled 3-term int8 (kernels_internal.h "xq"); math: IDP.4A on the 4/5/6-bit codes
-//     (exact integer partial sums), one F32 scale per 16/32 weights, 6-bit scale unpack amortised over a
-//     128-weight half super-block per lane.
-// Up to 3 matrices of mixed K-quant formats share a launch (fused QKV of a Q4_K_M file; gate+up with SwiGLU).
-// No tensor cores: the path is HBM-bound (BASELINE.json north_star).
+// gemv_kquant_q.cu — the quarter-block variant of the dequant-fused GEMV (gemv_kquant.cu holds the design notes; the lane mapping
+// and why it exists are in gemv_kq_device_q.cuh): lane <-> 64 weights, warp <-> 8 super-blocks of a row, up to 16 warps per CTA.
+// Everything else — per-warp TMA rings, chunk-stationary activations in registers, lock-step rounds with the split tail, the
+// norm + quantiser prologue staged over the not-yet-primed ring stages, the epilogues incl. the tensor-parallel peer stores — is
+// the half-block kernel's, so the two can be compared launch for launch (NT_B200_GEMV_QB=0 selects the half-block kernel).
+// Replaces reference kernels K1-K5 (src/cuda/gemm.cu:32-470) behind launch_gemv (gemm.cu:748-805).
 #include "kernels_internal.h"
 #include "ring.cuh"
 #include "xquant.cuh"
-#include "gemv_kq_device.cuh"
+#include "gemv_kq_device_q.cuh"
 #include <cuda_fp16.h>
 #include <cstdlib>
 
@@ -32,8 +16,7 @@ namespace nt { namespace b200 {
 namespace {
 
 constexpr int MAX_MATS = 3;
-constexpr int MIN_WARPS = 4, MAX_WARPS = 12;
-
+constexpr int MIN_WARPS_Q = 4, MAX_WARPS_Q = 16;
 
 struct KqMat {
     const uint8_t* W;
@@ -66,11 +49,11 @@ struct KqParams {
 
 // MASK: bit f set <=> matrices of format f may appear in this launch (mixed Q4_K_M projections share one launch).
 template <int MASK, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_constant__ KqParams p) {
-    constexpr int SLOT = RG * BS * max_blk(MASK);
+__global__ void __launch_bounds__(WARPS * 32, 1) gemv_kqq_kernel(const __grid_constant__ KqParams p) {
+    constexpr int SLOT = RG * BSQ * max_blk(MASK);
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float red[32];
-    __shared__ float partial[2][MAX_WARPS][2][RG];      // [buffer][warp][segment][row]
+    __shared__ float partial[2][MAX_WARPS_Q][2][RG];      // [buffer][warp][segment][row]
     const int K = p.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stages = p.stages, NC = p.NC, NB = p.NB, n_seg = p.n_seg, gpc = p.gpc;
@@ -82,7 +65,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
 
     const int chunk = warp % NC, gsub = warp / NC;        // this warp's chunk of every row, and its row-group slot
     const int n_rounds = p.full_rounds + (p.tail_groups > 0 ? 1 : 0);
-    const int nbc = min(BS, NB - chunk * BS);              // super-blocks in this warp's chunk
+    const int nbc = min(BSQ, NB - chunk * BSQ);              // super-blocks in this warp's chunk
     // what this warp slot holds in `round`: row-group g (global), the first row's offset inside it and the number of rows
     auto slot_of = [&](int round, int& g, int& row_sub, int& nr) -> bool {
         if (round < p.full_rounds || p.tail_nr >= RG) {
@@ -123,13 +106,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
             mbar_expect_tx(bar, bytes * nr);
             uint8_t* dst = ring + (size_t)slot * STAGE_STRIDE;
             const int row0 = gl * RG + row_sub;
-            const uint8_t* src = m.W + (long long)chunk * (BS * blkb) + (long long)row0 * m.row_pitch;
+            const uint8_t* src = m.W + (long long)chunk * (BSQ * blkb) + (long long)row0 * m.row_pitch;
             if (nr == RG && row0 + RG <= m.out) {
 #pragma unroll
-                for (int r = 0; r < RG; r++) bulk_g2s(dst + r * (BS * blkb), src + r * m.row_pitch, bytes, bar);
+                for (int r = 0; r < RG; r++) bulk_g2s(dst + r * (BSQ * blkb), src + r * m.row_pitch, bytes, bar);
             } else {                                         // tail stage / ragged last group: re-read the last valid row
                 for (int r = 0; r < nr; r++)
-                    bulk_g2s(dst + r * (BS * blkb), src + (long long)min(r, m.out - 1 - row0) * m.row_pitch, bytes, bar);
+                    bulk_g2s(dst + r * (BSQ * blkb), src + (long long)min(r, m.out - 1 - row0) * m.row_pitch, bytes, bar);
             }
         }
         if (++p_seg == n_seg) { p_seg = 0; p_round++; }
@@ -150,9 +133,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     pdl_wait();   // no-op unless launched with programmatic stream serialization
 
     // ---- this lane's activation slice -> registers (once) ----
-    const int blk = lane >> 1, h = lane & 1;
-    const uint32_t hb = (uint32_t)((chunk * BS + min(blk, nbc - 1)) * 2 + h);   // global half-block index (clamped for idle lanes)
-    XRegs X;
+    const int blk = lane >> 2, qq = lane & 3;
+    const uint32_t qu = (uint32_t)((chunk * BSQ + min(blk, nbc - 1)) * 4 + qq);   // global quarter-block index (clamped for idle lanes)
+    constexpr bool Q6 = (MASK == 4);                       // Q6_K consumes its 64 elements as four strided 16-element groups
+    XRegsQ X;
     float rms_inv = 1.0f;
     if (p.x_f32) {
         // Fused prologue (the stateless launch_gemv path and the decode chain): F32 vector -> xq form in shared memory, one pass.
@@ -231,20 +215,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
             for (int i = 0; i < WARPS; i++) t += red[i];    // fixed order: the same value in every warp and CTA
             rms_inv = rsqrtf(t / K + p.eps);
         }
-        {
-            const uint32_t sw = (hb & 7u) << 4;
 #pragma unroll
-            for (int pl = 0; pl < 3; pl++)
+        for (int pc = 0; pc < 4; pc++) {
+            const uint32_t o = xq_swizzle(xq_piece_offset<Q6>(qu, pc));
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int4 v = *reinterpret_cast<const int4*>(xs + (size_t)pl * K + ((hb * 128u + 16u * i) ^ sw));
-                    X.x[pl][4 * i] = v.x; X.x[pl][4 * i + 1] = v.y; X.x[pl][4 * i + 2] = v.z; X.x[pl][4 * i + 3] = v.w;
-                }
+            for (int pl = 0; pl < 3; pl++) {
+                const int4 v = *reinterpret_cast<const int4*>(xs + (size_t)pl * K + o);
+                X.x[pl][4 * pc] = v.x; X.x[pl][4 * pc + 1] = v.y; X.x[pl][4 * pc + 2] = v.z; X.x[pl][4 * pc + 3] = v.w;
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) X.sx[j] = xscale[hb * 4 + j];
-#pragma unroll
-        for (int j = 0; j < 8; j++) X.s16[j] = xsum16[hb * 8 + j];
+        for (int j = 0; j < 4; j++) {
+            X.sx[j] = Q6 ? xscale[(qu >> 1) * 4 + j] : xscale[qu * 2 + (j & 1)];
+            X.s16[j] = Q6 ? xsum16[(qu >> 1) * 8 + 2 * j + (qu & 1)] : xsum16[qu * 4 + j];
+        }
         if (p.x_alias) {
             __syncthreads();                                 // every lane holds its slice: the staging area becomes ring again
             if (lane == 0) {
@@ -255,21 +239,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     } else {
         // pre-quantised xq in global memory (planes stored with the 16-byte-column swizzle of xquant.cuh)
         const int8_t* xq = p.xq;
-        const uint32_t sw = (hb & 7u) << 4;
 #pragma unroll
-        for (int pl = 0; pl < 3; pl++)
+        for (int pc = 0; pc < 4; pc++) {
+            const uint32_t o = xq_swizzle(xq_piece_offset<Q6>(qu, pc));
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int4 v = __ldg(reinterpret_cast<const int4*>(xq + (size_t)pl * K + ((hb * 128u + 16u * i) ^ sw)));
-                X.x[pl][4 * i] = v.x; X.x[pl][4 * i + 1] = v.y; X.x[pl][4 * i + 2] = v.z; X.x[pl][4 * i + 3] = v.w;
+            for (int pl = 0; pl < 3; pl++) {
+                const int4 v = __ldg(reinterpret_cast<const int4*>(xq + (size_t)pl * K + o));
+                X.x[pl][4 * pc] = v.x; X.x[pl][4 * pc + 1] = v.y; X.x[pl][4 * pc + 2] = v.z; X.x[pl][4 * pc + 3] = v.w;
             }
+        }
         const float* fs = reinterpret_cast<const float*>(xq + 3 * (size_t)K);
-        const float4 sv = __ldg(reinterpret_cast<const float4*>(fs + hb * 4));
-        X.sx[0] = sv.x; X.sx[1] = sv.y; X.sx[2] = sv.z; X.sx[3] = sv.w;
-        const float4 u0 = __ldg(reinterpret_cast<const float4*>(fs + K / 32 + hb * 8));
-        const float4 u1 = __ldg(reinterpret_cast<const float4*>(fs + K / 32 + hb * 8 + 4));
-        X.s16[0] = u0.x; X.s16[1] = u0.y; X.s16[2] = u0.z; X.s16[3] = u0.w;
-        X.s16[4] = u1.x; X.s16[5] = u1.y; X.s16[6] = u1.z; X.s16[7] = u1.w;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            X.sx[j] = Q6 ? __ldg(fs + (qu >> 1) * 4 + j) : __ldg(fs + qu * 2 + (j & 1));
+            X.s16[j] = Q6 ? __ldg(fs + K / 32 + (qu >> 1) * 8 + 2 * j + (qu & 1)) : __ldg(fs + K / 32 + qu * 4 + j);
+        }
     }
     unsigned peer_seq = 0, peer_parity = 0;
     if (p.epilogue == GEMV_PEER) { peer_seq = __ldcg(p.peer.seq) + 1u; peer_parity = peer_seq & 1u; }
@@ -290,22 +274,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
                 const uint8_t* slot_base = ring + (size_t)slot * STAGE_STRIDE;
                 const int fmt = (MASK == 1) ? 0 : (MASK == 2) ? 1 : (MASK == 4) ? 2 : (MASK == 8) ? 3 : (MASK == 16) ? 4 : p.mat[mi].fmt;
                 if (nr == RG) {
-                    if ((MASK & 1) && fmt == 0) process_stage<0>(slot_base, blk, h, X, acc);
-                    if ((MASK & 2) && fmt == 1) process_stage<1>(slot_base, blk, h, X, acc);
-                    if ((MASK & 4) && fmt == 2) process_stage<2>(slot_base, blk, h, X, acc);
-                    if ((MASK & 8) && fmt == 3) process_stage<3>(slot_base, blk, h, X, acc);
-                    if ((MASK & 16) && fmt == 4) process_stage<4>(slot_base, blk, h, X, acc);
+                    if ((MASK & 1) && fmt == 0) process_stage_q<0>(slot_base, blk, qq, X, acc);
+                    if ((MASK & 2) && fmt == 1) process_stage_q<1>(slot_base, blk, qq, X, acc);
+                    if ((MASK & 4) && fmt == 2) process_stage_q<2>(slot_base, blk, qq, X, acc);
+                    if ((MASK & 8) && fmt == 3) process_stage_q<3>(slot_base, blk, qq, X, acc);
+                    if ((MASK & 16) && fmt == 4) process_stage_q<4>(slot_base, blk, qq, X, acc);
                 } else {                                     // tail stage of 1 or 2 rows: one row at a time
-                    const int rowp = BS * ((fmt == 0 || fmt == 4) ? 144 : fmt == 1 ? 176 : fmt == 2 ? 210 : 272);
+                    const int rowp = BSQ * ((fmt == 0 || fmt == 4) ? 144 : fmt == 1 ? 176 : fmt == 2 ? 210 : 272);
 #pragma unroll 1
                     for (int r = 0; r < nr; r++) {
                         float a1[RG] = {0.f, 0.f, 0.f, 0.f};
                         const uint8_t* rb = slot_base + r * rowp;
-                        if ((MASK & 1) && fmt == 0) process_stage<0, 1>(rb, blk, h, X, a1);
-                        if ((MASK & 2) && fmt == 1) process_stage<1, 1>(rb, blk, h, X, a1);
-                        if ((MASK & 4) && fmt == 2) process_stage<2, 1>(rb, blk, h, X, a1);
-                        if ((MASK & 8) && fmt == 3) process_stage<3, 1>(rb, blk, h, X, a1);
-                        if ((MASK & 16) && fmt == 4) process_stage<4, 1>(rb, blk, h, X, a1);
+                        if ((MASK & 1) && fmt == 0) process_stage_q<0, 1>(rb, blk, qq, X, a1);
+                        if ((MASK & 2) && fmt == 1) process_stage_q<1, 1>(rb, blk, qq, X, a1);
+                        if ((MASK & 4) && fmt == 2) process_stage_q<2, 1>(rb, blk, qq, X, a1);
+                        if ((MASK & 8) && fmt == 3) process_stage_q<3, 1>(rb, blk, qq, X, a1);
+                        if ((MASK & 16) && fmt == 4) process_stage_q<4, 1>(rb, blk, qq, X, a1);
                         acc[0] = (r == 0) ? a1[0] : acc[0];       // no dynamic indexing: acc stays in registers
                         acc[1] = (r == 1) ? a1[0] : acc[1];
                     }
@@ -357,76 +341,48 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_con
     }
 }
 
-// Q4_0 (reference K1, gemm.cu:32-86) runs on this path by default since its first hardware run (round 2: tests/test_q4_0_tma_gpu.py
-// against the oracle, <= 2e-5); NT_B200_Q4_0_TMA=0 sends it back to the generic kernel (gemv_generic.cu) for A/B comparisons.
-bool q4_0_tma_enabled() {
-    static const bool on = [] { const char* e = getenv("NT_B200_Q4_0_TMA"); return !(e && e[0] == '0' && e[1] == 0); }();
-    return on;
-}
-int fmt_of(DType dt) {
-    return dt == DType::Q4_K_M ? 0 : dt == DType::Q5_K ? 1 : dt == DType::Q6_K ? 2 : dt == DType::Q8_0 ? 3
-         : (dt == DType::Q4_0 && q4_0_tma_enabled()) ? 4 : -1;
+
+int fmt_of_q(DType dt) {
+    return dt == DType::Q4_K_M ? 0 : dt == DType::Q5_K ? 1 : dt == DType::Q6_K ? 2 : dt == DType::Q8_0 ? 3 : dt == DType::Q4_0 ? 4 : -1;
 }
 
-int g_num_sms = 0;
-int num_sms() {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return g_num_sms;
+int num_sms_q() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+    return n;
 }
 
-constexpr size_t SMEM_CAP = 227 * 1024 - 1024;    // static __shared__ (red, partial) counts against the cap
-
-bool quarter_enabled() {          // NT_B200_GEMV_QB=1: opt-in (measured slower than the half-block kernel, see below)
-    static const bool on = [] { const char* e = getenv("NT_B200_GEMV_QB"); return e && *e && !(e[0] == '0' && e[1] == 0); }();
-    return on;
-}
-
-bool quarter_split_enabled() {    // NT_B200_GEMV_QB_SPLIT=0: launches that mix Q6_K with Q4_K/Q5_K stay one half-block launch
-    static const bool on = [] { const char* e = getenv("NT_B200_GEMV_QB_SPLIT"); return !(e && e[0] == '0' && e[1] == 0); }();
-    return on;
-}
-
-bool tail_split_enabled() {       // NT_B200_TAIL_SPLIT=0 keeps whole 4-row stages in the last round (A/B aid)
-    static const bool on = [] { const char* e = getenv("NT_B200_TAIL_SPLIT"); return !(e && e[0] == '0' && e[1] == 0); }();
-    return on;
-}
+constexpr size_t SMEM_CAP_Q = 227 * 1024 - 2048;    // static __shared__ (red 128 B + partial 1 KB at 16 warps) counts against the 227 KB cap
 
 template <int MASK, int WARPS>
-void launch_kq(const KqParams& p, size_t smem, cudaStream_t s) {
+void launch_kqq(const KqParams& p, size_t smem, cudaStream_t s) {
     static unsigned long long configured = 0;      // bit per device id
-    opt_in_dynamic_smem(gemv_kq_kernel<MASK, WARPS>, (int)((int)SMEM_CAP), configured);
-    int grid = num_sms();
+    opt_in_dynamic_smem(gemv_kqq_kernel<MASK, WARPS>, (int)SMEM_CAP_Q, configured);
+    int grid = num_sms_q();
     KqParams q = p;
     const int slots = grid * q.gpc;
     q.full_rounds = q.total_groups / slots;
     q.tail_groups = q.total_groups % slots;
     q.tail_nr = RG;
-    if (q.tail_groups > 0 && tail_split_enabled()) {          // also when the whole launch is less than one round (narrow shards)
+    if (q.tail_groups > 0) {
         if (4 * q.tail_groups <= slots) q.tail_nr = 1;
         else if (2 * q.tail_groups <= slots) q.tail_nr = 2;
     }
-    if (q.full_rounds == 0) {                                  // fewer units than warp slots: no more CTAs than there is work
+    if (q.full_rounds == 0) {
         const int units = q.tail_groups * (RG / q.tail_nr);
         const int need = (units + q.gpc - 1) / q.gpc;
         if (need < grid) grid = need;
     }
-    launch_k(gemv_kq_kernel<MASK, WARPS>, dim3(grid), dim3(WARPS * 32), smem, s, q);
+    launch_k(gemv_kqq_kernel<MASK, WARPS>, dim3(grid), dim3(WARPS * 32), smem, s, q);
     count_launch();
 }
 
-// Warps per CTA: the largest multiple of NC (chunks per row) in [MIN_WARPS, MAX_WARPS] that affords `min_stages` ring
-// stages.  Measured on the 70B shapes (profiles/r01_gemv_width_scan.txt): 12 warps beat 8 and 10 on the fused gate+up
-// GEMV (55.6 vs 59.8 us) even though the last round is less full, so occupancy wins over tail balance.
-int pick_warps(int NC, int total_groups, size_t slot, size_t budget, int min_stages) {
-    (void)total_groups;
+// Warps per CTA: the largest multiple of NC (chunks per row) up to MAX_WARPS_Q that affords `min_stages` ring stages.
+int pick_warps_q(int NC, size_t slot, size_t budget, int min_stages) {
     const char* force = getenv("NT_B200_GEMV_WARPS");               // tuning aid
     int best = 0;
-    for (int w = NC; w <= MAX_WARPS; w += NC) {
-        if (w < MIN_WARPS) continue;
+    for (int w = NC; w <= MAX_WARPS_Q; w += NC) {
+        if (w < MIN_WARPS_Q) continue;
         if ((size_t)w * min_stages * (slot + 8) > budget) break;
         if (force && atoi(force) == w) return w;
         best = w;
@@ -435,16 +391,14 @@ int pick_warps(int NC, int total_groups, size_t slot, size_t budget, int min_sta
 }
 
 template <int MASK>
-void launch_fmt(KqParams& p, cudaStream_t s) {
-    constexpr int SLOT = RG * BS * max_blk(MASK);
+bool launch_fmt_q(KqParams& p, cudaStream_t s) {
+    constexpr int SLOT = RG * BSQ * max_blk(MASK);
     const size_t xq_sz = p.x_f32 ? (((size_t)3 * p.K + (size_t)(p.K / 32) * 4 + (size_t)(p.K / 16) * 4 + 127) & ~(size_t)127) + 128 : 0;
-    // F32 input: first try to stage x over ring stages >= 1 (full ring depth and CTA width, the ring is primed in two steps);
-    // vectors too long for that get their own area behind a smaller ring.
     int w = 0, stages = 0;
     p.x_alias = 0;
     if (p.x_f32) {
-        const size_t budget = SMEM_CAP - 256;
-        w = pick_warps(p.NC, p.total_groups, SLOT, budget, 2);
+        const size_t budget = SMEM_CAP_Q - 256;
+        w = pick_warps_q(p.NC, SLOT, budget, 2);
         if (w) {
             stages = (int)(budget / ((size_t)w * (SLOT + 8)));
             if (stages > 4) stages = 4;
@@ -452,10 +406,11 @@ void launch_fmt(KqParams& p, cudaStream_t s) {
         }
     }
     if (!w) {
-        const size_t budget = SMEM_CAP - xq_sz - 256;
-        w = pick_warps(p.NC, p.total_groups, SLOT, budget, 2);
-        if (!w) w = pick_warps(p.NC, p.total_groups, SLOT, budget, 1);   // long rows with in-kernel quantisation: single-stage ring
-        NT_CHECK(w != 0, "gemv_kq: shared memory budget exceeded");
+        if (xq_sz + 256 >= SMEM_CAP_Q) return false;
+        const size_t budget = SMEM_CAP_Q - xq_sz - 256;
+        w = pick_warps_q(p.NC, SLOT, budget, 2);
+        if (!w) w = pick_warps_q(p.NC, SLOT, budget, 1);
+        if (!w) return false;
         stages = (int)(budget / ((size_t)w * (SLOT + 8)));
         if (stages > 4) stages = 4;
     }
@@ -463,86 +418,39 @@ void launch_fmt(KqParams& p, cudaStream_t s) {
     p.stages = stages;
     const size_t smem = (size_t)w * stages * (SLOT + 8) + 128 + (p.x_alias ? 0 : xq_sz);
     switch (w) {
-        case 12: launch_kq<MASK, 12>(p, smem, s); break;
-        case 11: launch_kq<MASK, 11>(p, smem, s); break;
-        case 10: launch_kq<MASK, 10>(p, smem, s); break;
-        case 9: launch_kq<MASK, 9>(p, smem, s); break;
-        case 8: launch_kq<MASK, 8>(p, smem, s); break;
-        case 7: launch_kq<MASK, 7>(p, smem, s); break;
-        case 6: launch_kq<MASK, 6>(p, smem, s); break;
-        case 5: launch_kq<MASK, 5>(p, smem, s); break;
-        default: launch_kq<MASK, 4>(p, smem, s); break;
-    }
-}
-
-}  // namespace
-
-bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K) {
-    if (n_mat < 1 || n_mat > MAX_MATS || K % 256 != 0 || K <= 0) return false;
-    const int NB = K / 256, NC = (NB + BS - 1) / BS;
-    if (NC > MAX_WARPS) return false;              // one warp per chunk of a row (K <= 49152)
-    for (int i = 0; i < n_mat; i++) {
-        const int f = fmt_of(mats[i].dtype);
-        if (f < 0 || mats[i].out <= 0) return false;
-        const size_t pitch = mats[i].row_pitch ? mats[i].row_pitch : dtype_row_size(mats[i].dtype, K);
-        if ((reinterpret_cast<uintptr_t>(mats[i].W) & 15) || (pitch & 15)) return false;
-        // the last chunk of a row is copied in 16-byte units and must stay inside the row pitch
-        const size_t blk = dtype_row_size(mats[i].dtype, 256);     // bytes per 256 weights
-        const int last = NB - (NC - 1) * BS;
-        const size_t tail_end = (size_t)(NC - 1) * BS * blk + ((last * blk + 15) & ~(size_t)15);
-        if (tail_end > pitch) return false;
+        case 16: launch_kqq<MASK, 16>(p, smem, s); break;
+        case 15: launch_kqq<MASK, 15>(p, smem, s); break;
+        case 14: launch_kqq<MASK, 14>(p, smem, s); break;
+        case 13: launch_kqq<MASK, 13>(p, smem, s); break;
+        case 12: launch_kqq<MASK, 12>(p, smem, s); break;
+        case 11: launch_kqq<MASK, 11>(p, smem, s); break;
+        case 10: launch_kqq<MASK, 10>(p, smem, s); break;
+        case 9: launch_kqq<MASK, 9>(p, smem, s); break;
+        case 8: launch_kqq<MASK, 8>(p, smem, s); break;
+        case 7: launch_kqq<MASK, 7>(p, smem, s); break;
+        case 6: launch_kqq<MASK, 6>(p, smem, s); break;
+        case 5: launch_kqq<MASK, 5>(p, smem, s); break;
+        default: launch_kqq<MASK, 4>(p, smem, s); break;
     }
     return true;
 }
 
-namespace { const PeerOut* g_peer = nullptr; }      // set around the GEMV_PEER launch by gemv_kq_peer (single host thread, like the reference)
+}  // namespace
 
-void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpilogue ep, cudaStream_t s) {
-    NT_CHECK(gemv_kq_supported(mats, n_mat, K), "gemv_kq: unsupported shape/dtype/alignment");
-    NT_CHECK(ep != GEMV_PEER || (g_peer && n_mat == 1), "gemv_kq: GEMV_PEER goes through gemv_kq_peer");
-    // Opt-in A/B (NT_B200_GEMV_QB=1): the quarter-block kernel (gemv_kquant_q.cu: 16 warps per SM, 14 on the 28672-wide down
-    // projection); launches that mix Q6_K with another format are split per matrix for it.  Measured on the 70B shapes
-    // (profiles/r02_qb_layer_ncu_summary.txt): correct (all kernel / model tests) but slower — gate+up 62.0 us vs 53.2, Q6_K down
-    // 49.8 vs 45.0, step 84.0 vs 86.3 tok/s on the same box: the per-lane header / scale work is paid per 64 instead of per 128
-    // weights (+25 % instructions), which more than eats the fourth warp per scheduler.  The half-block kernel stays the default.
-    if (quarter_enabled()) {
-        int mask = 0;
-        for (int i = 0; i < n_mat; i++) mask |= 1 << fmt_of(mats[i].dtype);
-        const bool one_family = mask == 1 || mask == 2 || mask == 3 || mask == 4 || mask == 8 || mask == 16;
-        if (one_family) {
-            if (gemv_kq_quarter(mats, n_mat, K, in, ep, g_peer, s)) return;
-        } else if (ep != GEMV_SWIGLU && ep != GEMV_PEER && quarter_split_enabled()) {
-            // q/k (Q4_K) + v (Q6_K) of a Q4_K_M file: the Q4_K/Q5_K matrices in one launch, each Q6_K matrix in its own
-            GemvMat fam[MAX_MATS];
-            int nf = 0;
-            for (int i = 0; i < n_mat; i++) if (mats[i].dtype != DType::Q6_K) fam[nf++] = mats[i];
-            int fmask = 0;
-            for (int i = 0; i < nf; i++) fmask |= 1 << fmt_of(fam[i].dtype);
-            if (nf > 0 && (fmask == 1 || fmask == 2 || fmask == 3)) {
-                bool ok = gemv_kq_quarter(fam, nf, K, in, ep, nullptr, s);
-                for (int i = 0; i < n_mat && ok; i++)
-                    if (mats[i].dtype == DType::Q6_K) ok = gemv_kq_quarter(&mats[i], 1, K, in, ep, nullptr, s);
-                NT_CHECK(ok, "gemv_kq: the quarter-block kernel took part of a split launch only");
-                return;
-            }
-        }
-    }
-    NT_CHECK((in.xq != nullptr) != (in.x != nullptr), "gemv_kq: exactly one of xq / x must be given");
-    if (ep == GEMV_SWIGLU)
-        NT_CHECK(n_mat == 2 && mats[0].out == mats[1].out, "gemv_kq: SWIGLU needs gate and up of equal rows");
-    int mask = 0;
-    for (int i = 0; i < n_mat; i++) mask |= 1 << fmt_of(mats[i].dtype);
-    const bool plain = mask == 1 || mask == 2 || mask == 4 || mask == 8 || mask == 3 || mask == 5 || mask == 16;
-    if (!plain && ep != GEMV_SWIGLU) {                         // rare mixes: one launch per matrix
-        for (int i = 0; i < n_mat; i++) gemv_kq(&mats[i], 1, K, in, ep, s);
-        return;
-    }
-    NT_CHECK(plain, "gemv_kq: SWIGLU over this format mix is not instantiated");
+// Launches over one format family (Q4_K and Q5_K may mix; Q6_K's activation slice is laid out differently, so launches that mix
+// it with another format are split by the caller, gemv_kquant.cu).  Returns false when the shape does not fit (the caller then
+// uses the half-block kernel): K % 256 != 0, more than 16 chunks of 2048 weights per row, or shared memory.
+bool gemv_kq_quarter(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpilogue ep, const PeerOut* peer, cudaStream_t s) {
+    if (n_mat < 1 || n_mat > MAX_MATS || K % 256 != 0 || K <= 0) return false;
     KqParams p{};
-    p.K = K; p.NB = K / 256; p.NC = (p.NB + BS - 1) / BS;
+    p.K = K; p.NB = K / 256; p.NC = (p.NB + BSQ - 1) / BSQ;
+    if (p.NC > MAX_WARPS_Q) return false;
+    int mask = 0;
+    for (int i = 0; i < n_mat; i++) { const int f = fmt_of_q(mats[i].dtype); if (f < 0) return false; mask |= 1 << f; }
+    if (!(mask == 1 || mask == 2 || mask == 3 || mask == 4 || mask == 8 || mask == 16)) return false;
     p.xq = static_cast<const int8_t*>(in.xq);
     p.x_f32 = in.x; p.norm_w = in.norm_w; p.eps = in.eps;
-    if (ep == GEMV_PEER) p.peer = *g_peer;
+    if (ep == GEMV_PEER) { if (!peer) return false; p.peer = *peer; }
     p.epilogue = (int)ep;
     p.n_mat = n_mat;
     int total = 0;
@@ -552,34 +460,25 @@ void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpi
         m.y = mats[i].y;
         m.out = mats[i].out;
         m.groups = (mats[i].out + RG - 1) / RG;
-        m.fmt = fmt_of(mats[i].dtype);
+        m.fmt = fmt_of_q(mats[i].dtype);
         m.row_pitch = (long long)(mats[i].row_pitch ? mats[i].row_pitch : dtype_row_size(mats[i].dtype, K));
+        // the last chunk of a row is copied in 16-byte units and must stay inside the row pitch
+        const size_t blk = dtype_row_size(mats[i].dtype, 256);
+        const int last = p.NB - (p.NC - 1) * BSQ;
+        if ((size_t)(p.NC - 1) * BSQ * blk + ((last * blk + 15) & ~(size_t)15) > (size_t)m.row_pitch) return false;
+        if ((reinterpret_cast<uintptr_t>(m.W) & 15) || (m.row_pitch & 15)) return false;
         total += m.groups;
     }
     if (ep == GEMV_SWIGLU) { p.n_seg = 2; p.total_groups = p.mat[0].groups; }
     else { p.n_seg = 1; p.total_groups = total; }
     switch (mask) {
-        case 1: launch_fmt<1>(p, s); break;
-        case 2: launch_fmt<2>(p, s); break;
-        case 4: launch_fmt<4>(p, s); break;
-        case 3: launch_fmt<3>(p, s); break;
-        case 8: launch_fmt<8>(p, s); break;
-        case 16: launch_fmt<16>(p, s); break;
-        default: launch_fmt<5>(p, s); break;
+        case 1: return launch_fmt_q<1>(p, s);
+        case 2: return launch_fmt_q<2>(p, s);
+        case 3: return launch_fmt_q<3>(p, s);
+        case 4: return launch_fmt_q<4>(p, s);
+        case 8: return launch_fmt_q<8>(p, s);
+        default: return launch_fmt_q<16>(p, s);
     }
-}
-
-void gemv_kq_peer(const GemvMat& mat, int K, const GemvInput& in, const PeerOut& peer, cudaStream_t s) {
-    NT_CHECK(mat.out == peer.hidden && peer.size >= 2 && peer.size <= PeerOut::kMaxTP, "gemv_kq_peer: rows must equal the exchanged vector length");
-    g_peer = &peer;
-    gemv_kq(&mat, 1, K, in, GEMV_PEER, s);
-    g_peer = nullptr;
-}
-
-void gemv_kq(const GemvMat* mats, int n_mat, int K, const void* xq, GemvEpilogue ep, cudaStream_t s) {
-    GemvInput in;
-    in.xq = xq;
-    gemv_kq(mats, n_mat, K, in, ep, s);
 }
 
 }}  // namespace nt::b200

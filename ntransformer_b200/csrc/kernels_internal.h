@@ -59,6 +59,8 @@ struct GemvInput {
 bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K);
 void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpilogue ep, cudaStream_t s);
 void gemv_kq(const GemvMat* mats, int n_mat, int K, const void* xq, GemvEpilogue ep, cudaStream_t s);
+// gemv_kquant_q.cu: the quarter-block kernel (lane <-> 64 weights, up to 16 warps); false = shape not covered, nothing launched
+bool gemv_kq_quarter(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpilogue ep, const PeerOut* peer, cudaStream_t s);
 // epilogue GEMV_PEER: one matrix, rows == peer.hidden
 void gemv_kq_peer(const GemvMat& mat, int K, const GemvInput& in, const PeerOut& peer, cudaStream_t s);
 

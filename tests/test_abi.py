@@ -86,3 +86,17 @@ def test_product_never_touches_the_oracle():
         assert "nt_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
     out = subprocess.run(["ldd", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_quarter_block_gemv_and_peer_exchange_sass():
+    """gemv_kqq_kernel (csrc/gemv_kquant_q.cu): TMA bulk copies + dp4a, the tensor-parallel epilogue's 64-bit system-scope stores
+    {sequence : value} straight into peer memory, no tensor-core ops; xchg_reduce_kernel polls the same words with 64-bit
+    system-scope loads (csrc/engine/peer_xchg.cu)."""
+    b = ROOT / "ntransformer_b200" / "_build"
+    q = subprocess.run(["cuobjdump", "-sass", str(b / "gemv_kquant_q.cu.o")], capture_output=True, text=True, check=True).stdout
+    for mnemonic in ("UBLKCP", "IDP.4A", "SYNCS.ARRIVE.TRANS64", "STG.E.64.STRONG.SYS"):
+        assert mnemonic in q, f"{mnemonic} missing from the quarter-block GEMV"
+    for forbidden in ("HMMA", "UTCHMMA", "IMMA"):
+        assert forbidden not in q, forbidden
+    x = subprocess.run(["cuobjdump", "-sass", str(b / "engine__peer_xchg.cu.o")], capture_output=True, text=True, check=True).stdout
+    assert "LDG.E.64.STRONG.SYS" in x
