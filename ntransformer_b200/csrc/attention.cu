@@ -15,6 +15,7 @@
 #include "ring.cuh"
 #include "xquant.cuh"
 #include <cuda_fp16.h>
+#include <algorithm>
 #include <cfloat>
 #include <mutex>
 
@@ -24,6 +25,10 @@ namespace {
 
 constexpr int AW = 8;                    // warps per CTA
 constexpr int MAX_SPLITS = 64;
+// Graph-replayed decode (launch shape fixed by max_seq): a context slice holds at least this many keys.  Without the floor a short
+// context is cut into one-key slices (ctx 64 over 64 slices when a rank holds a single KV head) and the merge walks them all:
+// decode_combine took 13.9 us at tensor-parallel-8 shapes and 5.4 us at one GPU (profiles/r02_launches_tp8_shard.txt).
+constexpr int DYN_MIN_SPLIT = 32;
 constexpr int FUSED_MIN_SPLIT = 64;      // decode_fused_kernel: at least this many keys per context slice (one slice = no merge step)
 constexpr int KU = 8;                    // cache rows a warp keeps in flight in the score and P.V loops
 constexpr int ATTN_MAX_DYN_SMEM = 227 * 1024 - 1024;   // static __shared__ (s_max/s_sum) counts against the 227 KB cap
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(AW * 32) decode_kernel(float* __restrict__ out
     pdl_wait();
     if (pos_dev) {                       // CUDA-graph replay: context length lives in device memory
         seq_len = *pos_dev + 1;
-        split_len = (seq_len + n_splits - 1) / n_splits;
+        split_len = max((seq_len + n_splits - 1) / n_splits, DYN_MIN_SPLIT);
     }
     const int head0 = blockIdx.x * GC, split = blockIdx.y;
     const int kv_head = head0 / (n_heads / n_kv);
@@ -306,20 +311,45 @@ __global__ void __launch_bounds__(AW * 32) decode_kernel(float* __restrict__ out
 __global__ void decode_combine_kernel(float* __restrict__ out, const float* __restrict__ scratch, int n_heads, int hd,
                                       int n_splits, int seq_len, int split_len, const int* __restrict__ pos_dev,
                                       int8_t* __restrict__ xq_out) {
+    __shared__ float w_s[MAX_SPLITS];                // e^{m_i - m} per slice
+    __shared__ float inv_s;
     const int h = blockIdx.x;
     pdl_launch_dependents();
     pdl_wait();
-    if (pos_dev) { seq_len = *pos_dev + 1; split_len = (seq_len + n_splits - 1) / n_splits; }
+    if (pos_dev) { seq_len = *pos_dev + 1; split_len = max((seq_len + n_splits - 1) / n_splits, DYN_MIN_SPLIT); }
     const float* ml = scratch + (size_t)n_heads * n_splits * hd + (size_t)h * n_splits * 2;
     const int used = (seq_len + split_len - 1) / split_len;
-    float m = -FLT_MAX;
-    for (int i = 0; i < used; i++) m = fmaxf(m, ml[2 * i]);
-    float l = 0.f;
-    for (int i = 0; i < used; i++) l += ml[2 * i + 1] * expf(ml[2 * i] - m);
-    const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+    // the slices' (max, sum) pairs: one lane per slice (two when there are more than 32), one memory round trip, warp reductions
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int i0 = lane, i1 = lane + 32;
+        const float m0 = (i0 < used) ? ml[2 * i0] : -FLT_MAX, l0 = (i0 < used) ? ml[2 * i0 + 1] : 0.f;
+        const float m1 = (i1 < used) ? ml[2 * i1] : -FLT_MAX, l1 = (i1 < used) ? ml[2 * i1 + 1] : 0.f;
+        float m = fmaxf(m0, m1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        const float w0 = (i0 < used) ? expf(m0 - m) : 0.f, w1 = (i1 < used) ? expf(m1 - m) : 0.f;
+        float l = l0 * w0 + l1 * w1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xFFFFFFFFu, l, o);
+        if (i0 < MAX_SPLITS) w_s[i0] = w0;
+        if (i1 < MAX_SPLITS) w_s[i1] = w1;
+        if (lane == 0) inv_s = (l > 0.f) ? 1.0f / l : 0.f;
+    }
+    __syncthreads();
+    const float inv = inv_s;
     for (int d = threadIdx.x; d < hd; d += blockDim.x) {       // hd % 32 == 0: whole warps stay together
+        const float* sp = scratch + (size_t)h * n_splits * hd + d;
         float o = 0.f;
-        for (int i = 0; i < used; i++) o += scratch[((size_t)h * n_splits + i) * hd + d] * expf(ml[2 * i] - m);
+        int i = 0;
+        for (; i + 8 <= used; i += 8) {                        // 8 independent loads in flight
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) t[j] = sp[(size_t)(i + j) * hd];
+#pragma unroll
+            for (int j = 0; j < 8; j++) o = fmaf(t[j], w_s[i + j], o);
+        }
+        for (; i < used; i++) o = fmaf(sp[(size_t)i * hd], w_s[i], o);
         const float v = o * inv;
         out[(size_t)h * hd + d] = v;
         if (xq_out) {
@@ -494,7 +524,7 @@ void launch_decode_dyn(float* out, const float* q, const __half* kc, const __hal
                        int n_heads, int n_kv, float scale, float* scratch, int n_splits, int8_t* xq_out, cudaStream_t s) {
     constexpr int HD = DPL * 32;
     const int groups = n_heads / GC;
-    const int max_split_len = (max_seq + n_splits - 1) / n_splits;
+    const int max_split_len = std::max((max_seq + n_splits - 1) / n_splits, DYN_MIN_SPLIT);
     size_t smem = ((size_t)GC * max_split_len + (size_t)AW * GC * HD + (size_t)GC * HD + 2 * GC) * sizeof(float);
     NT_CHECK(smem <= (size_t)ATTN_MAX_DYN_SMEM, "attention_decode_dyn: context slice does not fit shared memory");
     static unsigned long long configured = 0;      // bit per device id

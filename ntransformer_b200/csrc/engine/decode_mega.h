@@ -42,6 +42,7 @@ constexpr int MEGA_MAX_STAGES = 4;          // TMA ring depth per warp
 constexpr int MEGA_MAX_TP = 8;
 constexpr int MEGA_ATTN_WARPS = 8;          // warps that work in the attention phase (attention.cu AW)
 constexpr int MEGA_SYNC_WORDS = 4 * 32;     // counter, go, abort, exchange sequence: one 128-byte line each
+constexpr int MEGA_COMPAT_MIN_SPLIT = 32;   // compat split rule: keys per context slice at least as in the graph path (attention.cu DYN_MIN_SPLIT)
 constexpr int MEGA_TRACE_CTAS = 4;          // CTAs that record the phase timeline when tracing is on
 
 enum MegaPhaseKind : int { MPH_NORM_XQ = 0, MPH_QUANT = 1, MPH_GEMV = 2, MPH_ATTN = 3, MPH_COMBINE = 4, MPH_REDUCE_XQ = 5 };

@@ -80,7 +80,7 @@ bool mega_make_plan(const MegaModelView& mv, const MegaBuffers& B, int grid, int
     const size_t fixed = ((size_t)AW * gc * mv.hd + (size_t)gc * mv.hd) * sizeof(float) + 2 * (size_t)mv.hd * sizeof(__half);
     int max_split = (int)std::min<size_t>(2048, (MEGA_DYN_SMEM - fixed) / ((size_t)gc * sizeof(float)));
     if (split_fixed > 0) {
-        const int need = (mv.max_seq + split_fixed - 1) / split_fixed;
+        const int need = std::max((mv.max_seq + split_fixed - 1) / split_fixed, MEGA_COMPAT_MIN_SPLIT);
         if (need > max_split) return fail("split_fixed: context slice does not fit shared memory");
         pl.n_splits_max = split_fixed;
     } else {

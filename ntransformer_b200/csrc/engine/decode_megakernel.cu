@@ -496,7 +496,7 @@ struct SplitRule { int split_len, used; };
 __device__ __forceinline__ SplitRule split_rule(const MegaParams& P, int ctx, int n_groups) {
     SplitRule r;
     if (P.split_fixed > 0) {
-        r.split_len = (ctx + P.split_fixed - 1) / P.split_fixed;
+        r.split_len = max((ctx + P.split_fixed - 1) / P.split_fixed, MEGA_COMPAT_MIN_SPLIT);   // the graph path's rule (attention.cu DYN_MIN_SPLIT)
     } else {
         const int cap = max(1, (int)gridDim.x / n_groups);
         r.split_len = max(P.min_split, (ctx + cap - 1) / cap);

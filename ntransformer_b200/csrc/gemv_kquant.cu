@@ -66,7 +66,7 @@ struct KqParams {
 
 // MASK: bit f set <=> matrices of format f may appear in this launch (mixed Q4_K_M projections share one launch).
 template <int MASK, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) gemv_kq_kernel(const __grid_constant__ KqParams p) {
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 6 ? 2 : 1) gemv_kq_kernel(const __grid_constant__ KqParams p) {   // <= 6 warps: two CTAs may share an SM
     constexpr int SLOT = RG * BS * max_blk(MASK);
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float red[32];
@@ -459,6 +459,8 @@ void launch_fmt(KqParams& p, cudaStream_t s) {
         stages = (int)(budget / ((size_t)w * (SLOT + 8)));
         if (stages > 4) stages = 4;
     }
+    static const int stage_cap = [] { const char* e = getenv("NT_B200_GEMV_STAGES"); return e ? atoi(e) : 0; }();   // tuning aid: ring depth cap
+    if (stage_cap >= 2 && stages > stage_cap && (!p.x_alias || ((size_t)w * (stage_cap - 1) * SLOT >= xq_sz))) stages = stage_cap;
     p.gpc = w / p.NC;
     p.stages = stages;
     const size_t smem = (size_t)w * stages * (SLOT + 8) + 128 + (p.x_alias ? 0 : xq_sz);

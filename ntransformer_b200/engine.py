@@ -6,6 +6,7 @@ of the NCCL id under tensor parallelism)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -70,8 +71,10 @@ class Model:
             else:
                 t = random_blocks_cuda(dt, max(rows, 1), cols, s, device=device)
             t = t.contiguous()
-            if tp_size > 1 and split_kind(name) == "cols" and t.shape[1] % 16:
-                # column shards: pad the row pitch to 16 B so rows stay TMA-aligned (what the GGUF loader does too)
+            pad_all = os.environ.get("NT_B200_SYNTH_PAD") == "1" and name != "token_embd.weight"      # tools/prof_decode.py --shard-of
+            if t.dim() == 2 and t.dtype == torch.uint8 and t.shape[1] % 16 and (pad_all or (tp_size > 1 and split_kind(name) == "cols")):
+                # rows whose byte length is not a multiple of 16 (column shards of Q6_K, narrow models): pad the row pitch so rows
+                # stay TMA-aligned (what the GGUF loader does for column shards too)
                 pitch = (t.shape[1] + 15) // 16 * 16
                 padded = torch.zeros((t.shape[0], pitch), dtype=torch.uint8, device=device)
                 padded[:, : t.shape[1]] = t

@@ -1,7 +1,7 @@
 """tcgen05/TMEM prefill GEMM (csrc/prefill_gemm.cu) against a plain torch reference of the same op.
 
 The weights are F16 (exact in the reference too); activations are F32 split into two F16 terms, so the only error
-left is the F32 accumulation: tolerance 1.5e-5 * max|C| against an F64 matmul for the store / residual GEMMs (K-chunked
+left is the F32 accumulation: tolerance 2.5e-5 * max|C| against an F64 matmul for the store / residual GEMMs (K-chunked
 accumulation), 1e-4 for the SwiGLU-fused one (single accumulator over K) (north_star allows 1e-3)."""
 import numpy as np
 import pytest
@@ -30,9 +30,9 @@ def test_gemm_f16_tc_vs_torch_f64(shape):
     torch.cuda.synchronize()
     ref = A.double() @ W.double().T
     err = (Cm.double() - ref).abs().max().item()
-    # K-chunked accumulation (1024 elements per fresh TMEM accumulator, partial sums added in F32 RN): round 1's single
-    # accumulator measured 4e-5 at K = 14336 (tensor cores truncate once per MMA step); chunked it stays below 1.5e-5
-    assert err <= 1.5e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
+    # K-chunked accumulation (4096 elements per fresh TMEM accumulator, partial sums added in F32 RN): round 1's single
+    # accumulator measured 4e-5 at K = 14336 (tensor cores truncate once per MMA step); chunked it stays below 2.5e-5
+    assert err <= 2.5e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
 
 
 def test_gemm_f16_tc_rejects_unaligned_shapes():

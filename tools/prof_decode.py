@@ -26,8 +26,13 @@ def main():
     ap.add_argument("--tokens", type=int, default=6)
     ap.add_argument("--max-seq", type=int, default=4096)
     ap.add_argument("--big-mix", type=int, default=1, help="use the >=64-layer Q4_K_M recipe (Q5_K attn_v) even with few layers")
+    ap.add_argument("--shard-of", type=int, default=1,
+                    help="g > 1: a single-GPU model with the per-rank shapes of g-way tensor parallelism (heads/g, kv/g, inter/g, vocab/g; hidden "
+                         "unchanged) — what one rank computes per token, without any exchange: the no-communication bound of TP-g")
     args = ap.parse_args()
     os.environ["NT_B200_MEGA_FUSE"] = str(args.fuse)
+    if args.shard_of > 1:
+        os.environ["NT_B200_SYNTH_PAD"] = "1"          # narrow rows padded to a 16-byte pitch, like the real tensor-parallel shards
     import torch
 
     from ntransformer_b200 import model_spec
@@ -36,6 +41,10 @@ def main():
 
     base = {"70b": LLAMA3_70B, "8b": LLAMA3_8B}[args.model]
     cfg = dataclasses.replace(base, n_layers=args.layers, max_seq_len=args.max_seq)
+    if args.shard_of > 1:
+        g = args.shard_of
+        cfg = dataclasses.replace(cfg, n_heads=base.n_heads // g, n_kv_heads=base.n_kv_heads // g, intermediate_size=base.intermediate_size // g,
+                                  vocab_size=-(-base.vocab_size // g))
     m = Model.synthetic(cfg, args.mix, seed=1)
     if args.mega:
         m.use_megakernel(True)
@@ -45,8 +54,19 @@ def main():
         m.forward([(i * 7919 + 5) % cfg.vocab_size], pos + i)
     torch.cuda.synchronize()
     dt = (time.time() - t0) / args.tokens
+    # device-timed steady state (graph replays, no host sync between steps)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.ExternalStream(m.stream)
+    n = 64
+    ev0.record(stream)
+    for i in range(n):
+        m.forward_async([(i * 7919 + 5) % cfg.vocab_size], pos + args.tokens + i)
+    ev1.record(stream)
+    m.sync()
+    ms = ev0.elapsed_time(ev1) / n
     print(json.dumps({"model": args.model, "layers": args.layers, "mix": args.mix, "mega": bool(args.mega and m.megakernel_active),
-                      "ctx": args.ctx, "ms_per_token_wall": round(dt * 1e3, 3)}))
+                      "shard_of": args.shard_of, "ctx": args.ctx, "ms_per_token_wall": round(dt * 1e3, 3), "ms_per_token_device": round(ms, 4),
+                      "us_per_layer": round(ms * 1e3 / args.layers, 2)}))
     m.close()
 
 
