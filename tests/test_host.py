@@ -126,3 +126,59 @@ def test_q4_k_m_mix_and_byte_counts_match_survey():
                 assert all(p == (R, Cc) for p in parts)
             else:
                 assert sum(r for r, _ in parts) == R and all(c == Cc for _, c in parts)
+
+
+def _valid_gguf(tmp_path):
+    from ntransformer_b200.gguf_write import synthetic_tensors_np, write_gguf
+    from ntransformer_b200.model_spec import TINY
+    p = tmp_path / "ok.gguf"
+    write_gguf(p, TINY, synthetic_tensors_np(TINY, "Q4_K_M", seed=2))
+    return p
+
+
+def _describe(path):
+    import ctypes as C
+    from ntransformer_b200._lib import lib
+    buf = C.create_string_buffer(4 << 20)
+    return lib().nt_gguf_describe(str(path).encode(), buf, len(buf))
+
+
+def test_gguf_parser_rejects_malformed_files_instead_of_trusting_them(tmp_path, capfd):
+    """counts, shapes and offsets read from the file are checked against the bytes that are there (the reference's
+    loader.cpp:23-276 trusts them).  Every mutation must make nt_gguf_describe fail cleanly — no crash, no exception escaping the
+    C-ABI — while the untouched file parses."""
+    import struct
+    ok = _valid_gguf(tmp_path)
+    assert _describe(ok) > 0
+    raw = bytearray(ok.read_bytes())
+
+    def variant(name, edit):
+        b = bytearray(raw)
+        edit(b)
+        p = tmp_path / name
+        p.write_bytes(bytes(b))
+        return p
+
+    # header: magic, version, absurd tensor / key counts
+    assert _describe(variant("magic.gguf", lambda b: b.__setitem__(slice(0, 4), b"GGUX"))) <= 0
+    assert _describe(variant("version.gguf", lambda b: b.__setitem__(slice(4, 8), struct.pack("<I", 9)))) <= 0
+    assert _describe(variant("ntensors.gguf", lambda b: b.__setitem__(slice(8, 16), struct.pack("<Q", 1 << 60)))) <= 0
+    assert _describe(variant("nkv.gguf", lambda b: b.__setitem__(slice(16, 24), struct.pack("<Q", 1 << 61)))) <= 0
+    # truncation inside the metadata and inside the tensor data
+    assert _describe(variant("trunc_meta.gguf", lambda b: b.__delitem__(slice(200, len(b))))) <= 0
+    assert _describe(variant("trunc_data.gguf", lambda b: b.__delitem__(slice(len(b) - 4096, len(b))))) <= 0
+    # a string length that runs past the end of the file (first key's length field sits right after the 24-byte header)
+    assert _describe(variant("strlen.gguf", lambda b: b.__setitem__(slice(24, 32), struct.pack("<Q", 1 << 40)))) <= 0
+    # tensor table: find the first tensor record and corrupt its dimension count, a dimension, and its offset
+    name = b"token_embd.weight"
+    at = raw.find(struct.pack("<Q", len(name)) + name)
+    assert at > 0
+    nd_at = at + 8 + len(name)
+    assert _describe(variant("nd0.gguf", lambda b: b.__setitem__(slice(nd_at, nd_at + 4), struct.pack("<I", 0)))) <= 0
+    assert _describe(variant("nd9.gguf", lambda b: b.__setitem__(slice(nd_at, nd_at + 4), struct.pack("<I", 9)))) <= 0
+    assert _describe(variant("dim0.gguf", lambda b: b.__setitem__(slice(nd_at + 4, nd_at + 12), struct.pack("<Q", 0)))) <= 0
+    assert _describe(variant("dimhuge.gguf", lambda b: b.__setitem__(slice(nd_at + 4, nd_at + 12), struct.pack("<Q", 1 << 62)))) <= 0
+    assert _describe(variant("dimodd.gguf", lambda b: b.__setitem__(slice(nd_at + 4, nd_at + 12), struct.pack("<Q", 100)))) <= 0   # not a multiple of the 256-weight block
+    off_at = nd_at + 4 + 16 + 4
+    assert _describe(variant("offset.gguf", lambda b: b.__setitem__(slice(off_at, off_at + 8), struct.pack("<Q", (1 << 64) - 64)))) <= 0
+    capfd.readouterr()
