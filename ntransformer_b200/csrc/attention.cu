@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(AW * 32) decode_fused_kernel(float* __restrict
     NewToken nt;
     nt.k = k_new; nt.v = v_new; nt.pos = pos; nt.theta = theta; nt.freq_scale = freq_scale;
     if (head0 % per_kv == 0) { nt.kc_w = kc; nt.vc_w = vc; }      // one CTA per KV head stores the new row (the split that holds pos)
-    if (used == 1 && !xq_out) {                            // short context: one slice per head group, normalised output, no merge
+    if (used == 1 && !xq_out && tickets) {                 // short context: one slice per head group, normalised output, no merge
         attend_group<DPL, GC>(out + (size_t)head0 * HD, q + (size_t)head0 * HD, kc, vc, kv_head, n_kv, k_begin, k_end, scale, nullptr, nullptr,
                               smem_dyn, nt);
         return;
@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(AW * 32) decode_fused_kernel(float* __restrict
         const int g = threadIdx.x >> 1;
         ml_all[((size_t)(head0 + g) * n_splits + split) * 2 + (threadIdx.x & 1)] = stage[GC * HD + threadIdx.x];
     }
+    if (!tickets) return;                                  // two-launch form: decode_combine_kernel merges (attention_decode_rope_dyn)
     // ---- last arriver of the head group merges the splits ----
     __threadfence();
     __syncthreads();
@@ -552,6 +553,25 @@ void launch_decode_fused(float* out, const float* q, const float* k_new, const f
     count_launch();
 }
 
+// RoPE + KV write folded into the split-context decode kernel, merge as its own small launch (same slices as launch_decode_dyn):
+// two launches instead of rope_kv_decode + decode + combine, without the one-launch form's serial chain or tickets.
+template <int DPL, int GC>
+void launch_decode_rope_dyn(float* out, const float* q, const float* k_new, const float* v_new, __half* kc, __half* vc, const int* pos_dev,
+                            int max_seq, int n_heads, int n_kv, float theta, float freq_scale, float scale, float* scratch, int n_splits,
+                            int8_t* xq_out, cudaStream_t s) {
+    constexpr int HD = DPL * 32;
+    const int groups = n_heads / GC;
+    const int max_split_len = std::max((max_seq + n_splits - 1) / n_splits, DYN_MIN_SPLIT);
+    size_t smem = ((size_t)GC * max_split_len + (size_t)AW * GC * HD + (size_t)GC * HD + 2 * GC) * sizeof(float);
+    NT_CHECK(smem <= (size_t)ATTN_MAX_DYN_SMEM, "attention_decode_rope_dyn: context slice does not fit shared memory");
+    static unsigned long long configured = 0;      // bit per device id
+    opt_in_dynamic_smem(decode_fused_kernel<DPL, GC>, (int)(ATTN_MAX_DYN_SMEM), configured);
+    launch_k(decode_fused_kernel<DPL, GC>, dim3(groups, n_splits), dim3(AW * 32), smem, s, out, q, k_new, v_new, kc, vc, pos_dev, n_heads,
+             n_kv, scale, theta, freq_scale, n_splits, DYN_MIN_SPLIT, scratch, (unsigned*)nullptr, (int8_t*)nullptr);
+    launch_k(decode_combine_kernel, dim3(n_heads), dim3(128), 0, s, out, (const float*)scratch, n_heads, HD, n_splits, 0, 0, pos_dev, xq_out);
+    count_launch(2);
+}
+
 template <int DPL, int GC>
 void launch_prefill(float* out, const float* Q, const __half* kc, const __half* vc, int seq_len, int start_pos, int n_heads,
                     int n_kv, float scale, cudaStream_t s) {
@@ -623,6 +643,17 @@ void attention_decode_fused(float* out, const float* q, const float* k, const fl
     if (xq_out) NT_CHECK((n_heads * hd) % 128 == 0, "attention_decode_fused: n_heads * head_dim must be a multiple of 128 for the fused quantiser");
     NT_DISPATCH_ATTN(launch_decode_fused, out, q, k, v, kh, vh, pos_dev, max_seq, n_heads, n_kv, theta, freq_scale, scale, scratch, n_splits,
                      tickets, static_cast<int8_t*>(xq_out), s);
+}
+
+void attention_decode_rope_dyn(float* out, const float* q, const float* k, const float* v, void* kc, void* vc, const int* pos_dev,
+                               int max_seq, int n_heads, int n_kv, int hd, float theta, float freq_scale, float scale, float* scratch,
+                               void* xq_out, cudaStream_t s) {
+    __half* kh = static_cast<__half*>(kc);
+    __half* vh = static_cast<__half*>(vc);
+    const int n_splits = attention_decode_dyn_splits(max_seq, n_heads, n_kv);
+    if (xq_out) NT_CHECK((n_heads * hd) % 128 == 0, "attention_decode_rope_dyn: n_heads * head_dim must be a multiple of 128 for the fused quantiser");
+    NT_DISPATCH_ATTN(launch_decode_rope_dyn, out, q, k, v, kh, vh, pos_dev, max_seq, n_heads, n_kv, theta, freq_scale, scale, scratch, n_splits,
+                     static_cast<int8_t*>(xq_out), s);
 }
 
 void attention_prefill(float* out, const float* Q, const void* kc, const void* vc, int seq_len, int start_pos, int n_heads,

@@ -513,6 +513,9 @@ void Model::step_body(cudaStream_t s) {
         if (attn1) {
             attention_decode_fused(attn_, q_, k_, v_, kc, vc, pos_dev, max_seq, nh_l_, nkv_l_, hd, cfg_.rope_theta, cfg_.rope_freq_scale, scale,
                                    attn_scratch_, attn_tickets_, o_xq ? xq_a_ : nullptr, s);
+        } else if (fuse_mask_ & 4) {
+            attention_decode_rope_dyn(attn_, q_, k_, v_, kc, vc, pos_dev, max_seq, nh_l_, nkv_l_, hd, cfg_.rope_theta, cfg_.rope_freq_scale, scale,
+                                      attn_scratch_, o_xq ? xq_a_ : nullptr, s);
         } else {
             rope_kv_decode(q_, k_, v_, kc, vc, pos_dev, nh_l_, nkv_l_, hd, cfg_.rope_theta, cfg_.rope_freq_scale, max_seq, s);
             attention_decode_dyn(attn_, q_, kc, vc, pos_dev, max_seq, nh_l_, nkv_l_, hd, scale, attn_scratch_, o_xq ? xq_a_ : nullptr, s);

@@ -130,7 +130,7 @@ private:
     float *act_ = nullptr, *up_ = nullptr, *part_ = nullptr, *logits_ = nullptr, *logits_l_ = nullptr, *attn_scratch_ = nullptr;
     void *xq_h_ = nullptr, *xq_a_ = nullptr, *xq_i_ = nullptr;
     unsigned* attn_tickets_ = nullptr;   // last-arriver tickets of the one-launch attention (zero between launches)
-    int fuse_mask_ = 1;                  // bit 0: norm + quantiser in the GEMV prologues (default), bit 1: one-launch attention (opt-in: measured slower, profiles/r02_*) (NT_B200_FUSE)
+    int fuse_mask_ = 1;                  // bit 0: norm + quantiser in the GEMV prologues (default), bit 1: one-launch attention (opt-in: measured slower, profiles/r02_*), bit 2: RoPE + KV write inside the decode kernel, merge separate (NT_B200_FUSE)
     void *kc_ = nullptr, *vc_ = nullptr;
     int* step_dev_ = nullptr;            // [0] token, [1] position
     int* argmax_dev_ = nullptr;

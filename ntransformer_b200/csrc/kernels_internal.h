@@ -109,6 +109,10 @@ int attention_decode_fused_tickets(int n_heads, int n_kv);
 void attention_decode_fused(float* out, const float* q, const float* k, const float* v, void* kc, void* vc, const int* pos_dev,
                             int max_seq, int n_heads, int n_kv, int hd, float theta, float freq_scale, float scale, float* scratch,
                             unsigned* tickets, void* xq_out, cudaStream_t s);
+// Two-launch form: RoPE + KV-cache write inside the split-context decode kernel (q, k not modified in memory), then the merge kernel.
+void attention_decode_rope_dyn(float* out, const float* q, const float* k, const float* v, void* kc, void* vc, const int* pos_dev,
+                               int max_seq, int n_heads, int n_kv, int hd, float theta, float freq_scale, float scale, float* scratch,
+                               void* xq_out, cudaStream_t s);
 // Fused RoPE (q, k in place; reference rotary.cu:16-62, non-interleaved pairs) + F16 KV-cache write at *pos_dev.
 void rope_kv_decode(float* q, float* k, const float* v, void* kc, void* vc, const int* pos_dev, int n_heads, int n_kv,
                     int hd, float theta, float freq_scale, int max_seq, cudaStream_t s);

@@ -162,6 +162,10 @@ def test_fused_chain_matches_the_unfused_launch_sequence(mix, monkeypatch):
     lb, ib, _, _ = run(0)
     assert ia == ib
     assert max(rel_err(a, b) for a, b in zip(la, lb)) <= 2e-4
+    for mask in (1, 5):                       # the default chain, and RoPE + KV write folded into the decode kernel (two-launch attention)
+        lc, ic, _, _ = run(mask)
+        assert ic == ib
+        assert max(rel_err(a, b) for a, b in zip(lc, lb)) <= 2e-4
     om = O.Model(cfg.dict(), host)
     pos, tok = 0, cfg.bos_token_id
     for i in range(12):
