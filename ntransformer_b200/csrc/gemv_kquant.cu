@@ -497,11 +497,9 @@ bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K) {
     return true;
 }
 
-namespace { const PeerOut* g_peer = nullptr; }      // set around the GEMV_PEER launch by gemv_kq_peer (single host thread, like the reference)
-
 void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpilogue ep, cudaStream_t s) {
     NT_CHECK(gemv_kq_supported(mats, n_mat, K), "gemv_kq: unsupported shape/dtype/alignment");
-    NT_CHECK(ep != GEMV_PEER || (g_peer && n_mat == 1), "gemv_kq: GEMV_PEER goes through gemv_kq_peer");
+    NT_CHECK(ep != GEMV_PEER || (in.peer && n_mat == 1), "gemv_kq: GEMV_PEER needs GemvInput::peer and a single matrix");
     // Opt-in A/B (NT_B200_GEMV_QB=1): the quarter-block kernel (gemv_kquant_q.cu: 16 warps per SM, 14 on the 28672-wide down
     // projection); launches that mix Q6_K with another format are split per matrix for it.  Measured on the 70B shapes
     // (profiles/r02_qb_layer_ncu_summary.txt): correct (all kernel / model tests) but slower — gate+up 62.0 us vs 53.2, Q6_K down
@@ -512,7 +510,7 @@ void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpi
         for (int i = 0; i < n_mat; i++) mask |= 1 << fmt_of(mats[i].dtype);
         const bool one_family = mask == 1 || mask == 2 || mask == 3 || mask == 4 || mask == 8 || mask == 16;
         if (one_family) {
-            if (gemv_kq_quarter(mats, n_mat, K, in, ep, g_peer, s)) return;
+            if (gemv_kq_quarter(mats, n_mat, K, in, ep, in.peer, s)) return;
         } else if (ep != GEMV_SWIGLU && ep != GEMV_PEER && quarter_split_enabled()) {
             // q/k (Q4_K) + v (Q6_K) of a Q4_K_M file: the Q4_K/Q5_K matrices in one launch, each Q6_K matrix in its own
             GemvMat fam[MAX_MATS];
@@ -544,7 +542,7 @@ void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpi
     p.K = K; p.NB = K / 256; p.NC = (p.NB + BS - 1) / BS;
     p.xq = static_cast<const int8_t*>(in.xq);
     p.x_f32 = in.x; p.norm_w = in.norm_w; p.eps = in.eps;
-    if (ep == GEMV_PEER) p.peer = *g_peer;
+    if (ep == GEMV_PEER) p.peer = *in.peer;
     p.epilogue = (int)ep;
     p.n_mat = n_mat;
     int total = 0;
@@ -573,9 +571,9 @@ void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpi
 
 void gemv_kq_peer(const GemvMat& mat, int K, const GemvInput& in, const PeerOut& peer, cudaStream_t s) {
     NT_CHECK(mat.out == peer.hidden && peer.size >= 2 && peer.size <= PeerOut::kMaxTP, "gemv_kq_peer: rows must equal the exchanged vector length");
-    g_peer = &peer;
-    gemv_kq(&mat, 1, K, in, GEMV_PEER, s);
-    g_peer = nullptr;
+    GemvInput ip = in;
+    ip.peer = &peer;
+    gemv_kq(&mat, 1, K, ip, GEMV_PEER, s);
 }
 
 void gemv_kq(const GemvMat* mats, int n_mat, int K, const void* xq, GemvEpilogue ep, cudaStream_t s) {

@@ -32,6 +32,13 @@ struct GemvMat {
 enum GemvEpilogue { GEMV_STORE = 0, GEMV_ADD = 1 /* y += W.x (residual) */, GEMV_SWIGLU = 2 /* y0 = silu(W0.x) * (W1.x) */,
                     GEMV_PEER = 3 /* tensor parallel: rows go to every rank's slot over NVLink (PeerOut), y is not written */ };
 
+
+// Fused K-quant GEMV over up to 3 matrices sharing one activation vector (already in xq form).
+// All matrices must be Q4_K / Q5_K / Q6_K with 16-byte aligned W and row pitch.
+// Where the shared activation vector comes from: either pre-quantised `xq`, or an F32 vector `x` that the
+// kernel quantises in its prologue (staged over the not-yet-primed part of its TMA ring), optionally as
+// RMSNorm(x) * norm_w: the prologue quantises x * norm_w, sums x^2 in the same pass and the scalar
+// rsqrt(mean(x^2) + eps) is applied to the results.
 // Where a tensor-parallel GEMV (o-projection / down-projection shard) delivers its partial rows (engine/peer_xchg.h): the slot
 // [parity][rank][hidden] of every rank.  A slot element is ONE 8-byte word {sequence number : value bits} written with a single
 // 64-bit store (single-copy atomic), so the data is its own arrival flag: no fence, no separate flag hop — the receiver polls
@@ -43,18 +50,12 @@ struct PeerOut {
     unsigned* abort_word;
     int rank, size, hidden;
 };
-
-// Fused K-quant GEMV over up to 3 matrices sharing one activation vector (already in xq form).
-// All matrices must be Q4_K / Q5_K / Q6_K with 16-byte aligned W and row pitch.
-// Where the shared activation vector comes from: either pre-quantised `xq`, or an F32 vector `x` that the
-// kernel quantises in its prologue (staged over the not-yet-primed part of its TMA ring), optionally as
-// RMSNorm(x) * norm_w: the prologue quantises x * norm_w, sums x^2 in the same pass and the scalar
-// rsqrt(mean(x^2) + eps) is applied to the results.
 struct GemvInput {
     const void* xq = nullptr;
     const float* x = nullptr;
     const float* norm_w = nullptr;
     float eps = 0.f;
+    const PeerOut* peer = nullptr;     // epilogue GEMV_PEER only
 };
 bool gemv_kq_supported(const GemvMat* mats, int n_mat, int K);
 void gemv_kq(const GemvMat* mats, int n_mat, int K, const GemvInput& in, GemvEpilogue ep, cudaStream_t s);
