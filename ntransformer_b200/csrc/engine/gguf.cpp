@@ -146,6 +146,10 @@ bool GGUFFile::parse() {
                 if (n > c.left() / 8) { c.ok = false; break; }          // a string takes >= 8 bytes
                 vocab_.tokens.reserve((size_t)n);
                 for (uint64_t j = 0; j < n && c.ok; j++) vocab_.tokens.push_back(c.str());
+            } else if (key == "tokenizer.ggml.merges" && et == T_STR) {
+                if (n > c.left() / 8) { c.ok = false; break; }
+                vocab_.merges.reserve((size_t)n);
+                for (uint64_t j = 0; j < n && c.ok; j++) vocab_.merges.push_back(c.str());
             } else if (key == "tokenizer.ggml.scores" && et == T_F32) {
                 if (n > c.left() / 4) { c.ok = false; break; }
                 vocab_.scores.reserve((size_t)n);

@@ -1,7 +1,7 @@
 // gguf.h — GGUF v2/v3 reader (mmap) for the resident engine.
 // Behaviour mirrors the reference loader (src/model/loader.cpp:23-276, src/model/config.cpp:18-50):
 // scalars are narrowed to int/float, the vocab size is overridden by the token array length, arrays other
-// than tokens/scores/token_type are skipped (so `tokenizer.ggml.merges` is ignored), tensor data starts at
+// than tokens/scores/token_type/merges are skipped (the reference also skips `tokenizer.ggml.merges`; we keep it for the opt-in BPE path), tensor data starts at
 // the header end rounded up to `general.alignment` (default 32).
 #pragma once
 #include <cstdint>
@@ -38,6 +38,7 @@ struct GGUFVocab {
     std::vector<std::string> tokens;
     std::vector<float> scores;
     std::vector<int> token_types;
+    std::vector<std::string> merges;      // "left right" pairs in rank order (tokenizer.ggml.merges); the reference skips this array
 };
 
 class GGUFFile {

@@ -27,6 +27,8 @@ static void usage(const char* prog) {
     fprintf(stderr, "  --device <int>           First CUDA device to use (default: 0)\n");
     fprintf(stderr, "  --tp <int>               Tensor-parallel over this many GPUs (devices device..device+tp-1, one process each,\n"
                     "                           attention heads and FFN columns sharded, partial sums exchanged over NVLink); 1, 2, 4 or 8\n");
+    fprintf(stderr, "  --bpe-merges             Tokenise with the GGUF's rank-ordered BPE merges + literal special tokens (default: the reference's\n"
+                    "                           score-based merging, which ignores tokenizer.ggml.merges)\n");
     fprintf(stderr, "  --host-sampler           Sample (penalty, top-k, top-p) on the host like the reference (default: on the GPU)\n");
     fprintf(stderr, "  --megakernel             Decode each token with one persistent kernel [opt-in]\n");
     fprintf(stderr, "  --benchmark              Run benchmark mode\n");
@@ -60,6 +62,7 @@ int main(int argc, char** argv) {
         else if (a == "--device") { if (auto v = val()) device = std::stoi(v); }
         else if (a == "--gpu-sampler") cfg.gpu_sampler = true;
         else if (a == "--host-sampler") cfg.gpu_sampler = false;
+        else if (a == "--bpe-merges") setenv("NT_B200_BPE_MERGES", "1", 1);
         else if (a == "--megakernel") setenv("NT_B200_MEGAKERNEL", "1", 1);
         else if (a == "--benchmark") bench = true;
         else if (a == "--chat") chat = true;

@@ -1,7 +1,9 @@
 #include "text.h"
 #include <algorithm>
 #include <cmath>
+#include <cctype>
 #include <cstdio>
+#include <cstdlib>
 #include <limits>
 
 namespace nt { namespace b200 {
@@ -36,6 +38,20 @@ void Tokenizer::init(const GGUFVocab& v, int bos_id, int eos_id) {
     ids_.reserve(tokens_.size() * 2);
     for (int i = 0; i < (int)tokens_.size(); i++) ids_[tokens_[i]] = i;       // later duplicates win, like the reference
     gpt2_ = ids_.count(bytemap().enc[0x20]) > 0;
+    merge_rank_.clear();
+    merge_rank_.reserve(v.merges.size() * 2);
+    for (int r = 0; r < (int)v.merges.size(); r++) {
+        const std::string& m = v.merges[(size_t)r];
+        const size_t sp = m.find(' ', 1);                    // the left symbol may itself start with the encoded space, never a raw ' '
+        if (sp == std::string::npos || sp + 1 >= m.size()) continue;
+        merge_rank_.emplace(m.substr(0, sp) + '\x01' + m.substr(sp + 1), r);
+    }
+    specials_.clear();
+    for (int i = 0; i < (int)tokens_.size(); i++)
+        if (i < (int)types_.size() && types_[i] == 3 && tokens_[i].size() >= 3 && tokens_[i].front() == '<' && tokens_[i].back() == '>')
+            specials_.emplace_back(tokens_[i], i);
+    std::sort(specials_.begin(), specials_.end(), [](const auto& a, const auto& b) { return a.first.size() > b.first.size(); });
+    if (const char* e = getenv("NT_B200_BPE_MERGES")) use_merges_ = e[0] && !(e[0] == '0' && e[1] == 0);
     fprintf(stderr, "Tokenizer: %d tokens, BOS=%d, EOS=%d, encoding=%s\n", (int)tokens_.size(), bos_, eos_,
             gpt2_ ? "GPT2-BPE" : "SentencePiece");
 }
@@ -52,6 +68,7 @@ std::vector<int> Tokenizer::encode(const std::string& text, bool add_bos) const 
     std::vector<int> out;
     if (add_bos) out.push_back(bos_);
     if (text.empty()) return out;
+    if (merges_active()) { encode_merges(text, out); return out; }
     std::string enc;
     if (gpt2_) { for (unsigned char c : text) enc += bytemap().enc[c]; }
     else { for (char c : text) { if (c == ' ') enc += "\xe2\x96\x81"; else enc += c; } }
@@ -88,6 +105,98 @@ std::vector<int> Tokenizer::encode(const std::string& text, bool add_bos) const 
     }
     for (const Sym& s : syms) if (s.id >= 0) out.push_back(s.id);
     return out;
+}
+
+// ---- opt-in: rank-ordered byte-level BPE (tokenizer.ggml.merges) ----------------------------------------------------------------
+namespace {
+bool is_letter(unsigned char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c >= 0x80; }   // non-ASCII bytes count as letters
+bool is_digit(unsigned char c) { return c >= '0' && c <= '9'; }
+bool is_space(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; }
+bool is_newline(unsigned char c) { return c == '\n' || c == '\r'; }
+
+// Llama-3 pre-tokeniser, byte classes in place of \p{L} / \p{N}:
+//   (?i:'s|'t|'re|'ve|'m|'ll|'d) | [^\r\n L N]? L+ | N{1,3} | ' '? [^\s L N]+ [\r\n]* | \s* [\r\n]+ | \s+ (?!\S) | \s+
+size_t next_piece(const std::string& t, size_t i) {
+    const size_t n = t.size();
+    auto at = [&](size_t k) -> unsigned char { return k < n ? (unsigned char)t[k] : 0; };
+    if (t[i] == '\'' && i + 1 < n) {                                   // contractions
+        const char a = (char)std::tolower(at(i + 1)), b = (char)std::tolower(at(i + 2));
+        if (a == 's' || a == 't' || a == 'm' || a == 'd') return i + 2;
+        if ((a == 'r' && b == 'e') || (a == 'v' && b == 'e') || (a == 'l' && b == 'l')) return i + 3;
+    }
+    {                                                                    // [^\r\n L N]? L+
+        size_t j = i;
+        if (!is_newline(at(j)) && !is_letter(at(j)) && !is_digit(at(j)) && j + 1 < n && is_letter(at(j + 1))) j++;
+        if (j < n && is_letter(at(j))) { while (j < n && is_letter(at(j))) j++; return j; }
+    }
+    if (is_digit(at(i))) { size_t j = i; while (j < n && j < i + 3 && is_digit(at(j))) j++; return j; }
+    {                                                                    // ' '? [^\s L N]+ [\r\n]*
+        size_t j = i;
+        if (at(j) == ' ') j++;
+        if (j < n && !is_space(at(j)) && !is_letter(at(j)) && !is_digit(at(j))) {
+            while (j < n && !is_space(at(j)) && !is_letter(at(j)) && !is_digit(at(j))) j++;
+            while (j < n && is_newline(at(j))) j++;
+            return j;
+        }
+    }
+    if (is_space(at(i))) {
+        size_t j = i, last_nl = 0;
+        while (j < n && is_space(at(j))) { if (is_newline(at(j))) last_nl = j + 1; j++; }
+        if (last_nl) return last_nl;                                     // \s* [\r\n]+
+        if (j < n && j - i > 1) return j - 1;                            // \s+ (?!\S): leave the last space to the next word
+        return j;
+    }
+    return i + 1;
+}
+}  // namespace
+
+// One pre-token: its bytes as byte-level symbols, then the adjacent pair of lowest rank is merged until none is left.
+void Tokenizer::bpe_word(const std::string& word, std::vector<int>& out) const {
+    std::vector<std::string> sym;
+    sym.reserve(word.size());
+    for (unsigned char c : word) sym.push_back(bytemap().enc[c]);
+    while (sym.size() > 1) {
+        int best = -1, best_rank = std::numeric_limits<int>::max();
+        for (int i = 0; i + 1 < (int)sym.size(); i++) {
+            auto it = merge_rank_.find(sym[(size_t)i] + '\x01' + sym[(size_t)i + 1]);
+            if (it != merge_rank_.end() && it->second < best_rank) { best_rank = it->second; best = i; }
+        }
+        if (best < 0) break;
+        sym[(size_t)best] += sym[(size_t)best + 1];
+        sym.erase(sym.begin() + best + 1);
+    }
+    for (const std::string& s : sym) {
+        auto it = ids_.find(s);
+        if (it != ids_.end()) { out.push_back(it->second); continue; }
+        // a merged symbol that is not in the vocabulary (inconsistent merges): fall back to its bytes
+        for (size_t pos = 0; pos < s.size();) {
+            int n = utf8_len((uint8_t)s[pos]);
+            if (!n || pos + n > s.size()) n = 1;
+            auto d = bytemap().dec.find(s.substr(pos, (size_t)n));
+            out.push_back(byte_token(d != bytemap().dec.end() ? d->second : (uint8_t)s[pos]));
+            pos += (size_t)n;
+        }
+    }
+}
+
+void Tokenizer::encode_merges(const std::string& text, std::vector<int>& out) const {
+    size_t i = 0, run = 0;                                   // [run, i) = ordinary text not yet tokenised
+    auto flush = [&](size_t end) {
+        const std::string part = text.substr(run, end - run);
+        for (size_t p = 0; p < part.size();) { const size_t q = next_piece(part, p); bpe_word(part.substr(p, q - p), out); p = q; }
+    };
+    while (i < text.size()) {
+        int hit = -1;
+        if (text[i] == '<')
+            for (int k = 0; k < (int)specials_.size(); k++)
+                if (text.compare(i, specials_[(size_t)k].first.size(), specials_[(size_t)k].first) == 0) { hit = k; break; }
+        if (hit < 0) { i++; continue; }
+        flush(i);
+        out.push_back(specials_[(size_t)hit].second);
+        i += specials_[(size_t)hit].first.size();
+        run = i;
+    }
+    flush(text.size());
 }
 
 std::string Tokenizer::decode_token(int id) const {

@@ -23,8 +23,18 @@ public:
     int eos_id() const { return eos_; }
     int vocab_size() const { return (int)tokens_.size(); }
     bool gpt2() const { return gpt2_; }
+    // Opt-in (CLI --bpe-merges, NT_B200_BPE_MERGES=1): rank-ordered byte-level BPE over tokenizer.ggml.merges with a Llama-3 style
+    // pre-tokeniser and literal special tokens — what llama.cpp does for this vocabulary family.  Off by default because the
+    // reference ignores the merges (loader.cpp skips the array, tokenizer.cpp:101-217 merges by score) and parity is against it.
+    void set_use_merges(bool on) { use_merges_ = on; }
+    bool merges_active() const { return use_merges_ && gpt2_ && !merge_rank_.empty(); }
 private:
     int byte_token(uint8_t b) const;
+    void encode_merges(const std::string& text, std::vector<int>& out) const;
+    void bpe_word(const std::string& word, std::vector<int>& out) const;
+    std::unordered_map<std::string, int> merge_rank_;     // "left\x01right" -> rank
+    std::vector<std::pair<std::string, int>> specials_;   // control tokens that may appear literally in text, longest first
+    bool use_merges_ = false;
     std::vector<std::string> tokens_;
     std::vector<float> scores_;
     std::vector<int> types_;

@@ -33,11 +33,12 @@ def gpt2_byte_tokens():
     return out
 
 
-def write_gguf(path, cfg: LlamaConfig, tensors: dict, vocab_tokens=None, name="synthetic", vocab_scores=None, vocab_types=None):
+def write_gguf(path, cfg: LlamaConfig, tensors: dict, vocab_tokens=None, name="synthetic", vocab_scores=None, vocab_types=None,
+               merges=None):
     """tensors: name -> (np.ndarray bytes/f32, DType, rows, cols) in GGUF block layout."""
     table = [(n, dt, r, c) for n, (a, dt, r, c) in tensors.items()]
     write_gguf_streaming(path, cfg, ((n, a, dt, r, c) for n, (a, dt, r, c) in tensors.items()), table, vocab_tokens, name,
-                         vocab_scores, vocab_types)
+                         vocab_scores, vocab_types, merges)
 
 
 def _tensor_nbytes(dt, rows, cols):
@@ -46,7 +47,7 @@ def _tensor_nbytes(dt, rows, cols):
 
 
 def write_gguf_streaming(path, cfg: LlamaConfig, gen, table=None, vocab_tokens=None, name="synthetic", vocab_scores=None,
-                         vocab_types=None):
+                         vocab_types=None, merges=None):
     """Like write_gguf but `gen` yields (name, array, DType, rows, cols) one tensor at a time, in the order of
     `table` ([(name, DType, rows, cols)], default tensor_table(cfg-independent order of gen is NOT allowed))."""
     if table is None:
@@ -82,6 +83,8 @@ def write_gguf_streaming(path, cfg: LlamaConfig, gen, table=None, vocab_tokens=N
     types = np.ones(len(vocab_tokens), dtype=np.int32) if vocab_types is None else np.asarray(vocab_types, dtype=np.int32)
     assert len(types) == len(vocab_tokens)
     kv.append(_s("tokenizer.ggml.token_type") + struct.pack("<IIQ", _T_ARR, _T_I32, len(types)) + types.tobytes())
+    if merges:              # "left right" in rank order, as llama.cpp writes them (the reference skips this array)
+        kv.append(_s("tokenizer.ggml.merges") + struct.pack("<IIQ", _T_ARR, _T_STR, len(merges)) + b"".join(_s(m) for m in merges))
 
     infos, offset, offsets = [], 0, {}
     for tname, dt, rows, cols in table:
