@@ -146,7 +146,12 @@ __device__ void mega_barrier(const MegaParams& P, int kind, SyncState& st) {
         if (xchg) { __threadfence_system(); red_relaxed_gpu_add(counter, 1u); }
         else red_release_gpu_add(counter, 1u);
         if (xchg && P.xchg_direct) {
-            // Experiment: no master hop.  Every CTA adds 1 to every rank's arrival counter (remote atomics over NVLink, posted) and
+            // Experiment (off by default; KNOWN GAP): with tp_size >= 3 a rank that has already passed exchange n can post
+            // its exchange-(n+1) arrivals into a slower rank's counter while another rank's exchange-n arrival is still in flight
+            // (relaxed reds to different destinations are unordered), so the counter can reach n * tp * grid early.  Needs one
+            // counter per exchange parity (or per source rank) before it may be used; the stand-alone exchange of
+            // engine/peer_xchg.cu avoids the issue altogether by making every value its own flag.
+            // No master hop.  Every CTA adds 1 to every rank's arrival counter (remote atomics over NVLink, posted) and
             // waits until its own rank's counter has seen all tp_size * grid CTAs of this exchange.  The counter is never reset:
             // the target grows with the exchange sequence number (a peer can be at most one exchange ahead).
             for (int r = 0; r < P.tp_size; r++) red_relaxed_sys_add(P.flags[r] + 32 * P.tp_size, 1u);
